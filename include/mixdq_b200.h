@@ -1,0 +1,165 @@
+/*
+ * mixdq_b200.h — C ABI of the B200-native (sm_100a) MixDQ quantized-UNet hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types. Every entry point
+ *   - enqueues work on the caller's stream and returns immediately (no allocation, no sync,
+ *     CUDA-graph capturable) — the conventions of the reference extension, which launches on
+ *     at::cuda::getCurrentCUDAStream() (reference kernels/mixdq_extension/csrc/quant_dequant/
+ *     quantize_kernel.cu:40, qlinear/cutlassGemm_withBias_optimalAlignment.cu:208);
+ *   - returns 0 on success or a negative MIXDQ_ERR_* code (see mixdq_strerror);
+ *   - takes DEVICE pointers unless the parameter is documented as host.
+ *
+ * Each function cites the reference interface it replaces (paths relative to the reference
+ * repository root, thu-nics/MixDQ @ 4f6b32ad).
+ */
+#ifndef MIXDQ_B200_H_
+#define MIXDQ_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIXDQ_ABI_VERSION 1
+
+/* error codes */
+#define MIXDQ_OK                 0
+#define MIXDQ_ERR_INVALID_ARG   -1   /* null pointer / non-positive size                      */
+#define MIXDQ_ERR_ALIGNMENT     -2   /* reference: "Int8 kernel with input or output alignment
+                                        not to 4 is not supported." (qlinear.cc:130-133)      */
+#define MIXDQ_ERR_UNSUPPORTED   -3   /* e.g. dilation != 1 (op/qconv2d.py:120-123)            */
+#define MIXDQ_ERR_CUDA          -4   /* a CUDA runtime/driver call failed (launch, tensor map) */
+#define MIXDQ_ERR_WORKSPACE     -5   /* workspace too small                                    */
+
+typedef void* mixdq_stream_t;      /* a cudaStream_t */
+typedef uint16_t mixdq_half_t;     /* IEEE binary16 bit pattern (__half)  */
+
+int         mixdq_abi_version(void);
+const char* mixdq_strerror(int code);
+/* Name of the kernel family the last call on this thread dispatched to ("tcgen05", "simt", ...).
+   Test/diagnostic aid only. */
+const char* mixdq_last_path(void);
+/* Force every GEMM/conv onto the portable SIMT kernels (1) or restore heuristics (0). Test aid:
+   lets the tcgen05 path be cross-checked against an independent implementation on the device. */
+void        mixdq_force_simt(int on);
+
+/* ------------------------------------------------------------------------------------------
+ * A1  static per-tensor activation quantisation, fp16 -> int8
+ *     q = (int8) clamp(lrintf(fmaf(x, *scale_inv, *zp)), -128, 127)
+ * replaces  quantize_per_tensor_to_int8 / quantize_per_tensor_to_int8_vectorized
+ *           (csrc/quant_dequant/quantize.cc:9-53; kernels quantize_kernel.cu:10-27,
+ *            quantize_kernel_vectorized.cu:29-72).  scale_inv / zp are fp32 device scalars
+ *            (zp already shifted by -128, nn/utils.py:428).
+ * The strided form reads a 3-D view [d0][d1][cols] whose innermost dimension is contiguous
+ * (element strides s0, s1) and writes a dense [d0*d1][cols] int8 array with row pitch
+ * `out_pitch` elements (>= cols). It covers channel slices of NHWC tensors (split shortcuts,
+ * nn/Conv2d.py:313-318) and the BOS token slice x[:,1:,:] (nn/Linear.py:180).
+ * ---------------------------------------------------------------------------------------- */
+int mixdq_quant_i8_static(const mixdq_half_t* x, int64_t numel,
+                          const float* scale_inv, const float* zp,
+                          int8_t* q, mixdq_stream_t stream);
+
+int mixdq_quant_i8_static_strided(const mixdq_half_t* x, int64_t d0, int64_t d1, int64_t cols,
+                                  int64_t s0, int64_t s1,
+                                  const float* scale_inv, const float* zp,
+                                  int8_t* q, int64_t out_pitch, mixdq_stream_t stream);
+
+/* A1 + the int8 NCHW -> NHWC copy of qconv2d.cc:91-92 fused: reads fp16 logical [N][C][H][W]
+ * with arbitrary element strides `xstride[4]` (host array), takes channels [c_begin, c_end),
+ * writes dense int8 NHWC [N][H][W][c_end-c_begin]. */
+int mixdq_quant_i8_nchw2nhwc(const mixdq_half_t* x, int N, int C, int H, int W,
+                             const int64_t xstride[4], int c_begin, int c_end,
+                             const float* scale_inv, const float* zp,
+                             int8_t* q_nhwc, mixdq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A10 dynamic per-tensor activation quantisation (qdiff min-max, asymmetric, 8 bit)
+ *     x_min = min(min(x),0), x_max = max(max(x),0), delta = max((x_max-x_min)/255, 1e-6)
+ *     z = rint(-x_min/delta); q = clamp(rint(x/delta) + z, 0, 255) - 128
+ * restates  BaseQuantizer.init_quant_params / forward
+ *           (quant_utils/qdiff/quantizer/base_quantizer.py:155-190, 122-128) in fp32.
+ * Outputs: q int8 (dense, same element order as x), *scale_out = delta,
+ *          *zp_out = z - 128 (the "kernel format" zero point of nn/utils.py:428).
+ * `ws` is a device workspace of at least mixdq_quant_dynamic_ws_bytes() bytes that must be
+ * zero-initialised ONCE by the caller; the kernels leave it zeroed again on exit.
+ * ---------------------------------------------------------------------------------------- */
+int64_t mixdq_quant_dynamic_ws_bytes(void);
+int mixdq_quant_i8_dynamic(const mixdq_half_t* x, int64_t numel,
+                           float* scale_out, float* zp_out, int8_t* q,
+                           void* ws, mixdq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A2  W8A8 linear:  D[m,n] = half( (float(sum_k A[m,k]*W[n,k]) - bias0[n]) * scale[n]
+ *                                  (+ float(bias[n])) )     each step one fp32 RN operation
+ * replaces  qlinear_w8_a8_ohalf (csrc/qlinear/qlinear.cc:14-137) and the four CUTLASS
+ *           instantiations cutlassGemm_{withBias,noBias}_{optimal,small}Alignment.cu
+ *           (epilogue order: cutlassGemm_withBias_optimalAlignment.cu:39-95).
+ * A int8 [M][K] row pitch lda; W int8 [N][K] dense; D fp16 [M][N] row pitch ldd.
+ * K % 4 == 0 and N % 4 == 0 required (MIXDQ_ERR_ALIGNMENT otherwise, as the reference).
+ * `acc_out` (nullable, int32 [M][N] dense) additionally receives the raw INT32 accumulators —
+ * test hook for the bit-exact parity check; production callers pass NULL.
+ * ---------------------------------------------------------------------------------------- */
+int mixdq_gemm_w8a8_f16(const int8_t* A, int64_t lda, const int8_t* W,
+                        const float* bias0, const float* scale, const mixdq_half_t* bias,
+                        mixdq_half_t* D, int64_t ldd, int M, int N, int K,
+                        int32_t* acc_out, mixdq_stream_t stream);
+
+/* Dynamic-scale variant: the epilogue forms scale[n] = w_scale[n] * (*a_scale) and
+ * bias0[n] = wsum[n] * (*a_zp) itself from the device scalars a dynamic quantise call produced
+ * (the arguments the reference signature carries but never reads, qlinear.cc:25-73). */
+int mixdq_gemm_w8a8_f16_dyn(const int8_t* A, int64_t lda, const int8_t* W,
+                            const float* w_scale, const float* wsum,
+                            const float* a_scale, const float* a_zp, const mixdq_half_t* bias,
+                            mixdq_half_t* D, int64_t ldd, int M, int N, int K,
+                            int32_t* acc_out, mixdq_stream_t stream);
+
+/* W4A8 (north star; no kernel in the reference): W_packed uint8 [N][K/2], two signed 4-bit
+ * two's-complement codes per byte, EVEN k in the HIGH nibble (nibble order of
+ * nn/utils.py:26-28). Same epilogue as A2. K % 32 == 0 required. */
+int mixdq_gemm_w4a8_f16(const int8_t* A, int64_t lda, const uint8_t* W_packed,
+                        const float* bias0, const float* scale, const mixdq_half_t* bias,
+                        mixdq_half_t* D, int64_t ldd, int M, int N, int K,
+                        int32_t* acc_out, mixdq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A3 + A4  W8A8 conv2d fprop, NHWC, cross-correlation, dilation 1, square stride/padding,
+ *          with the activation zero-point propagation folded into the epilogue:
+ *   y[n,p,q,k] = half( (float(acc) - zpw) * scale[k] (+ float(bias[k])) )
+ *   zpw = (pad>0) ? float(sum_{(r,s) in bounds} wsum_krs[k,r,s]) * (*zp) : bias0_k[k]
+ * replaces  qconv2d_w8_a8_ohalf (csrc/qconv2d/qconv2d.cc:28-206), the eight CUTLASS conv
+ *           instantiations (cutlassConv2d_*.cu) and activation_zero_point_propagate
+ *           (conv_act_zero_point_propagate.cu:10-83) — the fp32 [N,P,Q,K] correction tensor is
+ *           never materialised.
+ * x int8 NHWC [N][H][W][C] with pixel pitch `x_cpitch` elements (>= C; lets a channel slice of
+ * a wider NHWC tensor be consumed in place); w int8 KRSC [K][R][S][C] dense; y fp16 NHWC
+ * [N][P][Q][K] dense. C % 4 == 0 and K % 4 == 0 required.
+ * wsum_krs fp32 [K][R][S] is required iff pad > 0, bias0_k fp32 [K] iff pad == 0
+ * (qconv2d.cc:117-124).
+ * ---------------------------------------------------------------------------------------- */
+int mixdq_conv_w8a8_f16(const int8_t* x_nhwc, int64_t x_cpitch, const int8_t* w_krsc,
+                        const float* scale, const float* wsum_krs, const float* bias0_k,
+                        const float* zp, const mixdq_half_t* bias, mixdq_half_t* y_nhwc,
+                        int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
+                        int32_t* acc_out, mixdq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A6  split 1x1 shortcut convolution (the nine up-block conv_shortcut layers): the two channel
+ * halves carry independent activation (scale, zp) and weight scales; the reference runs two
+ * convs and adds their fp16 results (nn/Conv2d.py:312-347). Fused here as
+ *   y = half( half_rn(t0) + half_rn(t1) )  with  t0 = (acc0-bias0_a[k])*scale_a[k] + bias[k],
+ *                                                t1 = (acc1-bias0_b[k])*scale_b[k]
+ * i.e. exactly the reference's two fp16 roundings followed by an fp16 add, in one kernel with
+ * two accumulators. xa/xb are int8 [M][Ca] / [M][Cb] with row pitches lda/ldb.
+ * ---------------------------------------------------------------------------------------- */
+int mixdq_conv1x1_split_w8a8_f16(const int8_t* xa, int64_t lda, const int8_t* wa, int Ca,
+                                 const float* bias0_a, const float* scale_a,
+                                 const int8_t* xb, int64_t ldb, const int8_t* wb, int Cb,
+                                 const float* bias0_b, const float* scale_b,
+                                 const mixdq_half_t* bias, mixdq_half_t* y, int64_t ldy,
+                                 int M, int K, mixdq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIXDQ_B200_H_ */

@@ -1,0 +1,106 @@
+"""ctypes binding of the C-ABI library (include/mixdq_b200.h).
+
+There is no CPU fallback: if the library cannot be loaded the ops raise. Loading never
+triggers a build implicitly on a machine without nvcc — `__graft_entry__.build()` (or
+`python -m mixdq_b200.build`) produces the .so in-tree.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_int, c_int32, c_int64, c_void_p, POINTER
+from pathlib import Path
+
+_LIB = None
+LIB_PATH = Path(__file__).resolve().parent / "libmixdq_b200.so"
+
+# every symbol include/mixdq_b200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "mixdq_abi_version", "mixdq_strerror", "mixdq_last_path", "mixdq_force_simt",
+    "mixdq_quant_i8_static", "mixdq_quant_i8_static_strided", "mixdq_quant_i8_nchw2nhwc",
+    "mixdq_quant_dynamic_ws_bytes", "mixdq_quant_i8_dynamic",
+    "mixdq_gemm_w8a8_f16", "mixdq_gemm_w8a8_f16_dyn", "mixdq_gemm_w4a8_f16",
+    "mixdq_conv_w8a8_f16", "mixdq_conv1x1_split_w8a8_f16",
+]
+
+
+class MixdqLibraryError(RuntimeError):
+    pass
+
+
+def _declare(lib: ctypes.CDLL) -> None:
+    P = c_void_p
+    lib.mixdq_abi_version.restype = c_int
+    lib.mixdq_abi_version.argtypes = []
+    lib.mixdq_strerror.restype = c_char_p
+    lib.mixdq_strerror.argtypes = [c_int]
+    lib.mixdq_last_path.restype = c_char_p
+    lib.mixdq_last_path.argtypes = []
+    lib.mixdq_force_simt.restype = None
+    lib.mixdq_force_simt.argtypes = [c_int]
+
+    lib.mixdq_quant_i8_static.restype = c_int
+    lib.mixdq_quant_i8_static.argtypes = [P, c_int64, P, P, P, P]
+    lib.mixdq_quant_i8_static_strided.restype = c_int
+    lib.mixdq_quant_i8_static_strided.argtypes = [P, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                                  P, P, P, c_int64, P]
+    lib.mixdq_quant_i8_nchw2nhwc.restype = c_int
+    lib.mixdq_quant_i8_nchw2nhwc.argtypes = [P, c_int, c_int, c_int, c_int, POINTER(c_int64),
+                                             c_int, c_int, P, P, P, P]
+    lib.mixdq_quant_dynamic_ws_bytes.restype = c_int64
+    lib.mixdq_quant_dynamic_ws_bytes.argtypes = []
+    lib.mixdq_quant_i8_dynamic.restype = c_int
+    lib.mixdq_quant_i8_dynamic.argtypes = [P, c_int64, P, P, P, P, P]
+
+    lib.mixdq_gemm_w8a8_f16.restype = c_int
+    lib.mixdq_gemm_w8a8_f16.argtypes = [P, c_int64, P, P, P, P, P, c_int64, c_int, c_int, c_int,
+                                        P, P]
+    lib.mixdq_gemm_w8a8_f16_dyn.restype = c_int
+    lib.mixdq_gemm_w8a8_f16_dyn.argtypes = [P, c_int64, P, P, P, P, P, P, P, c_int64, c_int,
+                                            c_int, c_int, P, P]
+    lib.mixdq_gemm_w4a8_f16.restype = c_int
+    lib.mixdq_gemm_w4a8_f16.argtypes = [P, c_int64, P, P, P, P, P, c_int64, c_int, c_int, c_int,
+                                        P, P]
+    lib.mixdq_conv_w8a8_f16.restype = c_int
+    lib.mixdq_conv_w8a8_f16.argtypes = [P, c_int64, P, P, P, P, P, P, P,
+                                        c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_int, P, P]
+    lib.mixdq_conv1x1_split_w8a8_f16.restype = c_int
+    lib.mixdq_conv1x1_split_w8a8_f16.argtypes = [P, c_int64, P, c_int, P, P,
+                                                 P, c_int64, P, c_int, P, P,
+                                                 P, P, c_int64, c_int, c_int, P]
+
+
+def load() -> ctypes.CDLL:
+    """Load libmixdq_b200.so (once). Raises MixdqLibraryError if it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = Path(os.environ.get("MIXDQ_B200_LIB", LIB_PATH))
+    if not path.exists():
+        raise MixdqLibraryError(
+            f"{path} not found: the CUDA extension is not built. Run "
+            "`python -m mixdq_b200.build` (needs nvcc). There is no CPU fallback.")
+    try:
+        lib = ctypes.CDLL(str(path))
+    except OSError as e:  # pragma: no cover - depends on the machine
+        raise MixdqLibraryError(f"cannot load {path}: {e}") from e
+    for sym in ABI_SYMBOLS:
+        if not hasattr(lib, sym):
+            raise MixdqLibraryError(f"{path} does not export {sym}")
+    _declare(lib)
+    if lib.mixdq_abi_version() != 1:
+        raise MixdqLibraryError("ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+def check(code: int) -> None:
+    """Turn a non-zero status into the RuntimeError the reference's TORCH_CHECK would raise."""
+    if code != 0:
+        msg = load().mixdq_strerror(code).decode()
+        raise RuntimeError(msg)
+
+
+def last_path() -> str:
+    return load().mixdq_last_path().decode()

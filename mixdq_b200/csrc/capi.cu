@@ -1,0 +1,338 @@
+// capi.cu — extern "C" entry points of the contraction kernels: argument validation, TMA tensor-map
+// construction, tile-shape heuristic, launch. Declared in include/mixdq_b200.h.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/mixdq_b200.h"
+#include "simt.h"
+#include "tc_kernel.cuh"
+
+using namespace mixdq;
+
+// ------------------------------------------------------------------------------------------
+// misc state
+// ------------------------------------------------------------------------------------------
+static thread_local const char* g_last_path = "none";
+static int g_force_simt = 0;
+
+extern "C" int mixdq_abi_version(void) { return MIXDQ_ABI_VERSION; }
+extern "C" const char* mixdq_last_path(void) { return g_last_path; }
+extern "C" void mixdq_force_simt(int on) { g_force_simt = on; }
+
+extern "C" const char* mixdq_strerror(int code) {
+  switch (code) {
+    case MIXDQ_OK: return "success";
+    case MIXDQ_ERR_INVALID_ARG: return "invalid argument (null pointer or non-positive size)";
+    case MIXDQ_ERR_ALIGNMENT:
+      return "Int8 kernel with input or output alignment not to 4 is not supported.";
+    case MIXDQ_ERR_UNSUPPORTED: return "unsupported configuration";
+    case MIXDQ_ERR_CUDA: return "CUDA kernel failed";
+    case MIXDQ_ERR_WORKSPACE: return "workspace too small";
+    default: return "unknown error";
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA tensor maps (driver entry point fetched at run time: no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// rank-R uint8 tensor, dims/box innermost first, strides in bytes for dims 1..R-1.
+static bool make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides, const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, static_cast<cuuint32_t>(rank),
+                   const_cast<void*>(base), reinterpret_cast<const cuuint64_t*>(dims),
+                   reinterpret_cast<const cuuint64_t*>(strides),
+                   reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static bool make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows,
+                         uint64_t pitch_bytes, uint32_t box_rows) {
+  uint64_t dims[2] = {cols, rows};
+  uint64_t strides[1] = {pitch_bytes};
+  uint32_t box[2] = {BLOCK_K, box_rows};
+  return make_tmap(m, base, 2, dims, strides, box);
+}
+
+// ------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------
+template <int BN, int STAGES, int KIND>
+static int launch_tc(dim3 grid, const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a1,
+                     const CUtensorMap& w1, const TcParams& p, cudaStream_t st) {
+  using L = TcSmem<BN, STAGES, KIND>;
+  static bool attr_set = false;
+  auto kern = tc_i8_kernel<BN, STAGES, KIND>;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) !=
+        cudaSuccess)
+      return MIXDQ_ERR_CUDA;
+    attr_set = true;
+  }
+  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(a, w, a1, w1, p);
+  return cudaGetLastError() == cudaSuccess ? MIXDQ_OK : MIXDQ_ERR_CUDA;
+}
+
+// Tile-width heuristic: the widest BN that still yields at least ~one CTA per SM; B=1 shapes
+// (M = 256) are weight-bandwidth bound and need many narrow tiles in flight, B>=8 shapes are
+// tensor bound and take 128 x 256.
+static int pick_bn(int m_tiles, int N) {
+  static int env_bn = -1;
+  if (env_bn < 0) {
+    const char* e = getenv("MIXDQ_FORCE_BN");
+    env_bn = e ? atoi(e) : 0;
+  }
+  if (env_bn == 16 || env_bn == 32 || env_bn == 64 || env_bn == 128 || env_bn == 256) return env_bn;
+  const int cands[5] = {256, 128, 64, 32, 16};
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cands[i];
+    if (bn > 16 && bn / 2 >= N) continue;  // do not pick a tile twice as wide as the problem
+    const long ctas = static_cast<long>(m_tiles) * ((N + bn - 1) / bn);
+    if (ctas >= 132) return bn;
+  }
+  return (N >= 32) ? 32 : 16;
+}
+
+template <int KIND>
+static int dispatch_tc(int bn, dim3 grid, const CUtensorMap& a, const CUtensorMap& w,
+                       const CUtensorMap& a1, const CUtensorMap& w1, const TcParams& p,
+                       cudaStream_t st) {
+  switch (bn) {
+    case 256: return launch_tc<256, 4, KIND>(grid, a, w, a1, w1, p, st);
+    case 128: return launch_tc<128, 6, KIND>(grid, a, w, a1, w1, p, st);
+    case 64: return launch_tc<64, 8, KIND>(grid, a, w, a1, w1, p, st);
+    case 32: return launch_tc<32, 8, KIND>(grid, a, w, a1, w1, p, st);
+    case 16: return launch_tc<16, 8, KIND>(grid, a, w, a1, w1, p, st);
+    default: return MIXDQ_ERR_UNSUPPORTED;
+  }
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ------------------------------------------------------------------------------------------
+// GEMM (A2)
+// ------------------------------------------------------------------------------------------
+static int gemm_common(const int8_t* A, int64_t lda, const int8_t* W, const float* p_scale,
+                       const float* p_bias0, const float* a_scale, const float* a_zp,
+                       const mixdq_half_t* bias, mixdq_half_t* D, int64_t ldd, int M, int N, int K,
+                       int32_t* acc_out, cudaStream_t st) {
+  if (M < 0 || N <= 0 || K <= 0 || !W || !p_scale || !p_bias0) return MIXDQ_ERR_INVALID_ARG;
+  if (M == 0) return MIXDQ_OK;
+  if (!A || !D || lda < K || ldd < N) return MIXDQ_ERR_INVALID_ARG;
+  if ((K & 3) || (N & 3)) return MIXDQ_ERR_ALIGNMENT;
+
+  const bool tc_ok = !g_force_simt && (K % 16 == 0) && (N % 8 == 0) && (lda % 16 == 0) &&
+                     (ldd % 8 == 0) && al16(A) && al16(W) && al16(D) &&
+                     (!acc_out || al16(acc_out));
+  if (!tc_ok) {
+    SimtGemmArgs g{};
+    g.A = A; g.lda = lda; g.W = W; g.K = K;
+    g.scale = p_scale; g.bias0 = p_bias0; g.a_scale = a_scale; g.a_zp = a_zp;
+    g.bias = reinterpret_cast<const __half*>(bias);
+    g.D = reinterpret_cast<__half*>(D); g.ldd = ldd; g.M = M; g.N = N; g.acc_out = acc_out;
+    g_last_path = "simt";
+    return simt_gemm_launch(g, st) == 0 ? MIXDQ_OK : MIXDQ_ERR_CUDA;
+  }
+
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const int bn = pick_bn(m_tiles, N);
+  CUtensorMap tmA, tmW;
+  if (!make_tmap_2d(&tmA, A, K, M, lda, BLOCK_M)) return MIXDQ_ERR_CUDA;
+  if (!make_tmap_2d(&tmW, W, K, N, K, bn)) return MIXDQ_ERR_CUDA;
+  TcParams p{};
+  p.M = M; p.N = N; p.num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  p.scale = p_scale; p.bias0 = p_bias0; p.a_scale = a_scale; p.a_zp = a_zp;
+  p.bias = reinterpret_cast<const __half*>(bias);
+  p.D = reinterpret_cast<__half*>(D); p.ldd = ldd; p.acc_out = acc_out;
+  dim3 grid(m_tiles, (N + bn - 1) / bn);
+  g_last_path = "tcgen05";
+  return dispatch_tc<KIND_GEMM>(bn, grid, tmA, tmW, tmA, tmW, p, st);
+}
+
+extern "C" int mixdq_gemm_w8a8_f16(const int8_t* A, int64_t lda, const int8_t* W,
+                                   const float* bias0, const float* scale,
+                                   const mixdq_half_t* bias, mixdq_half_t* D, int64_t ldd, int M,
+                                   int N, int K, int32_t* acc_out, mixdq_stream_t stream) {
+  return gemm_common(A, lda, W, scale, bias0, nullptr, nullptr, bias, D, ldd, M, N, K, acc_out,
+                     static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mixdq_gemm_w8a8_f16_dyn(const int8_t* A, int64_t lda, const int8_t* W,
+                                       const float* w_scale, const float* wsum,
+                                       const float* a_scale, const float* a_zp,
+                                       const mixdq_half_t* bias, mixdq_half_t* D, int64_t ldd,
+                                       int M, int N, int K, int32_t* acc_out,
+                                       mixdq_stream_t stream) {
+  if (!a_scale || !a_zp) return MIXDQ_ERR_INVALID_ARG;
+  return gemm_common(A, lda, W, w_scale, wsum, a_scale, a_zp, bias, D, ldd, M, N, K, acc_out,
+                     static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mixdq_gemm_w4a8_f16(const int8_t* A, int64_t lda, const uint8_t* W_packed,
+                                   const float* bias0, const float* scale,
+                                   const mixdq_half_t* bias, mixdq_half_t* D, int64_t ldd, int M,
+                                   int N, int K, int32_t* acc_out, mixdq_stream_t stream) {
+  if (M < 0 || N <= 0 || K <= 0 || !W_packed || !scale || !bias0) return MIXDQ_ERR_INVALID_ARG;
+  if (M == 0) return MIXDQ_OK;
+  if (!A || !D || lda < K || ldd < N) return MIXDQ_ERR_INVALID_ARG;
+  if ((K & 31) || (N & 3)) return MIXDQ_ERR_ALIGNMENT;
+  SimtGemmArgs g{};
+  g.A = A; g.lda = lda; g.W = reinterpret_cast<const int8_t*>(W_packed); g.K = K;
+  g.scale = scale; g.bias0 = bias0; g.bias = reinterpret_cast<const __half*>(bias);
+  g.D = reinterpret_cast<__half*>(D); g.ldd = ldd; g.M = M; g.N = N; g.acc_out = acc_out; g.w4 = 1;
+  g_last_path = "simt-w4";
+  return simt_gemm_launch(g, static_cast<cudaStream_t>(stream)) == 0 ? MIXDQ_OK : MIXDQ_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------
+// conv (A3 + A4)
+// ------------------------------------------------------------------------------------------
+extern "C" int mixdq_conv_w8a8_f16(const int8_t* x, int64_t x_cpitch, const int8_t* w,
+                                   const float* scale, const float* wsum_krs,
+                                   const float* bias0_k, const float* zp,
+                                   const mixdq_half_t* bias, mixdq_half_t* y, int N, int H, int W,
+                                   int C, int K, int R, int S, int stride, int pad,
+                                   int32_t* acc_out, mixdq_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N < 0 || H <= 0 || W <= 0 || C <= 0 || K <= 0 || R <= 0 || S <= 0 || stride <= 0 ||
+      pad < 0 || !w || !scale)
+    return MIXDQ_ERR_INVALID_ARG;
+  if (pad > 0 ? (!wsum_krs || !zp) : !bias0_k) return MIXDQ_ERR_INVALID_ARG;
+  if (x_cpitch < C) return MIXDQ_ERR_INVALID_ARG;
+  if ((C & 3) || (K & 3)) return MIXDQ_ERR_ALIGNMENT;
+  const int P = (H + 2 * pad - R) / stride + 1;
+  const int Q = (W + 2 * pad - S) / stride + 1;
+  if (P <= 0 || Q <= 0) return MIXDQ_ERR_INVALID_ARG;
+  if (N == 0) return MIXDQ_OK;
+  if (!x || !y) return MIXDQ_ERR_INVALID_ARG;
+
+  const bool geom_ok = (stride == 1) && (pad == 0 || (pad == 1 && R == 3 && S == 3)) && Q <= 128;
+  const bool tc_ok = !g_force_simt && geom_ok && (C % 16 == 0) && (x_cpitch % 16 == 0) &&
+                     (K % 8 == 0) && al16(x) && al16(w) && al16(y) && (!acc_out || al16(acc_out));
+  if (!tc_ok) {
+    SimtConvArgs c{};
+    c.x = x; c.x_cpitch = x_cpitch; c.w = w; c.scale = scale;
+    c.wsum_krs = pad > 0 ? wsum_krs : nullptr; c.bias0_k = bias0_k; c.zp = zp;
+    c.bias = reinterpret_cast<const __half*>(bias); c.y = reinterpret_cast<__half*>(y);
+    c.N = N; c.H = H; c.W = W; c.C = C; c.K = K; c.R = R; c.S = S; c.stride = stride; c.pad = pad;
+    c.P = P; c.Q = Q; c.acc_out = acc_out;
+    g_last_path = "simt";
+    return simt_conv_launch(c, st) == 0 ? MIXDQ_OK : MIXDQ_ERR_CUDA;
+  }
+
+  // A box: boxN x boxH x boxW output pixels (<= 128 rows of the UMMA tile)
+  int boxW = Q, boxH = BLOCK_M / boxW;
+  if (boxH > P) boxH = P;
+  int boxN = 1;
+  if (boxH == P) { boxN = BLOCK_M / (boxW * boxH); if (boxN > N) boxN = N; if (boxN < 1) boxN = 1; }
+  const int tilesQ = 1, tilesP = (P + boxH - 1) / boxH, tilesN = (N + boxN - 1) / boxN;
+  const int m_tiles = tilesQ * tilesP * tilesN;
+  const int bn = pick_bn(m_tiles, K);
+
+  CUtensorMap tmA, tmW;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                        static_cast<uint64_t>(N)};
+    uint64_t strides[3] = {static_cast<uint64_t>(x_cpitch), static_cast<uint64_t>(x_cpitch) * W,
+                           static_cast<uint64_t>(x_cpitch) * W * H};
+    uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(boxW), static_cast<uint32_t>(boxH),
+                       static_cast<uint32_t>(boxN)};
+    if (!make_tmap(&tmA, x, 4, dims, strides, box)) return MIXDQ_ERR_CUDA;
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(R) * S,
+                        static_cast<uint64_t>(K)};
+    uint64_t strides[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(C) * R * S};
+    uint32_t box[3] = {BLOCK_K, 1, static_cast<uint32_t>(bn)};
+    if (!make_tmap(&tmW, w, 3, dims, strides, box)) return MIXDQ_ERR_CUDA;
+  }
+  TcParams p{};
+  p.M = N * P * Q; p.N = K;
+  p.kb_per_tap = (C + BLOCK_K - 1) / BLOCK_K;
+  p.num_kb = R * S * p.kb_per_tap;
+  p.S = S; p.pad = pad; p.NB = N; p.H = H; p.W = W; p.P = P; p.Q = Q;
+  p.boxW = boxW; p.boxH = boxH; p.boxN = boxN; p.tilesQ = tilesQ; p.tilesP = tilesP;
+  p.a_tx_bytes = static_cast<uint32_t>(boxW) * boxH * boxN * BLOCK_K;
+  p.has_table = pad > 0 ? 1 : 0;
+  p.scale = scale; p.bias0 = pad > 0 ? wsum_krs : bias0_k; p.a_zp = zp;
+  p.bias = reinterpret_cast<const __half*>(bias);
+  p.D = reinterpret_cast<__half*>(y); p.ldd = K; p.acc_out = acc_out;
+  dim3 grid(m_tiles, (K + bn - 1) / bn);
+  g_last_path = "tcgen05";
+  return dispatch_tc<KIND_CONV>(bn, grid, tmA, tmW, tmA, tmW, p, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// split 1x1 shortcut (A6)
+// ------------------------------------------------------------------------------------------
+extern "C" int mixdq_conv1x1_split_w8a8_f16(const int8_t* xa, int64_t lda, const int8_t* wa, int Ca,
+                                            const float* bias0_a, const float* scale_a,
+                                            const int8_t* xb, int64_t ldb, const int8_t* wb, int Cb,
+                                            const float* bias0_b, const float* scale_b,
+                                            const mixdq_half_t* bias, mixdq_half_t* y, int64_t ldy,
+                                            int M, int K, mixdq_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (M < 0 || K <= 0 || Ca <= 0 || Cb <= 0 || !wa || !wb || !bias0_a || !scale_a || !bias0_b ||
+      !scale_b)
+    return MIXDQ_ERR_INVALID_ARG;
+  if (M == 0) return MIXDQ_OK;
+  if (!xa || !xb || !y || lda < Ca || ldb < Cb || ldy < K) return MIXDQ_ERR_INVALID_ARG;
+  if ((Ca & 3) || (Cb & 3) || (K & 3)) return MIXDQ_ERR_ALIGNMENT;
+  const bool tc_ok = !g_force_simt && (Ca % 16 == 0) && (Cb % 16 == 0) && (K % 8 == 0) &&
+                     (lda % 16 == 0) && (ldb % 16 == 0) && (ldy % 8 == 0) && al16(xa) && al16(xb) &&
+                     al16(wa) && al16(wb) && al16(y);
+  if (!tc_ok) {
+    SimtGemmArgs g{};
+    g.A = xa; g.lda = lda; g.W = wa; g.K = Ca;
+    g.A1 = xb; g.lda1 = ldb; g.W1 = wb; g.K1 = Cb;
+    g.scale = scale_a; g.bias0 = bias0_a; g.scale1 = scale_b; g.bias0_1 = bias0_b;
+    g.bias = reinterpret_cast<const __half*>(bias);
+    g.D = reinterpret_cast<__half*>(y); g.ldd = ldy; g.M = M; g.N = K;
+    g_last_path = "simt";
+    return simt_gemm_launch(g, st) == 0 ? MIXDQ_OK : MIXDQ_ERR_CUDA;
+  }
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  int bn = pick_bn(m_tiles, K);
+  if (bn > 128) bn = 128;  // two accumulators: 2 x BN TMEM columns, keep smem params small
+  CUtensorMap tmA, tmW, tmA1, tmW1;
+  if (!make_tmap_2d(&tmA, xa, Ca, M, lda, BLOCK_M) || !make_tmap_2d(&tmW, wa, Ca, K, Ca, bn) ||
+      !make_tmap_2d(&tmA1, xb, Cb, M, ldb, BLOCK_M) || !make_tmap_2d(&tmW1, wb, Cb, K, Cb, bn))
+    return MIXDQ_ERR_CUDA;
+  TcParams p{};
+  p.M = M; p.N = K;
+  p.num_kb = (Ca + BLOCK_K - 1) / BLOCK_K;
+  p.num_kb1 = (Cb + BLOCK_K - 1) / BLOCK_K;
+  p.scale = scale_a; p.bias0 = bias0_a; p.scale1 = scale_b; p.bias0_1 = bias0_b;
+  p.bias = reinterpret_cast<const __half*>(bias);
+  p.D = reinterpret_cast<__half*>(y); p.ldd = ldy;
+  dim3 grid(m_tiles, (K + bn - 1) / bn);
+  g_last_path = "tcgen05";
+  return dispatch_tc<KIND_SPLIT>(bn, grid, tmA, tmW, tmA1, tmW1, p, st);
+}

@@ -1,0 +1,367 @@
+// quant.cu — K-Q: per-tensor activation quantisation fp16 -> int8 (HBM-bound, 3 B/element).
+//
+//   static  : q = clamp(lrintf(fmaf(x, 1/delta, zp)), -128, 127)      reference CUDA formula
+//             (reference csrc/quant_dequant/quantize_kernel.cu:20-24, nvcc contracts x*s+z to FMA)
+//   dynamic : q = clamp(rint(x / delta) + z, 0, 255) - 128             qdiff formula, fp32, true
+//             division (reference quant_utils/qdiff/quantizer/base_quantizer.py:122-128)
+//
+// Layout variants: flat dense, 3-D strided view -> dense rows, NCHW(strided) -> NHWC transpose.
+// All loads are 16-byte (8 halves), all stores 8-byte (8 codes) on the vector paths.
+#include "common.cuh"
+#include "../../include/mixdq_b200.h"
+
+namespace mixdq {
+
+enum QuantMode { kStaticFma = 0, kDynamicDiv = 1 };
+
+struct QParams {
+  float a;  // static: 1/delta      dynamic: delta
+  float b;  // static: zp (-128 shifted)   dynamic: z (unshifted, in [0,255])
+};
+
+template <int MODE>
+__device__ __forceinline__ int quant_one(float x, QParams p) {
+  if (MODE == kStaticFma) {
+    int v = __float2int_rn(__fmaf_rn(x, p.a, p.b));
+    return min(max(v, -128), 127);
+  } else {
+    float r = __fadd_rn(rintf(__fdiv_rn(x, p.a)), p.b);
+    r = fminf(fmaxf(r, 0.0f), 255.0f);
+    return static_cast<int>(r) - 128;
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ QParams load_qparams(const float* a, const float* b) {
+  QParams p;
+  p.a = __ldg(a);
+  p.b = __ldg(b);
+  if (MODE == kDynamicDiv) p.b = p.b + 128.0f;  // stored zero point is z-128; exact in fp32
+  return p;
+}
+
+template <int MODE>
+__device__ __forceinline__ uint2 quant_vec8(const int4& raw, QParams p) {
+  const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+  int q[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h2[i]);
+    q[2 * i] = quant_one<MODE>(f.x, p);
+    q[2 * i + 1] = quant_one<MODE>(f.y, p);
+  }
+  uint2 out;
+  out.x = (q[0] & 0xff) | ((q[1] & 0xff) << 8) | ((q[2] & 0xff) << 16) | ((q[3] & 0xff) << 24);
+  out.y = (q[4] & 0xff) | ((q[5] & 0xff) << 8) | ((q[6] & 0xff) << 16) | ((q[7] & 0xff) << 24);
+  return out;
+}
+
+__device__ __forceinline__ int4 ld_stream16(const void* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// ---- flat dense ---------------------------------------------------------------------------
+constexpr int kQuantThreads = 256;
+constexpr int kQuantUnroll = 4;  // 16-byte loads in flight per thread
+
+template <int MODE>
+__global__ void __launch_bounds__(kQuantThreads)
+quant_flat_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int64_t numel,
+                  const float* __restrict__ pa, const float* __restrict__ pb) {
+  const QParams p = load_qparams<MODE>(pa, pb);
+  const int64_t nvec = numel >> 3;
+  const int4* xv = reinterpret_cast<const int4*>(x);
+  uint2* qv = reinterpret_cast<uint2*>(q);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kQuantThreads;
+  int64_t i = static_cast<int64_t>(blockIdx.x) * kQuantThreads + threadIdx.x;
+  for (; i + (kQuantUnroll - 1) * stride < nvec; i += kQuantUnroll * stride) {
+    int4 r[kQuantUnroll];
+#pragma unroll
+    for (int u = 0; u < kQuantUnroll; ++u) r[u] = ld_stream16(xv + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < kQuantUnroll; ++u) qv[i + u * stride] = quant_vec8<MODE>(r[u], p);
+  }
+  for (; i < nvec; i += stride) qv[i] = quant_vec8<MODE>(ld_stream16(xv + i), p);
+  // scalar tail (numel % 8)
+  const int64_t tail0 = nvec << 3;
+  const int64_t t = tail0 + static_cast<int64_t>(blockIdx.x) * kQuantThreads + threadIdx.x;
+  if (t < numel) q[t] = static_cast<int8_t>(quant_one<MODE>(__half2float(x[t]), p));
+}
+
+// Unaligned base pointers (never produced by torch allocations, but legal through the C ABI).
+template <int MODE>
+__global__ void __launch_bounds__(kQuantThreads)
+quant_flat_scalar_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int64_t numel,
+                         const float* __restrict__ pa, const float* __restrict__ pb) {
+  const QParams p = load_qparams<MODE>(pa, pb);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kQuantThreads;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kQuantThreads + threadIdx.x; i < numel;
+       i += stride)
+    q[i] = static_cast<int8_t>(quant_one<MODE>(__half2float(x[i]), p));
+}
+
+// ---- 3-D strided view [d0][d1][cols] -> dense rows -----------------------------------------
+template <int MODE, bool VEC>
+__global__ void __launch_bounds__(kQuantThreads)
+quant_strided_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int64_t rows,
+                     int64_t d1, int64_t cols, int64_t s0, int64_t s1, int64_t out_pitch,
+                     const float* __restrict__ pa, const float* __restrict__ pb) {
+  const QParams p = load_qparams<MODE>(pa, pb);
+  const int64_t cpr = VEC ? (cols >> 3) : cols;  // work items per row
+  const int64_t total = rows * cpr;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kQuantThreads;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kQuantThreads + threadIdx.x; i < total;
+       i += stride) {
+    const int64_t row = i / cpr;
+    const int64_t c = i - row * cpr;
+    const int64_t i0 = row / d1;
+    const int64_t i1 = row - i0 * d1;
+    const __half* src = x + i0 * s0 + i1 * s1;
+    int8_t* dst = q + row * out_pitch;
+    if (VEC) {
+      int4 r = ld_stream16(reinterpret_cast<const int4*>(src) + c);
+      reinterpret_cast<uint2*>(dst)[c] = quant_vec8<MODE>(r, p);
+    } else {
+      dst[c] = static_cast<int8_t>(quant_one<MODE>(__half2float(src[c]), p));
+    }
+  }
+}
+
+// ---- NCHW (arbitrary strides) -> NHWC, channel range [c0, c1) ------------------------------
+constexpr int kTrC = 64;   // channels per tile
+constexpr int kTrP = 64;   // pixels per tile
+template <int MODE>
+__global__ void __launch_bounds__(256)
+quant_nchw2nhwc_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int C0, int Csel,
+                       int H, int W, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
+                       const float* __restrict__ pa, const float* __restrict__ pb) {
+  __shared__ int8_t tile[kTrP][kTrC + 4];
+  const QParams p = load_qparams<MODE>(pa, pb);
+  const int HW = H * W;
+  const int n = blockIdx.z;
+  const int pix0 = blockIdx.x * kTrP;
+  const int ch0 = blockIdx.y * kTrC;
+  const int tp = threadIdx.x & (kTrP - 1);
+  const int tc = threadIdx.x >> 6;  // 0..3
+  const int pix = pix0 + tp;
+  if (pix < HW) {
+    const int h = pix / W, w = pix - h * W;
+    const __half* src = x + n * sn + h * sh + w * sw;
+#pragma unroll 4
+    for (int i = 0; i < kTrC / 4; ++i) {
+      const int c = ch0 + tc + 4 * i;
+      if (c < Csel)
+        tile[tp][tc + 4 * i] =
+            static_cast<int8_t>(quant_one<MODE>(__half2float(src[(C0 + c) * sc]), p));
+    }
+  }
+  __syncthreads();
+  // store: 16 threads x 4 B cover one pixel's 64 channels
+  const int lane16 = threadIdx.x & 15;
+  const int prow = threadIdx.x >> 4;  // 0..15
+  const bool vec_ok = (Csel & 3) == 0;
+#pragma unroll
+  for (int i = 0; i < kTrP / 16; ++i) {
+    const int pl = prow + 16 * i;
+    const int pp = pix0 + pl;
+    const int c = ch0 + lane16 * 4;
+    if (pp < HW && c < Csel) {
+      int8_t* dst = q + (static_cast<int64_t>(n) * HW + pp) * Csel + c;
+      if (vec_ok) {
+        *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(&tile[pl][lane16 * 4]);
+      } else {
+        for (int j = 0; j < 4 && c + j < Csel; ++j) dst[j] = tile[pl][lane16 * 4 + j];
+      }
+    }
+  }
+}
+
+// ---- dynamic: min/max reduction + qparam computation ----------------------------------------
+constexpr int kMaxPartials = 1024;
+struct DynWs {
+  unsigned int counter;
+  unsigned int pad[3];
+  float2 partial[kMaxPartials];
+};
+
+__global__ void __launch_bounds__(kQuantThreads)
+minmax_kernel(const __half* __restrict__ x, int64_t numel, DynWs* __restrict__ ws,
+              float* __restrict__ scale_out, float* __restrict__ zp_out) {
+  float mn = 0.0f, mx = 0.0f;  // qdiff clamps x_min <= 0 <= x_max (base_quantizer.py:155-158)
+  const int64_t nvec = numel >> 3;
+  const int4* xv = reinterpret_cast<const int4*>(x);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kQuantThreads;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kQuantThreads + threadIdx.x; i < nvec;
+       i += stride) {
+    int4 raw = __ldg(xv + i);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __half22float2(h2[j]);
+      mn = fminf(mn, fminf(f.x, f.y));
+      mx = fmaxf(mx, fmaxf(f.x, f.y));
+    }
+  }
+  const int64_t t = (nvec << 3) + static_cast<int64_t>(blockIdx.x) * kQuantThreads + threadIdx.x;
+  if (t < numel) {
+    float f = __half2float(x[t]);
+    mn = fminf(mn, f);
+    mx = fmaxf(mx, f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __shared__ float smn[kQuantThreads / 32], smx[kQuantThreads / 32];
+  __shared__ bool is_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { smn[warp] = mn; smx[warp] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kQuantThreads / 32; ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
+    ws->partial[blockIdx.x] = make_float2(mn, mx);
+    __threadfence();
+    const unsigned int done = atomicAdd(&ws->counter, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  mn = 0.0f; mx = 0.0f;
+  for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += kQuantThreads) {
+    float2 v = __ldcg(&ws->partial[i]);
+    mn = fminf(mn, v.x);
+    mx = fmaxf(mx, v.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __syncthreads();
+  if (lane == 0) { smn[warp] = mn; smx[warp] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kQuantThreads / 32; ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
+    // delta = (x_max - x_min) / (n_levels - 1); eps clamp (base_quantizer.py:178-182)
+    float delta = __fdiv_rn(__fsub_rn(mx, mn), 255.0f);
+    if (delta < 1e-6f) delta = 1e-6f;
+    // zero_point = round(-x_min / delta) (base_quantizer.py:187)
+    const float z = rintf(__fdiv_rn(-mn, delta));
+    *scale_out = delta;
+    *zp_out = z - 128.0f;
+    ws->counter = 0;  // leave the workspace ready for the next call
+  }
+}
+
+static inline int grid_for(int64_t items, int per_block, int max_blocks) {
+  int64_t g = (items + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return static_cast<int>(g);
+}
+
+}  // namespace mixdq
+
+using namespace mixdq;
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
+
+#define MIXDQ_CHECK_LAUNCH()                                   \
+  do {                                                         \
+    cudaError_t e__ = cudaGetLastError();                      \
+    if (e__ != cudaSuccess) return MIXDQ_ERR_CUDA;             \
+  } while (0)
+
+template <int MODE>
+static int launch_flat(const __half* x, int64_t numel, const float* a, const float* b, int8_t* q,
+                       cudaStream_t st) {
+  if (numel == 0) return MIXDQ_OK;
+  const int max_blocks = 148 * 8;
+  if (aligned16(x) && aligned8(q)) {
+    int grid = grid_for(numel >> 3, kQuantThreads * kQuantUnroll, max_blocks);
+    quant_flat_kernel<MODE><<<grid, kQuantThreads, 0, st>>>(x, q, numel, a, b);
+  } else {
+    int grid = grid_for(numel, kQuantThreads, max_blocks);
+    quant_flat_scalar_kernel<MODE><<<grid, kQuantThreads, 0, st>>>(x, q, numel, a, b);
+  }
+  MIXDQ_CHECK_LAUNCH();
+  return MIXDQ_OK;
+}
+
+extern "C" int mixdq_quant_i8_static(const mixdq_half_t* x, int64_t numel, const float* scale_inv,
+                                     const float* zp, int8_t* q, mixdq_stream_t stream) {
+  if (numel < 0 || (numel > 0 && (!x || !q)) || !scale_inv || !zp) return MIXDQ_ERR_INVALID_ARG;
+  return launch_flat<kStaticFma>(reinterpret_cast<const __half*>(x), numel, scale_inv, zp, q,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mixdq_quant_i8_static_strided(const mixdq_half_t* x, int64_t d0, int64_t d1,
+                                             int64_t cols, int64_t s0, int64_t s1,
+                                             const float* scale_inv, const float* zp, int8_t* q,
+                                             int64_t out_pitch, mixdq_stream_t stream) {
+  if (d0 < 0 || d1 < 0 || cols < 0 || out_pitch < cols || !scale_inv || !zp)
+    return MIXDQ_ERR_INVALID_ARG;
+  const int64_t rows = d0 * d1;
+  if (rows == 0 || cols == 0) return MIXDQ_OK;
+  if (!x || !q) return MIXDQ_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __half* xh = reinterpret_cast<const __half*>(x);
+  // fully dense view -> flat kernel
+  if (s1 == cols && (s0 == d1 * cols || d0 == 1) && out_pitch == cols)
+    return launch_flat<kStaticFma>(xh, rows * cols, scale_inv, zp, q, st);
+  const bool vec = (cols % 8 == 0) && (s0 % 8 == 0) && (s1 % 8 == 0) && (out_pitch % 8 == 0) &&
+                   aligned16(x) && aligned8(q);
+  const int64_t items = vec ? rows * (cols >> 3) : rows * cols;
+  int grid = grid_for(items, kQuantThreads, 148 * 16);
+  if (vec)
+    quant_strided_kernel<kStaticFma, true><<<grid, kQuantThreads, 0, st>>>(
+        xh, q, rows, d1, cols, s0, s1, out_pitch, scale_inv, zp);
+  else
+    quant_strided_kernel<kStaticFma, false><<<grid, kQuantThreads, 0, st>>>(
+        xh, q, rows, d1, cols, s0, s1, out_pitch, scale_inv, zp);
+  MIXDQ_CHECK_LAUNCH();
+  return MIXDQ_OK;
+}
+
+extern "C" int mixdq_quant_i8_nchw2nhwc(const mixdq_half_t* x, int N, int C, int H, int W,
+                                        const int64_t xstride[4], int c_begin, int c_end,
+                                        const float* scale_inv, const float* zp, int8_t* q_nhwc,
+                                        mixdq_stream_t stream) {
+  if (N < 0 || C <= 0 || H < 0 || W < 0 || !xstride || c_begin < 0 || c_end > C ||
+      c_begin >= c_end || !scale_inv || !zp)
+    return MIXDQ_ERR_INVALID_ARG;
+  if (N == 0 || H == 0 || W == 0) return MIXDQ_OK;
+  if (!x || !q_nhwc || N > 65535) return MIXDQ_ERR_INVALID_ARG;
+  const int Csel = c_end - c_begin;
+  const int HW = H * W;
+  dim3 grid((HW + kTrP - 1) / kTrP, (Csel + kTrC - 1) / kTrC, N);
+  if (grid.y > 65535) return MIXDQ_ERR_UNSUPPORTED;
+  quant_nchw2nhwc_kernel<kStaticFma><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), q_nhwc, c_begin, Csel, H, W, xstride[0], xstride[1],
+      xstride[2], xstride[3], scale_inv, zp);
+  MIXDQ_CHECK_LAUNCH();
+  return MIXDQ_OK;
+}
+
+extern "C" int64_t mixdq_quant_dynamic_ws_bytes(void) { return sizeof(DynWs); }
+
+extern "C" int mixdq_quant_i8_dynamic(const mixdq_half_t* x, int64_t numel, float* scale_out,
+                                      float* zp_out, int8_t* q, void* ws,
+                                      mixdq_stream_t stream) {
+  if (numel <= 0 || !x || !q || !scale_out || !zp_out || !ws) return MIXDQ_ERR_INVALID_ARG;
+  if (!aligned16(x)) return MIXDQ_ERR_ALIGNMENT;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __half* xh = reinterpret_cast<const __half*>(x);
+  int grid = grid_for(numel >> 3, kQuantThreads * 2, kMaxPartials);
+  minmax_kernel<<<grid, kQuantThreads, 0, st>>>(xh, numel, static_cast<DynWs*>(ws), scale_out,
+                                               zp_out);
+  MIXDQ_CHECK_LAUNCH();
+  return launch_flat<kDynamicDiv>(xh, numel, scale_out, zp_out, q, st);
+}

@@ -1,0 +1,129 @@
+// simt.cu — portable dp4a kernels for the shapes the tcgen05 path does not take
+// (K or C not a multiple of 16, N not a multiple of 8 — e.g. SDXL conv_in C=4 / conv_out K=4 —
+// strided convolutions, exotic padding) and as an independent on-device cross-check of the
+// tensor-core kernels in the parity tests. Same integer arithmetic, same epilogue order.
+#include "common.cuh"
+#include "simt.h"
+
+namespace mixdq {
+
+__device__ __forceinline__ int dot_i8(const int8_t* __restrict__ a, const int8_t* __restrict__ b,
+                                      int k, bool vec16) {
+  int acc = 0;
+  if (vec16) {
+    const int4* a4 = reinterpret_cast<const int4*>(a);
+    const int4* b4 = reinterpret_cast<const int4*>(b);
+    for (int i = 0; i < (k >> 4); ++i) {
+      const int4 x = __ldg(a4 + i), y = __ldg(b4 + i);
+      acc = __dp4a(x.x, y.x, acc);
+      acc = __dp4a(x.y, y.y, acc);
+      acc = __dp4a(x.z, y.z, acc);
+      acc = __dp4a(x.w, y.w, acc);
+    }
+  } else {
+    const int* a1 = reinterpret_cast<const int*>(a);
+    const int* b1 = reinterpret_cast<const int*>(b);
+    for (int i = 0; i < (k >> 2); ++i) acc = __dp4a(__ldg(a1 + i), __ldg(b1 + i), acc);
+  }
+  return acc;
+}
+
+__device__ __forceinline__ int8_t nib_hi(uint8_t b) { return static_cast<int8_t>(b) >> 4; }
+__device__ __forceinline__ int8_t nib_lo(uint8_t b) {
+  return static_cast<int8_t>(static_cast<int8_t>(b << 4) >> 4);
+}
+
+__global__ void __launch_bounds__(256)
+simt_gemm_kernel(SimtGemmArgs g) {
+  const int n = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= g.M || n >= g.N) return;
+  int acc = 0, acc1 = 0;
+  if (g.w4) {
+    // packed signed 4-bit weights, even k in the high nibble
+    const int8_t* a = g.A + static_cast<int64_t>(m) * g.lda;
+    const uint8_t* w = reinterpret_cast<const uint8_t*>(g.W) + static_cast<int64_t>(n) * (g.K >> 1);
+    for (int k = 0; k < g.K; k += 2) {
+      const uint8_t b = __ldg(w + (k >> 1));
+      acc += static_cast<int>(a[k]) * nib_hi(b) + static_cast<int>(a[k + 1]) * nib_lo(b);
+    }
+  } else {
+    const bool v16 = (g.K % 16 == 0) && (g.lda % 16 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(g.A) | reinterpret_cast<uintptr_t>(g.W)) & 15) == 0;
+    acc = dot_i8(g.A + static_cast<int64_t>(m) * g.lda, g.W + static_cast<int64_t>(n) * g.K, g.K, v16);
+    if (g.A1 != nullptr) {
+      const bool v16b = (g.K1 % 16 == 0) && (g.lda1 % 16 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(g.A1) | reinterpret_cast<uintptr_t>(g.W1)) & 15) == 0;
+      acc1 = dot_i8(g.A1 + static_cast<int64_t>(m) * g.lda1, g.W1 + static_cast<int64_t>(n) * g.K1,
+                    g.K1, v16b);
+    }
+  }
+  if (g.acc_out) g.acc_out[static_cast<int64_t>(m) * g.N + n] = acc;
+  float sc, b0;
+  if (g.a_scale) {
+    sc = __fmul_rn(__ldg(g.scale + n), __ldg(g.a_scale));
+    b0 = __fmul_rn(__ldg(g.bias0 + n), __ldg(g.a_zp));
+  } else {
+    sc = __ldg(g.scale + n);
+    b0 = __ldg(g.bias0 + n);
+  }
+  float f = dequant_f32(acc, b0, sc);
+  if (g.bias) f = __fadd_rn(f, __half2float(g.bias[n]));
+  __half h = __float2half_rn(f);
+  if (g.A1 != nullptr) {
+    const float f1 = dequant_f32(acc1, __ldg(g.bias0_1 + n), __ldg(g.scale1 + n));
+    h = __float2half_rn(__fadd_rn(__half2float(h), __half2float(__float2half_rn(f1))));
+  }
+  g.D[static_cast<int64_t>(m) * g.ldd + n] = h;
+}
+
+__global__ void __launch_bounds__(256)
+simt_conv_kernel(SimtConvArgs c) {
+  const int k = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int64_t pix = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int64_t npix = static_cast<int64_t>(c.N) * c.P * c.Q;
+  if (k >= c.K || pix >= npix) return;
+  const int q = static_cast<int>(pix % c.Q);
+  const int p = static_cast<int>((pix / c.Q) % c.P);
+  const int n = static_cast<int>(pix / (static_cast<int64_t>(c.Q) * c.P));
+  const int h0 = p * c.stride - c.pad, w0 = q * c.stride - c.pad;
+  const bool v16 = (c.C % 16 == 0) && (c.x_cpitch % 16 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(c.x) | reinterpret_cast<uintptr_t>(c.w)) & 15) == 0;
+  int acc = 0;
+  float wacc = 0.f;
+  for (int r = 0; r < c.R; ++r) {
+    const int h = h0 + r;
+    if (h < 0 || h >= c.H) continue;
+    for (int s = 0; s < c.S; ++s) {
+      const int w = w0 + s;
+      if (w < 0 || w >= c.W) continue;
+      const int8_t* xp = c.x + ((static_cast<int64_t>(n) * c.H + h) * c.W + w) * c.x_cpitch;
+      const int8_t* wp = c.w + ((static_cast<int64_t>(k) * c.R + r) * c.S + s) * c.C;
+      acc += dot_i8(xp, wp, c.C, v16);
+      if (c.wsum_krs) wacc = __fadd_rn(wacc, __ldg(c.wsum_krs + (static_cast<int64_t>(k) * c.R + r) * c.S + s));
+    }
+  }
+  if (c.acc_out) c.acc_out[pix * c.K + k] = acc;
+  // zero-point propagation: float(acc_w) * zp (conv_act_zero_point_propagate.cu:35-49)
+  const float b0 = c.wsum_krs ? __fmul_rn(wacc, __ldg(c.zp)) : __ldg(c.bias0_k + k);
+  float f = dequant_f32(acc, b0, __ldg(c.scale + k));
+  if (c.bias) f = __fadd_rn(f, __half2float(c.bias[k]));
+  c.y[pix * c.K + k] = __float2half_rn(f);
+}
+
+int simt_gemm_launch(const SimtGemmArgs& g, cudaStream_t st) {
+  dim3 grid((g.M + 7) / 8, (g.N + 31) / 32);
+  if (grid.y > 65535) return -1;
+  simt_gemm_kernel<<<grid, 256, 0, st>>>(g);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int simt_conv_launch(const SimtConvArgs& c, cudaStream_t st) {
+  const int64_t npix = static_cast<int64_t>(c.N) * c.P * c.Q;
+  dim3 grid(static_cast<unsigned>((npix + 7) / 8), (c.K + 31) / 32);
+  if (grid.y > 65535 || (npix + 7) / 8 > 2147483647LL) return -1;
+  simt_conv_kernel<<<grid, 256, 0, st>>>(c);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace mixdq

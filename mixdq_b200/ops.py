@@ -1,0 +1,431 @@
+"""Host side of the op layer: the reference's `mixdq_extension._C` functions, re-implemented as a
+thin Python shim over the C ABI (include/mixdq_b200.h).
+
+Same names, argument order, checks and error behaviour as the reference's pybind module
+(reference kernels/mixdq_extension/csrc/main.cpp:9-13, quant_dequant/quantize.cc:9-62,
+qlinear/qlinear.cc:14-234, qconv2d/qconv2d.cc:28-235): outputs are allocated here with
+torch.empty* on the caching allocator, work is enqueued on the current CUDA stream without any
+synchronisation (CUDA-graph capturable), inputs are never mutated, violations raise RuntimeError.
+PyTorch is plumbing only (device memory + streams); all arithmetic happens in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_c_int64_4 = ctypes.c_int64 * 4
+
+
+def _check(cond: bool, msg: str) -> None:
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _is_dense(t: torch.Tensor) -> bool:
+    """non-overlapping and dense in some dimension order (what empty_like preserves)."""
+    if t.is_contiguous():
+        return True
+    if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+        return True
+    dims = sorted(range(t.dim()), key=lambda d: (t.stride(d), t.size(d)))
+    expect = 1
+    for d in dims:
+        if t.size(d) == 1:
+            continue
+        if t.stride(d) != expect:
+            return False
+        expect *= t.size(d)
+    return True
+
+
+class _DeviceGuard:
+    __slots__ = ("dev", "prev")
+
+    def __init__(self, t: torch.Tensor):
+        self.dev = t.device.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.dev is not None and cur != self.dev:
+            self.prev = cur
+            torch.cuda.set_device(self.dev)
+
+    def __exit__(self, *a):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+# ---------------------------------------------------------------------------------------------
+# A1  quantize_per_tensor_to_int8[_vectorized]
+# ---------------------------------------------------------------------------------------------
+def _check_quant_args(input, scale_inv, zero_point):
+    _check(input.device.type == "cuda", "input should be on CUDA")
+    _check(input.device == scale_inv.device, "input and scale should be on the same device")
+    _check(input.device == zero_point.device,
+           "input and zero_point should be on the same device")
+    _check(input.dtype == torch.float16, "input should be fp16")
+    _check(scale_inv.dtype == torch.float32, "scale_inv should be fp32")
+    _check(zero_point.dtype == torch.float32, "zero_point should be fp32")
+
+
+def quantize_per_tensor_to_int8(input: torch.Tensor, scale_inv: torch.Tensor,
+                                zero_point: torch.Tensor) -> torch.Tensor:
+    """q = int8(clamp(lrintf(x * scale_inv + zero_point), -128, 127)); returns empty_like(input).
+
+    Reference: quantize.cc:9-30 (+ kernel quantize_kernel.cu:10-27). Unlike the reference, which
+    walks `data_ptr()` linearly over `numel` whatever the strides are, a non-dense view
+    (x[:, :split], x[:, 1:, :] at batch > 1) is read through its strides and the result is the
+    logically correct dense tensor.
+    """
+    _check_quant_args(input, scale_inv, zero_point)
+    lib = _lib.load()
+    with _DeviceGuard(input):
+        if _is_dense(input):
+            out = torch.empty_like(input, dtype=torch.int8)
+            _lib.check(lib.mixdq_quant_i8_static(input.data_ptr(), input.numel(),
+                                                 scale_inv.data_ptr(), zero_point.data_ptr(),
+                                                 out.data_ptr(), _stream(input)))
+            return out
+        return _quantize_view(input, scale_inv, zero_point)
+
+
+# one kernel family serves both reference entry points
+quantize_per_tensor_to_int8_vectorized = quantize_per_tensor_to_int8
+
+
+def _quantize_view(x: torch.Tensor, scale_inv, zero_point) -> torch.Tensor:
+    """Non-dense views. NHWC channel slices and [B, T', K] token slices go through the strided
+    kernel in place; anything else is densified first."""
+    lib = _lib.load()
+    st = _stream(x)
+    if x.dim() == 4 and x.stride(1) == 1 and x.stride(3) >= x.size(1) \
+            and x.stride(2) == x.size(3) * x.stride(3) and x.stride(0) == x.size(2) * x.stride(2):
+        # channel slice of an NHWC tensor -> dense NHWC int8 (logical NCHW, channels_last)
+        n, c, h, w = x.shape
+        out = torch.empty((n, c, h, w), dtype=torch.int8, device=x.device,
+                          memory_format=torch.channels_last)
+        _lib.check(lib.mixdq_quant_i8_static_strided(
+            x.data_ptr(), 1, n * h * w, c, 0, x.stride(3), scale_inv.data_ptr(),
+            zero_point.data_ptr(), out.data_ptr(), c, st))
+        return out
+    if x.dim() == 3 and x.stride(2) == 1:
+        b, t, k = x.shape
+        out = torch.empty((b, t, k), dtype=torch.int8, device=x.device)
+        _lib.check(lib.mixdq_quant_i8_static_strided(
+            x.data_ptr(), b, t, k, x.stride(0), x.stride(1), scale_inv.data_ptr(),
+            zero_point.data_ptr(), out.data_ptr(), k, st))
+        return out
+    xc = x.contiguous()
+    out = torch.empty_like(xc, dtype=torch.int8)
+    _lib.check(lib.mixdq_quant_i8_static(xc.data_ptr(), xc.numel(), scale_inv.data_ptr(),
+                                         zero_point.data_ptr(), out.data_ptr(), st))
+    return out
+
+
+def quantize_to_nhwc(input: torch.Tensor, scale_inv: torch.Tensor, zero_point: torch.Tensor,
+                     c_begin: int = 0, c_end: Optional[int] = None) -> torch.Tensor:
+    """Fused quantize + layout: fp16 [N,C,H,W] (any strides) channels [c_begin,c_end) -> int8
+    channels_last. Replaces quantize + the int8 `.contiguous(ChannelsLast)` copy of
+    qconv2d.cc:91-92, and the `x[:, :split]` slicing of nn/Conv2d.py:313-318."""
+    _check_quant_args(input, scale_inv, zero_point)
+    _check(input.dim() == 4, "input should be 4-D")
+    n, c, h, w = input.shape
+    c_end = c if c_end is None else c_end
+    _check(0 <= c_begin < c_end <= c, "bad channel range")
+    lib = _lib.load()
+    csel = c_end - c_begin
+    out = torch.empty((n, csel, h, w), dtype=torch.int8, device=input.device,
+                      memory_format=torch.channels_last)
+    with _DeviceGuard(input):
+        st = _stream(input)
+        nhwc = input.stride(1) == 1 and input.stride(2) == w * input.stride(3) \
+            and input.stride(0) == h * input.stride(2)
+        if nhwc:
+            base = input.data_ptr() + 2 * c_begin
+            _lib.check(lib.mixdq_quant_i8_static_strided(
+                base, 1, n * h * w, csel, 0, input.stride(3), scale_inv.data_ptr(),
+                zero_point.data_ptr(), out.data_ptr(), csel, st))
+        else:
+            strides = _c_int64_4(*input.stride())
+            _lib.check(lib.mixdq_quant_i8_nchw2nhwc(
+                input.data_ptr(), n, c, h, w, strides, c_begin, c_end, scale_inv.data_ptr(),
+                zero_point.data_ptr(), out.data_ptr(), st))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# A10  dynamic (qdiff min-max) quantisation
+# ---------------------------------------------------------------------------------------------
+_dyn_ws = {}
+
+
+def _dynamic_workspace(device: torch.device) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _dyn_ws.get(key)
+    if ws is None:
+        nbytes = _lib.load().mixdq_quant_dynamic_ws_bytes()
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _dyn_ws[key] = ws
+    return ws
+
+
+def quantize_per_tensor_dynamic(input: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """qdiff asymmetric 8-bit min-max quantisation of one tensor (base_quantizer.py:155-190).
+    Returns (q int8, scale fp32[], zero_point fp32[] (shifted by -128))."""
+    _check(input.device.type == "cuda", "input should be on CUDA")
+    _check(input.dtype == torch.float16, "input should be fp16")
+    lib = _lib.load()
+    x = input if _is_dense(input) else input.contiguous()
+    out = torch.empty_like(x, dtype=torch.int8)
+    qp = torch.empty(2, dtype=torch.float32, device=x.device)
+    with _DeviceGuard(x):
+        ws = _dynamic_workspace(x.device)
+        _lib.check(lib.mixdq_quant_i8_dynamic(x.data_ptr(), x.numel(), qp.data_ptr(),
+                                              qp.data_ptr() + 4, out.data_ptr(), ws.data_ptr(),
+                                              _stream(x)))
+    return out, qp[0], qp[1]
+
+
+# ---------------------------------------------------------------------------------------------
+# A2  qlinear_w8_a8_ohalf
+# ---------------------------------------------------------------------------------------------
+def _check_linear_common(input_int8, weight_int8, weight_scale, input_scale, input_zero_point,
+                         weight_sum_by_input_channels, bias):
+    dev = input_int8.device
+    _check(dev.type == "cuda", "Input should be on GPU.")
+    _check(dev == weight_int8.device, "input and weight_int8 should be on the same device.")
+    _check(dev == weight_scale.device, "input and weight_scale should be on the same device.")
+    _check(dev == input_scale.device, "input and input_scale should be on the same device.")
+    _check(dev == input_zero_point.device,
+           "input and input_zero_point should be on the same device.")
+    _check(dev == weight_sum_by_input_channels.device,
+           "input and input_zero_point should be on the same device.")
+    if bias is not None:
+        _check(dev == bias.device, "input and bias should be on the same device.")
+    _check(input_int8.dtype == torch.int8, "input_int8 should be int8 type")
+    _check(weight_int8.dtype == torch.int8, "weight_int8 should be int8 type")
+    _check(weight_scale.dtype == torch.float32,
+           "Currently only support weight_scale with float32 type")
+    _check(input_scale.dtype == torch.float32,
+           "Currently only support input_scale with float32 type")
+    _check(input_zero_point.dtype == torch.float32,
+           "Currently only support input_zero_point with float32 type")
+    _check(weight_sum_by_input_channels.dtype == torch.float32,
+           "Currently only support weight_sum_by_input_channels with float32 type")
+    if bias is not None:
+        _check(bias.dtype == torch.float16, "Currently only support bias with float16 type")
+
+
+def qlinear_w8_a8_ohalf(input_int8, weight_int8, weight_scale, input_scale, input_zero_point,
+                        weight_sum_by_input_channels, scale, bias0, bias=None,
+                        _acc_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """D = half((float(A @ W^T) - bias0) * scale [+ bias]); reference qlinear.cc:14-137."""
+    _check_linear_common(input_int8, weight_int8, weight_scale, input_scale, input_zero_point,
+                         weight_sum_by_input_channels, bias)
+    N, K = weight_int8.shape[0], weight_int8.shape[1]
+    _check(weight_scale.numel() == N,
+           "The size of the weight_scale vector should be equal to output_channels.")
+    _check(weight_sum_by_input_channels.numel() == N,
+           "The size of weight_sum_by_input_channels should equal output_channels.")
+    if bias is not None:
+        _check(bias.numel() == N,
+               "The size of the bias vector should be equal to output_channels.")
+    _check(input_int8.size(-1) == K,
+           f"The last dimension of input and weight should match, got {input_int8.size(-1)} "
+           f"and {K}.")
+    _check(scale.dtype == torch.float32 and bias0.dtype == torch.float32
+           and scale.numel() == N and bias0.numel() == N,
+           "scale and bias0 should be float32 vectors of size output_channels.")
+    a = input_int8.contiguous()
+    w = weight_int8.contiguous()
+    M = a.numel() // K if K else 0
+    out = torch.empty((*input_int8.shape[:-1], N), dtype=torch.float16, device=a.device)
+    lib = _lib.load()
+    with _DeviceGuard(a):
+        _lib.check(lib.mixdq_gemm_w8a8_f16(a.data_ptr(), K, w.data_ptr(), bias0.data_ptr(),
+                                           scale.data_ptr(), _ptr(bias), out.data_ptr(), N,
+                                           M, N, K, _ptr(_acc_out), _stream(a)))
+    return out
+
+
+def qlinear_w8_a8_ohalf_dynamic(input_int8, weight_int8, weight_scale, input_scale,
+                                input_zero_point, weight_sum_by_input_channels, bias=None,
+                                _acc_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Dynamic-scale variant: scale = weight_scale*input_scale and bias0 = wsum*input_zp are
+    formed in the kernel epilogue from device scalars."""
+    _check_linear_common(input_int8, weight_int8, weight_scale, input_scale, input_zero_point,
+                         weight_sum_by_input_channels, bias)
+    N, K = weight_int8.shape
+    a = input_int8.contiguous()
+    w = weight_int8.contiguous()
+    M = a.numel() // K
+    out = torch.empty((*input_int8.shape[:-1], N), dtype=torch.float16, device=a.device)
+    lib = _lib.load()
+    with _DeviceGuard(a):
+        _lib.check(lib.mixdq_gemm_w8a8_f16_dyn(
+            a.data_ptr(), K, w.data_ptr(), weight_scale.data_ptr(),
+            weight_sum_by_input_channels.data_ptr(), input_scale.data_ptr(),
+            input_zero_point.data_ptr(), _ptr(bias), out.data_ptr(), N, M, N, K,
+            _ptr(_acc_out), _stream(a)))
+    return out
+
+
+def qlinear_w4_a8_ohalf(input_int8, weight_packed, scale, bias0, bias=None,
+                        _acc_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """W4A8: weight_packed uint8 [N, K/2], even k in the high nibble, signed 4-bit codes."""
+    _check(input_int8.dtype == torch.int8, "input_int8 should be int8 type")
+    _check(weight_packed.dtype == torch.uint8, "weight_packed should be uint8 type")
+    N, K = weight_packed.shape[0], weight_packed.shape[1] * 2
+    _check(input_int8.size(-1) == K, "The last dimension of input and weight should match")
+    a = input_int8.contiguous()
+    w = weight_packed.contiguous()
+    M = a.numel() // K
+    out = torch.empty((*input_int8.shape[:-1], N), dtype=torch.float16, device=a.device)
+    lib = _lib.load()
+    with _DeviceGuard(a):
+        _lib.check(lib.mixdq_gemm_w4a8_f16(a.data_ptr(), K, w.data_ptr(), bias0.data_ptr(),
+                                           scale.data_ptr(), _ptr(bias), out.data_ptr(), N,
+                                           M, N, K, _ptr(_acc_out), _stream(a)))
+    return out
+
+
+def qlinear_fp_reference(input: torch.Tensor, weight: torch.Tensor,
+                         bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Debug fp16 GEMM input[M,K] @ weight[K,N] (qlinear.cc:141-204; the reference ignores bias).
+    A library GEMM: not part of the quantized hot path."""
+    _check(input.dtype == torch.float16 and weight.dtype == torch.float16,
+           "input and weight should be fp16")
+    return torch.matmul(input, weight)
+
+
+# ---------------------------------------------------------------------------------------------
+# A3 + A4  qconv2d_w8_a8_ohalf
+# ---------------------------------------------------------------------------------------------
+def _nhwc_pitch(x: torch.Tensor) -> Optional[int]:
+    """channel pitch if x (logical NCHW) is an NHWC tensor or a channel slice of one."""
+    n, c, h, w = x.shape
+    if x.stride(1) != 1 and c != 1:
+        return None
+    pitch = x.stride(3)
+    if pitch < c or x.stride(2) != w * pitch or x.stride(0) != h * w * pitch:
+        return None
+    return pitch
+
+
+def qconv2d_w8_a8_ohalf(input_int8, weight_int8, weight_scale, input_scale, input_zero_point,
+                        scale, weight_sum_by_input_channels=None, bias0=None, bias=None,
+                        stride: Optional[int] = 1, padding: Optional[int] = 0,
+                        dilation: Optional[int] = 1,
+                        _acc_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """INT8 NHWC conv2d fprop with fused dequant; reference qconv2d.cc:28-206. Returns fp16
+    logical [N,K,P,Q] in channels_last memory."""
+    dev = input_int8.device
+    _check(dev.type == "cuda", "Input should be on GPU.")
+    _check(dev == weight_int8.device, "input and weight_int8 should be on the same device.")
+    _check(dev == weight_scale.device, "input and weight_scale should be on the same device.")
+    _check(dev == input_scale.device, "input and input_scale should be on the same device.")
+    _check(dev == input_zero_point.device,
+           "input and input_zero_point should be on the same device.")
+    if weight_sum_by_input_channels is not None:
+        _check(dev == weight_sum_by_input_channels.device,
+               "input and weight_sum_by_input_channels should be on the same device.")
+    if bias0 is not None:
+        _check(dev == bias0.device, "input and bias0 should be on the same device.")
+    if bias is not None:
+        _check(dev == bias.device, "input and bias should be on the same device.")
+    _check(input_int8.dtype == torch.int8, "input_int8 should be int8 type")
+    _check(weight_int8.dtype == torch.int8, "weight_int8 should be int8 type")
+    _check(weight_scale.dtype == torch.float32,
+           "Currently only support weight_scale with float32 type")
+    _check(input_scale.dtype == torch.float32,
+           "Currently only support input_scale with float32 type")
+    _check(input_zero_point.dtype == torch.float32,
+           "Currently only support input_zero_point with float32 type")
+    if weight_sum_by_input_channels is not None:
+        _check(weight_sum_by_input_channels.dtype == torch.float32,
+               "Currently only support weight_sum_by_input_channels with float32 type")
+    if bias0 is not None:
+        _check(bias0.dtype == torch.float32, "Currently only support bias0 with float32 type")
+    if bias is not None:
+        _check(bias.dtype == torch.float16, "Currently only support bias with float16 type")
+
+    stride = 1 if stride is None else int(stride)
+    padding = 0 if padding is None else int(padding)
+    dilation = 1 if dilation is None else int(dilation)
+    _check(dilation == 1, "dilation > 1 is not supported")  # reference: "has bugs" op/qconv2d.py:120
+
+    n, c, h, w = input_int8.shape
+    k, _, r, s = weight_int8.shape
+    _check(weight_int8.shape[1] == c, "input and weight channel counts should match")
+    p = (h + 2 * padding - dilation * (r - 1) - 1) // stride + 1
+    q = (w + 2 * padding - dilation * (s - 1) - 1) // stride + 1
+    _check(weight_scale.numel() == k,
+           "The size of the weight_scale vector should be equal to output_channels.")
+    if padding == 0:
+        _check(bias0 is not None and bias0.numel() == k,
+               "The size of bias0 should equal output_channels.")
+    else:
+        _check(weight_sum_by_input_channels is not None
+               and weight_sum_by_input_channels.numel() == k * r * s,
+               "The size of weight_sum_by_input_channels should equal K*R*S.")
+    if bias is not None:
+        _check(bias.numel() == k,
+               "The size of the bias vector should be equal to output_channels.")
+
+    pitch = _nhwc_pitch(input_int8)
+    x = input_int8
+    if pitch is None:
+        x = input_int8.contiguous(memory_format=torch.channels_last)
+        pitch = c
+    wt = weight_int8.contiguous(memory_format=torch.channels_last)
+    wsum = None
+    if padding > 0:
+        wsum = weight_sum_by_input_channels.contiguous()
+    out = torch.empty((n, k, p, q), dtype=torch.float16, device=dev,
+                      memory_format=torch.channels_last)
+    lib = _lib.load()
+    with _DeviceGuard(x):
+        _lib.check(lib.mixdq_conv_w8a8_f16(
+            x.data_ptr(), pitch, wt.data_ptr(), scale.data_ptr(), _ptr(wsum),
+            _ptr(bias0) if padding == 0 else None, input_zero_point.data_ptr(), _ptr(bias),
+            out.data_ptr(), n, h, w, c, k, r, s, stride, padding, _ptr(_acc_out), _stream(x)))
+    return out
+
+
+def qconv1x1_split_w8_a8_ohalf(xa_int8, wa_int8, scale_a, bias0_a, xb_int8, wb_int8, scale_b,
+                               bias0_b, bias=None) -> torch.Tensor:
+    """Fused split shortcut (nn/Conv2d.py:312-347): two 1x1 convs over channel halves with
+    independent quantisation parameters, summed as the reference does. x* are int8 logical
+    [N,C*,H,W] NHWC (or NHWC channel slices); w* int8 [K,C*,1,1]."""
+    n, ca, h, w = xa_int8.shape
+    cb = xb_int8.shape[1]
+    k = wa_int8.shape[0]
+    pa, pb = _nhwc_pitch(xa_int8), _nhwc_pitch(xb_int8)
+    if pa is None:
+        xa_int8 = xa_int8.contiguous(memory_format=torch.channels_last); pa = ca
+    if pb is None:
+        xb_int8 = xb_int8.contiguous(memory_format=torch.channels_last); pb = cb
+    wa = wa_int8.reshape(k, ca).contiguous()
+    wb = wb_int8.reshape(k, cb).contiguous()
+    out = torch.empty((n, k, h, w), dtype=torch.float16, device=xa_int8.device,
+                      memory_format=torch.channels_last)
+    lib = _lib.load()
+    with _DeviceGuard(xa_int8):
+        _lib.check(lib.mixdq_conv1x1_split_w8a8_f16(
+            xa_int8.data_ptr(), pa, wa.data_ptr(), ca, bias0_a.data_ptr(), scale_a.data_ptr(),
+            xb_int8.data_ptr(), pb, wb.data_ptr(), cb, bias0_b.data_ptr(), scale_b.data_ptr(),
+            _ptr(bias), out.data_ptr(), k, n * h * w, k, _stream(xa_int8)))
+    return out
