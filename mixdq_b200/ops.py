@@ -33,6 +33,48 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+# ---- launch accounting (bench.py: `gpu_launches`, kernel-family replay for the roofline) --------
+_launch_count = 0
+_recorder = None   # when a list: every launch appends (family, algo_bytes, algo_ops, replay, keep)
+
+
+def launch_count() -> int:
+    """Number of kernels of this library launched (or captured) so far in this process."""
+    return _launch_count
+
+
+def start_recording() -> list:
+    global _recorder
+    _recorder = []
+    return _recorder
+
+
+def stop_recording() -> list:
+    global _recorder
+    rec, _recorder = _recorder, None
+    return rec
+
+
+def _launch(family: str, fn, args: tuple, ref: torch.Tensor, kernels: int = 1, keep=(),
+            algo_bytes: int = 0, algo_ops: int = 0) -> None:
+    """Call one C-ABI entry point (stream appended as the last argument)."""
+    global _launch_count
+    _lib.check(fn(*args, _stream(ref)))
+    _launch_count += kernels
+    if _recorder is not None:
+        dev = ref.device
+
+        def replay(fn=fn, args=args, dev=dev):
+            _lib.check(fn(*args, torch.cuda.current_stream(dev).cuda_stream))
+        _recorder.append((family, algo_bytes, algo_ops, replay, keep, kernels))
+
+
+def _gemm_bytes(M, N, K_in, NK_bytes):
+    """activations once + weights once + fp16 output + 10 B/channel of epilogue
+    vectors."""
+    return M * K_in + NK_bytes + 2 * M * N + 10 * N
+
+
 def _is_dense(t: torch.Tensor) -> bool:
     """non-overlapping and dense in some dimension order (what empty_like preserves)."""
     if t.is_contiguous():
@@ -95,9 +137,10 @@ def quantize_per_tensor_to_int8(input: torch.Tensor, scale_inv: torch.Tensor,
     with _DeviceGuard(input):
         if _is_dense(input):
             out = torch.empty_like(input, dtype=torch.int8)
-            _lib.check(lib.mixdq_quant_i8_static(input.data_ptr(), input.numel(),
-                                                 scale_inv.data_ptr(), zero_point.data_ptr(),
-                                                 out.data_ptr(), _stream(input)))
+            _launch("quant", lib.mixdq_quant_i8_static,
+                    (input.data_ptr(), input.numel(), scale_inv.data_ptr(), zero_point.data_ptr(),
+                     out.data_ptr()), input, keep=(input, scale_inv, zero_point, out),
+                    algo_bytes=3 * input.numel())
             return out
         return _quantize_view(input, scale_inv, zero_point)
 
@@ -110,28 +153,31 @@ def _quantize_view(x: torch.Tensor, scale_inv, zero_point) -> torch.Tensor:
     """Non-dense views. NHWC channel slices and [B, T', K] token slices go through the strided
     kernel in place; anything else is densified first."""
     lib = _lib.load()
-    st = _stream(x)
+    keep = (x, scale_inv, zero_point)
     if x.dim() == 4 and x.stride(1) == 1 and x.stride(3) >= x.size(1) \
             and x.stride(2) == x.size(3) * x.stride(3) and x.stride(0) == x.size(2) * x.stride(2):
         # channel slice of an NHWC tensor -> dense NHWC int8 (logical NCHW, channels_last)
         n, c, h, w = x.shape
         out = torch.empty((n, c, h, w), dtype=torch.int8, device=x.device,
                           memory_format=torch.channels_last)
-        _lib.check(lib.mixdq_quant_i8_static_strided(
-            x.data_ptr(), 1, n * h * w, c, 0, x.stride(3), scale_inv.data_ptr(),
-            zero_point.data_ptr(), out.data_ptr(), c, st))
+        _launch("quant", lib.mixdq_quant_i8_static_strided,
+                (x.data_ptr(), 1, n * h * w, c, 0, x.stride(3), scale_inv.data_ptr(),
+                 zero_point.data_ptr(), out.data_ptr(), c), x, keep=keep + (out,),
+                algo_bytes=3 * out.numel())
         return out
     if x.dim() == 3 and x.stride(2) == 1:
         b, t, k = x.shape
         out = torch.empty((b, t, k), dtype=torch.int8, device=x.device)
-        _lib.check(lib.mixdq_quant_i8_static_strided(
-            x.data_ptr(), b, t, k, x.stride(0), x.stride(1), scale_inv.data_ptr(),
-            zero_point.data_ptr(), out.data_ptr(), k, st))
+        _launch("quant", lib.mixdq_quant_i8_static_strided,
+                (x.data_ptr(), b, t, k, x.stride(0), x.stride(1), scale_inv.data_ptr(),
+                 zero_point.data_ptr(), out.data_ptr(), k), x, keep=keep + (out,),
+                algo_bytes=3 * out.numel())
         return out
     xc = x.contiguous()
     out = torch.empty_like(xc, dtype=torch.int8)
-    _lib.check(lib.mixdq_quant_i8_static(xc.data_ptr(), xc.numel(), scale_inv.data_ptr(),
-                                         zero_point.data_ptr(), out.data_ptr(), st))
+    _launch("quant", lib.mixdq_quant_i8_static,
+            (xc.data_ptr(), xc.numel(), scale_inv.data_ptr(), zero_point.data_ptr(),
+             out.data_ptr()), xc, keep=(xc, scale_inv, zero_point, out), algo_bytes=3 * xc.numel())
     return out
 
 
@@ -149,20 +195,22 @@ def quantize_to_nhwc(input: torch.Tensor, scale_inv: torch.Tensor, zero_point: t
     csel = c_end - c_begin
     out = torch.empty((n, csel, h, w), dtype=torch.int8, device=input.device,
                       memory_format=torch.channels_last)
+    keep = (input, scale_inv, zero_point, out)
     with _DeviceGuard(input):
-        st = _stream(input)
         nhwc = input.stride(1) == 1 and input.stride(2) == w * input.stride(3) \
             and input.stride(0) == h * input.stride(2)
         if nhwc:
             base = input.data_ptr() + 2 * c_begin
-            _lib.check(lib.mixdq_quant_i8_static_strided(
-                base, 1, n * h * w, csel, 0, input.stride(3), scale_inv.data_ptr(),
-                zero_point.data_ptr(), out.data_ptr(), csel, st))
+            _launch("quant", lib.mixdq_quant_i8_static_strided,
+                    (base, 1, n * h * w, csel, 0, input.stride(3), scale_inv.data_ptr(),
+                     zero_point.data_ptr(), out.data_ptr(), csel), input, keep=keep,
+                    algo_bytes=3 * out.numel())
         else:
             strides = _c_int64_4(*input.stride())
-            _lib.check(lib.mixdq_quant_i8_nchw2nhwc(
-                input.data_ptr(), n, c, h, w, strides, c_begin, c_end, scale_inv.data_ptr(),
-                zero_point.data_ptr(), out.data_ptr(), st))
+            _launch("quant", lib.mixdq_quant_i8_nchw2nhwc,
+                    (input.data_ptr(), n, c, h, w, strides, c_begin, c_end, scale_inv.data_ptr(),
+                     zero_point.data_ptr(), out.data_ptr()), input, keep=keep + (strides,),
+                    algo_bytes=3 * out.numel())
     return out
 
 
@@ -193,9 +241,9 @@ def quantize_per_tensor_dynamic(input: torch.Tensor) -> Tuple[torch.Tensor, torc
     qp = torch.empty(2, dtype=torch.float32, device=x.device)
     with _DeviceGuard(x):
         ws = _dynamic_workspace(x.device)
-        _lib.check(lib.mixdq_quant_i8_dynamic(x.data_ptr(), x.numel(), qp.data_ptr(),
-                                              qp.data_ptr() + 4, out.data_ptr(), ws.data_ptr(),
-                                              _stream(x)))
+        _launch("quant_dyn", lib.mixdq_quant_i8_dynamic,
+                (x.data_ptr(), x.numel(), qp.data_ptr(), qp.data_ptr() + 4, out.data_ptr(),
+                 ws.data_ptr()), x, kernels=2, keep=(x, qp, out, ws), algo_bytes=3 * x.numel())
     return out, qp[0], qp[1]
 
 
@@ -255,9 +303,11 @@ def qlinear_w8_a8_ohalf(input_int8, weight_int8, weight_scale, input_scale, inpu
     out = torch.empty((*input_int8.shape[:-1], N), dtype=torch.float16, device=a.device)
     lib = _lib.load()
     with _DeviceGuard(a):
-        _lib.check(lib.mixdq_gemm_w8a8_f16(a.data_ptr(), K, w.data_ptr(), bias0.data_ptr(),
-                                           scale.data_ptr(), _ptr(bias), out.data_ptr(), N,
-                                           M, N, K, _ptr(_acc_out), _stream(a)))
+        _launch("gemm", lib.mixdq_gemm_w8a8_f16,
+                (a.data_ptr(), K, w.data_ptr(), bias0.data_ptr(), scale.data_ptr(), _ptr(bias),
+                 out.data_ptr(), N, M, N, K, _ptr(_acc_out)), a,
+                keep=(a, w, bias0, scale, bias, out, _acc_out),
+                algo_bytes=_gemm_bytes(M, N, K, N * K), algo_ops=2 * M * N * K)
     return out
 
 
@@ -275,11 +325,14 @@ def qlinear_w8_a8_ohalf_dynamic(input_int8, weight_int8, weight_scale, input_sca
     out = torch.empty((*input_int8.shape[:-1], N), dtype=torch.float16, device=a.device)
     lib = _lib.load()
     with _DeviceGuard(a):
-        _lib.check(lib.mixdq_gemm_w8a8_f16_dyn(
-            a.data_ptr(), K, w.data_ptr(), weight_scale.data_ptr(),
-            weight_sum_by_input_channels.data_ptr(), input_scale.data_ptr(),
-            input_zero_point.data_ptr(), _ptr(bias), out.data_ptr(), N, M, N, K,
-            _ptr(_acc_out), _stream(a)))
+        _launch("gemm", lib.mixdq_gemm_w8a8_f16_dyn,
+                (a.data_ptr(), K, w.data_ptr(), weight_scale.data_ptr(),
+                 weight_sum_by_input_channels.data_ptr(), input_scale.data_ptr(),
+                 input_zero_point.data_ptr(), _ptr(bias), out.data_ptr(), N, M, N, K,
+                 _ptr(_acc_out)), a,
+                keep=(a, w, weight_scale, weight_sum_by_input_channels, input_scale,
+                      input_zero_point, bias, out, _acc_out),
+                algo_bytes=_gemm_bytes(M, N, K, N * K), algo_ops=2 * M * N * K)
     return out
 
 
@@ -296,9 +349,11 @@ def qlinear_w4_a8_ohalf(input_int8, weight_packed, scale, bias0, bias=None,
     out = torch.empty((*input_int8.shape[:-1], N), dtype=torch.float16, device=a.device)
     lib = _lib.load()
     with _DeviceGuard(a):
-        _lib.check(lib.mixdq_gemm_w4a8_f16(a.data_ptr(), K, w.data_ptr(), bias0.data_ptr(),
-                                           scale.data_ptr(), _ptr(bias), out.data_ptr(), N,
-                                           M, N, K, _ptr(_acc_out), _stream(a)))
+        _launch("gemm_w4", lib.mixdq_gemm_w4a8_f16,
+                (a.data_ptr(), K, w.data_ptr(), bias0.data_ptr(), scale.data_ptr(), _ptr(bias),
+                 out.data_ptr(), N, M, N, K, _ptr(_acc_out)), a,
+                keep=(a, w, bias0, scale, bias, out, _acc_out),
+                algo_bytes=_gemm_bytes(M, N, K, N * K // 2), algo_ops=2 * M * N * K)
     return out
 
 
@@ -398,10 +453,13 @@ def qconv2d_w8_a8_ohalf(input_int8, weight_int8, weight_scale, input_scale, inpu
                       memory_format=torch.channels_last)
     lib = _lib.load()
     with _DeviceGuard(x):
-        _lib.check(lib.mixdq_conv_w8a8_f16(
-            x.data_ptr(), pitch, wt.data_ptr(), scale.data_ptr(), _ptr(wsum),
-            _ptr(bias0) if padding == 0 else None, input_zero_point.data_ptr(), _ptr(bias),
-            out.data_ptr(), n, h, w, c, k, r, s, stride, padding, _ptr(_acc_out), _stream(x)))
+        _launch("conv", lib.mixdq_conv_w8a8_f16,
+                (x.data_ptr(), pitch, wt.data_ptr(), scale.data_ptr(), _ptr(wsum),
+                 _ptr(bias0) if padding == 0 else None, input_zero_point.data_ptr(), _ptr(bias),
+                 out.data_ptr(), n, h, w, c, k, r, s, stride, padding, _ptr(_acc_out)), x,
+                keep=(x, wt, scale, wsum, bias0, input_zero_point, bias, out, _acc_out),
+                algo_bytes=_gemm_bytes(n * p * q, k, c * h * w // max(p * q, 1), k * c * r * s),
+                algo_ops=2 * n * p * q * k * c * r * s)
     return out
 
 
@@ -424,8 +482,12 @@ def qconv1x1_split_w8_a8_ohalf(xa_int8, wa_int8, scale_a, bias0_a, xb_int8, wb_i
                       memory_format=torch.channels_last)
     lib = _lib.load()
     with _DeviceGuard(xa_int8):
-        _lib.check(lib.mixdq_conv1x1_split_w8a8_f16(
-            xa_int8.data_ptr(), pa, wa.data_ptr(), ca, bias0_a.data_ptr(), scale_a.data_ptr(),
-            xb_int8.data_ptr(), pb, wb.data_ptr(), cb, bias0_b.data_ptr(), scale_b.data_ptr(),
-            _ptr(bias), out.data_ptr(), k, n * h * w, k, _stream(xa_int8)))
+        m = n * h * w
+        _launch("conv_split", lib.mixdq_conv1x1_split_w8a8_f16,
+                (xa_int8.data_ptr(), pa, wa.data_ptr(), ca, bias0_a.data_ptr(), scale_a.data_ptr(),
+                 xb_int8.data_ptr(), pb, wb.data_ptr(), cb, bias0_b.data_ptr(), scale_b.data_ptr(),
+                 _ptr(bias), out.data_ptr(), k, m, k), xa_int8,
+                keep=(xa_int8, wa, bias0_a, scale_a, xb_int8, wb, bias0_b, scale_b, bias, out),
+                algo_bytes=_gemm_bytes(m, k, ca + cb, k * (ca + cb)) + 8 * k,
+                algo_ops=2 * m * k * (ca + cb))
     return out

@@ -1,0 +1,278 @@
+"""Host-side logic on CPU: from_float buffers against the reference's (golden), bit-config
+registration, convert(), split derivation, the UNet skeleton's layer inventory."""
+import json
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+from torch.ao.quantization import PlaceholderObserver, QConfig
+
+from mixdq_b200 import mixdq, quantize
+from mixdq_b200.nn import QuantizedConv2d, QuantizedLinear
+from mixdq_b200.nn import utils as U
+from mixdq_b200.unet import build_unet
+
+
+def _load(path):
+    z = np.load(path, allow_pickle=False)
+    return {k: torch.from_numpy(z[k]) if z[k].dtype.kind != "U" else str(z[k]) for k in z.files}
+
+
+@pytest.fixture(scope="module")
+def ref(golden_dir):
+    return _load(golden_dir / "ref_from_float.npz")
+
+
+def _ckpt(g):
+    ck = {}
+    for k in g:
+        if k.startswith("ckpt."):
+            name, field = k[5:].rsplit(".", 1)
+            ck.setdefault(name, {})[field] = g[k]
+    return ck
+
+
+def _prep(mod, name, w_dtype=torch.qint8, a_dtype=torch.qint8, w_bit=8, a_bit=8):
+    mod.qconfig = QConfig(activation=PlaceholderObserver.with_args(dtype=a_dtype),
+                          weight=PlaceholderObserver.with_args(dtype=w_dtype))
+    mod.module_name = name
+    mod.w_bit = w_bit
+    if a_bit is not None:
+        mod.a_bit = a_bit
+    return mod
+
+
+def _float_mod(g, tag, cls, *a, **kw):
+    m = cls(*a, **kw)
+    with torch.no_grad():
+        m.weight.copy_(g[tag + ".weight"])
+        m.bias.copy_(g[tag + ".bias"])
+    return m
+
+
+@pytest.mark.parametrize("tag", ["linear", "conv_p1", "conv_p0", "conv_split"])
+def test_from_float_state_dict_equals_reference(ref, tag):
+    """Same buffer names and bit-identical values as the reference's from_float run on the
+    shipped new_ckpt.pth (SURVEY §8(b) 'Module buffers')."""
+    ck = _ckpt(ref)
+    name = ref[tag + ".name"]
+    if tag == "linear":
+        fm = _float_mod(ref, tag, nn.Linear, 32, 1280)
+        q = QuantizedLinear.from_float(_prep(fm, name), ckpt=ck)
+    elif tag == "conv_p1":
+        fm = _float_mod(ref, tag, nn.Conv2d, 4, 320, 3, padding=1)
+        q = QuantizedConv2d.from_float(_prep(fm, name), ckpt=ck)
+    elif tag == "conv_p0":
+        fm = _float_mod(ref, tag, nn.Conv2d, 32, 640, 1)
+        q = QuantizedConv2d.from_float(_prep(fm, name), ckpt=ck)
+    else:
+        fm = _float_mod(ref, tag, nn.Conv2d, 48, 320, 1)
+        q = QuantizedConv2d.from_float(_prep(fm, name), split=int(ref[tag + ".split"]), ckpt=ck)
+    assert q.valid_for_acceleration == bool(ref[tag + ".valid"])
+    want = {k[len(tag) + 5:]: v for k, v in ref.items() if k.startswith(tag + ".buf.")}
+    got = q.state_dict()
+    assert set(got) == set(want)
+    for k, v in want.items():
+        assert got[k].dtype == v.dtype, k
+        assert torch.equal(got[k], v), k
+    assert q._get_name() in ("QuantizedLinearW8A8", "QuantizedConv2dW8A8")
+
+
+def test_fp_fallback_gates(ref):
+    ck = _ckpt(ref)
+    name = ref["linear.name"]
+    # activation left fp16 (layer absent from the act yaml) -> FP fallback, as the reference
+    fm = _float_mod(ref, "linear", nn.Linear, 32, 1280)
+    q = QuantizedLinear.from_float(_prep(fm, name, a_dtype=torch.float16, a_bit=None), ckpt=ck)
+    assert not q.valid_for_acceleration and q._get_name() == "QuantizedLinearFPFallback"
+    assert set(q.state_dict()) == {"weight", "bias"}
+    x = torch.randn(3, 32)
+    assert torch.equal(q(x), torch.nn.functional.linear(x, fm.weight, fm.bias))
+    # 4-bit activations are not accelerated (reference nn/Linear.py:28-36)
+    q = QuantizedLinear.from_float(_prep(fm, name, a_dtype=torch.quint4x2, a_bit=4), ckpt=ck)
+    assert not q.valid_for_acceleration
+    # misaligned features -> warning + fallback (nn/Linear.py:37-43)
+    odd = nn.Linear(30, 1280)
+    q = QuantizedLinear.from_float(_prep(odd, name), ckpt=ck)
+    assert not q.valid_for_acceleration
+
+
+def test_w4_linear_packs_signed_nibbles(ref):
+    ck = _ckpt(ref)
+    name = ref["linear.name"]
+    fm = _float_mod(ref, "linear", nn.Linear, 32, 1280)
+    q = QuantizedLinear.from_float(_prep(fm, name, w_dtype=torch.quint4x2, w_bit=4), ckpt=ck)
+    assert q.valid_for_acceleration and q._get_name() == "QuantizedLinearW4A8"
+    assert q.weight_int4.shape == (1280, 16) and q.weight_int4.dtype == torch.uint8
+    codes = U.unpack_int4(q.weight_int4)
+    assert codes.min() >= -8 and codes.max() <= 7
+    # 4-bit scales are row 1 of delta_list (bit_idx = log2(4)-1)
+    assert torch.equal(q.weight_scales, ck[name + ".weight_quantizer"]["delta_list"][1].float())
+    assert torch.equal(q.weight_sum_by_input_channels, codes.float().sum(1))
+
+
+def test_get_quant_para_shift_and_index(ref):
+    ck = _ckpt(ref)
+    s, z, s0, z0 = U.get_quant_para(ck, 8, "conv_in", "act")
+    assert s0 is None and z0 is None
+    assert float(z) == float(ck["conv_in.act_quantizer"]["zero_point_list"][2]) - 128
+    s4, z4, _, _ = U.get_quant_para(ck, 4, "conv_in", "act")
+    assert float(s4) == float(ck["conv_in.act_quantizer"]["delta_list"][1])
+    with pytest.raises(KeyError):
+        U.get_quant_para(ck, 8, "no.such.layer", "weight")
+
+
+def test_sdxl_skeleton_matches_reference_inventory(golden_dir):
+    """794 quantizable leaves, names == the reference's YAML keys, Cout == ckpt entries."""
+    cfg = json.loads((golden_dir / "bit_configs.json").read_text())
+    summary = json.loads((golden_dir / "ckpt_summary.json").read_text())
+    with torch.device("meta"):
+        unet = build_unet("sdxl-turbo")
+    layers = unet.quantizable_layers()
+    assert sorted(n for n, _ in layers) == cfg["names"]
+    assert sum(isinstance(m, nn.Linear) for _, m in layers) == 743
+    assert sum(isinstance(m, nn.Conv2d) for _, m in layers) == 51
+    for n, m in layers:
+        assert summary[n + ".weight_quantizer"][0] == m.weight.shape[0]
+    assert sum(m.weight.numel() for _, m in layers) == 2_565_857_280 or \
+        abs(sum(m.weight.numel() for _, m in layers) / 1e9 - 2.566) < 2e-3
+    # split list of the reference (kernels/quantize.py:61), in traversal order
+    splits = quantize.derive_up_block_splits(unet)
+    assert list(splits.values()) == quantize._SPLIT
+    assert set(k + ".act_quantizer_0" for k in splits) == {k for k in summary if k.endswith("act_quantizer_0")}
+    # BOS layers
+    bos = json.loads((golden_dir / "bos_shapes.json").read_text())
+    attn2_kv = [n for n, _ in layers if "attn2" in n and ("to_k" in n or "to_v" in n)]
+    assert sorted(attn2_kv) == sorted(bos)
+    mods = dict(layers)
+    for n, shp in bos.items():
+        assert shp == [1, 1, mods[n].weight.shape[0]]
+
+
+def test_sd_turbo_skeleton_counts():
+    with torch.device("meta"):
+        unet = build_unet("sd-turbo")
+    layers = unet.quantizable_layers()
+    assert len(layers) == 282
+    assert abs(sum(m.weight.numel() for _, m in layers) / 1e9 - 0.866) < 2e-3
+    assert list(quantize.derive_up_block_splits(unet).values()) == \
+        [1280] * 7 + [640, 640, 640, 320, 320]
+
+
+def test_packaged_bit_configs():
+    w8 = mixdq.load_bit_config("weight/weight_8.00.yaml")
+    assert len(w8) == 794 and sorted(set(w8.values())) == [4, 8]
+    assert sum(v == 4 for v in w8.values()) == 4
+    a8 = mixdq.load_bit_config("./cfgs/act/act_8.00.yaml")
+    assert len(a8) == 785 and "conv_in" not in a8 and "conv_out" not in a8
+    w5 = mixdq.load_bit_config("weight/weight_5.02.yaml")
+    assert (sum(v == 8 for v in w5.values()), sum(v == 4 for v in w5.values()),
+            sum(v == 2 for v in w5.values())) == (401, 246, 147)
+    with pytest.raises(FileNotFoundError):
+        mixdq.load_bit_config("weight/nope.yaml")
+
+
+def test_yaml_file_config_with_model_prefix(tmp_path):
+    p = tmp_path / "w.yaml"
+    p.write_text("model.conv_in: 8\nmodel.conv_out: 4\n")
+    assert mixdq.load_bit_config(str(p)) == {"conv_in": 8, "conv_out": 4}
+
+
+def _tiny_quantized(dynamic=True, a_config="uniform"):
+    unet = build_unet("tiny", seed=1)
+    names = [n for n, _ in unet.quantizable_layers()]
+    args = SimpleNamespace(w_config={"model." + n: 8 for n in names},
+                           a_config=None if a_config is None else {"model." + n: 8 for n in names})
+    return unet, names, args
+
+
+def test_quantize_unet_tiny_dynamic_cpu():
+    unet, names, args = _tiny_quantized()
+    mixdq.quantize_unet(unet, args, ckpt=None, bos=False, bos_dict=None)
+    mods = dict(unet.named_modules())
+    for n in names:
+        assert isinstance(mods[n], (QuantizedLinear, QuantizedConv2d)), n
+        assert mods[n].valid_for_acceleration, n
+        assert not hasattr(mods[n], "qconfig")
+    sc = mods["up_blocks.0.resnets.0.conv_shortcut"]
+    assert sc.split == 128 and sc.weight_int.shape[1] == 128 and sc.weight_int_0.shape[1] == 128
+    assert mods["up_blocks.1.resnets.1.conv_shortcut"].split == 64
+    # weights are buffers, not parameters
+    assert all(not isinstance(m, (nn.Linear, nn.Conv2d)) for m in unet.modules())
+    # non-fp16 input takes the dequantised fallback and stays close to the float layer
+    q = mods["time_embedding.linear_1"]
+    x = torch.randn(2, q.in_features)
+    ref_unet = build_unet("tiny", seed=1)
+    want = dict(ref_unet.named_modules())["time_embedding.linear_1"](x)
+    assert torch.allclose(q(x), want, atol=2e-2)
+
+
+def test_register_qconfig_unknown_name_raises():
+    unet, names, args = _tiny_quantized()
+    args.w_config["model.not_a_layer"] = 8
+    with pytest.raises(RuntimeError, match="weight yaml"):
+        mixdq.register_qconfig_from_input_files(unet, args, bos=False, bos_dict=None)
+    unet, names, args = _tiny_quantized()
+    args.a_config["model.not_a_layer"] = 8
+    with pytest.raises(RuntimeError, match="act yaml"):
+        mixdq.register_qconfig_from_input_files(unet, args, bos=False, bos_dict=None)
+
+
+def test_convert_twice_does_not_walk_off_split_list():
+    """The reference keeps the split position in a never-reset global (kernels/quantize.py:64), so a
+    second convert() in one process indexes past the 9-entry list; here every convert() starts
+    fresh, and an architecture-derived `.split` attribute takes precedence over the list."""
+    seen = []
+
+    class Recorder(nn.Module):
+        @classmethod
+        def from_float(cls, mod, split=0, ckpt=None):
+            seen.append((mod.module_name, split))
+            return cls()
+
+    def tree():
+        root = nn.Module()
+        root.up_blocks = nn.ModuleList()
+        for b in range(3):
+            blk = nn.Module()
+            blk.resnets = nn.ModuleList()
+            for i in range(3):
+                r = nn.Module()
+                r.conv_shortcut = nn.Conv2d(4, 4, 1)
+                r.conv_shortcut.qconfig = object()
+                r.conv_shortcut.module_name = f"up_blocks.{b}.resnets.{i}.conv_shortcut"
+                blk.resnets.append(r)
+            root.up_blocks.append(blk)
+        return root
+
+    for _ in range(2):
+        seen.clear()
+        quantize.convert(tree(), mapping={nn.Conv2d: Recorder}, inplace=True, remove_qconfig=False)
+        assert [s for _, s in seen] == quantize._SPLIT
+    t = tree()
+    t.up_blocks[0].resnets[0].conv_shortcut.split = 96
+    seen.clear()
+    quantize.convert(t, mapping={nn.Conv2d: Recorder}, inplace=True, remove_qconfig=False)
+    assert seen[0][1] == 96 and seen[1][1] == quantize._SPLIT[0]
+
+
+def test_bos_registration():
+    unet, names, args = _tiny_quantized()
+    ehs = torch.randn(1, 77, unet.cfg.cross_attention_dim)
+    bos_dict = mixdq.compute_bos_dict(unet, ehs)
+    assert all(v.shape[:2] == (1, 1) for v in bos_dict.values()) and len(bos_dict) == 8
+    mixdq.quantize_unet(unet, args, ckpt=None, bos=True, bos_dict=bos_dict)
+    m = dict(unet.named_modules())["mid_block.attentions.0.transformer_blocks.0.attn2.to_k"]
+    assert m.bos is True and "bos_pre_computed" in m.state_dict()
+
+
+def test_node_mappings_match_reference_workflow():
+    assert set(mixdq.NODE_CLASS_MAPPINGS) == {"Mixdq", "LoadPipe", "OrgGen", "MixdqIntegral"}
+    assert mixdq.Mixdq.RETURN_TYPES == ("IMAGE", "STRING") and mixdq.Mixdq.FUNCTION == "mixdq_quant"
+    assert "org_pipeline" in mixdq.Mixdq.INPUT_TYPES()["required"]
+    import mixdq_extension.op.qconv2d as qc
+    import mixdq_extension.op.qlinear as ql
+    import mixdq_extension.op.quant as qq
+    assert callable(qc.qconv2d) and callable(ql.qlinear) and callable(qq.quantize_per_tensor)
