@@ -36,6 +36,11 @@ typedef void* mixdq_stream_t;      /* a cudaStream_t */
 typedef uint16_t mixdq_half_t;     /* IEEE binary16 bit pattern (__half)  */
 
 int         mixdq_abi_version(void);
+/* Register a device scratch buffer (caller-owned, >= 16-byte aligned) for CUDA device `device`:
+   split-K launches exchange their partial INT32 tiles through it (it stays L2-resident). Without
+   a workspace the contraction kernels never split K. Launches on different streams of one device
+   must not run concurrently while sharing a workspace. NULL / 0 unregisters. */
+int         mixdq_set_workspace(int device, void* ptr, int64_t bytes);
 const char* mixdq_strerror(int code);
 /* Name of the kernel family the last call on this thread dispatched to ("tcgen05", "simt", ...).
    Test/diagnostic aid only. */
@@ -43,6 +48,19 @@ const char* mixdq_last_path(void);
 /* Force every GEMM/conv onto the portable SIMT kernels (1) or restore heuristics (0). Test aid:
    lets the tcgen05 path be cross-checked against an independent implementation on the device. */
 void        mixdq_force_simt(int on);
+/* Force the output-tile width of the tcgen05 kernels (16/32/64/128/256; 0 = heuristic). Tuning and
+   test aid (also settable through the MIXDQ_FORCE_BN environment variable). */
+void        mixdq_debug_force_bn(int bn);
+/* Force the split-K factor (cluster size) of the tcgen05 kernels (1/2/4/8; 0 = heuristic). */
+void        mixdq_debug_force_splits(int splits);
+/* Give the tcgen05 kernels a device buffer of 8 uint64 PER CTA of the largest grid launched:
+   every CTA writes %globaltimer (ns) at {entry, setup done, first TMA, last TMA, first stage
+   landed, last MMA issued, accumulators ready, epilogue done}. NULL disables. Profiling aid. */
+void        mixdq_debug_set_timing_buffer(void* dev_ptr);
+/* Enable (1, default) / disable (0) programmatic dependent launch of the tcgen05 kernels. */
+void        mixdq_debug_set_pdl(int on);
+/* Profiling only (results are garbage): bit0 = skip the MMA issue, bit1 = skip the TMA loads. */
+void        mixdq_debug_set_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------
  * A1  static per-tensor activation quantisation, fp16 -> int8

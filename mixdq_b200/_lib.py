@@ -16,7 +16,9 @@ LIB_PATH = Path(__file__).resolve().parent / "libmixdq_b200.so"
 
 # every symbol include/mixdq_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "mixdq_abi_version", "mixdq_strerror", "mixdq_last_path", "mixdq_force_simt",
+    "mixdq_abi_version", "mixdq_set_workspace", "mixdq_debug_set_pdl", "mixdq_strerror", "mixdq_last_path", "mixdq_force_simt",
+    "mixdq_debug_force_bn", "mixdq_debug_force_splits", "mixdq_debug_set_timing_buffer",
+    "mixdq_debug_set_mode",
     "mixdq_quant_i8_static", "mixdq_quant_i8_static_strided", "mixdq_quant_i8_nchw2nhwc",
     "mixdq_quant_dynamic_ws_bytes", "mixdq_quant_i8_dynamic",
     "mixdq_gemm_w8a8_f16", "mixdq_gemm_w8a8_f16_dyn", "mixdq_gemm_w4a8_f16",
@@ -32,12 +34,24 @@ def _declare(lib: ctypes.CDLL) -> None:
     P = c_void_p
     lib.mixdq_abi_version.restype = c_int
     lib.mixdq_abi_version.argtypes = []
+    lib.mixdq_set_workspace.restype = c_int
+    lib.mixdq_set_workspace.argtypes = [c_int, P, c_int64]
+    lib.mixdq_debug_set_pdl.restype = None
+    lib.mixdq_debug_set_pdl.argtypes = [c_int]
     lib.mixdq_strerror.restype = c_char_p
     lib.mixdq_strerror.argtypes = [c_int]
     lib.mixdq_last_path.restype = c_char_p
     lib.mixdq_last_path.argtypes = []
     lib.mixdq_force_simt.restype = None
     lib.mixdq_force_simt.argtypes = [c_int]
+    lib.mixdq_debug_force_bn.restype = None
+    lib.mixdq_debug_force_bn.argtypes = [c_int]
+    lib.mixdq_debug_force_splits.restype = None
+    lib.mixdq_debug_force_splits.argtypes = [c_int]
+    lib.mixdq_debug_set_timing_buffer.restype = None
+    lib.mixdq_debug_set_timing_buffer.argtypes = [P]
+    lib.mixdq_debug_set_mode.restype = None
+    lib.mixdq_debug_set_mode.argtypes = [c_int]
 
     lib.mixdq_quant_i8_static.restype = c_int
     lib.mixdq_quant_i8_static.argtypes = [P, c_int64, P, P, P, P]

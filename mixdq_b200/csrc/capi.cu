@@ -84,6 +84,7 @@ static bool make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64
 // ------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------
+extern int g_use_pdl_fwd;
 template <int BN, int STAGES, int KIND>
 static int launch_tc(dim3 grid, const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a1,
                      const CUtensorMap& w1, const TcParams& p, cudaStream_t st) {
@@ -96,28 +97,113 @@ static int launch_tc(dim3 grid, const CUtensorMap& a, const CUtensorMap& w, cons
       return MIXDQ_ERR_CUDA;
     attr_set = true;
   }
-  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(a, w, a1, w1, p);
-  return cudaGetLastError() == cudaSuccess ? MIXDQ_OK : MIXDQ_ERR_CUDA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = L::DYN_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = grid.z;   // split-K ranks of one tile form a cluster
+  // programmatic dependent launch: prologue + weight prefetch overlap the preceding kernel
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl_fwd ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, w, a1, w1, p);
+  return e == cudaSuccess ? MIXDQ_OK : MIXDQ_ERR_CUDA;
 }
 
-// Tile-width heuristic: the widest BN that still yields at least ~one CTA per SM; B=1 shapes
-// (M = 256) are weight-bandwidth bound and need many narrow tiles in flight, B>=8 shapes are
-// tensor bound and take 128 x 256.
-static int pick_bn(int m_tiles, int N) {
-  static int env_bn = -1;
-  if (env_bn < 0) {
+// ------------------------------------------------------------------------------------------
+// Tile-shape heuristic: a cost model fitted to in-kernel %globaltimer stamps on B200
+// (tools/phase_timing.py, tools/sweep_shapes.py; numbers in ns):
+//   * ~1400 from the end of the preceding kernel to the first stage landing (PDL wait + TMA);
+//   * 340 per 128-byte k-block for BN <= 128 (4 tcgen05.mma at ~97 cycles issue floor + barrier
+//     round trip), 440 for BN = 256 (160 cycles per MMA) — independent of the tile width, so a
+//     CTA's mainloop is proportional to its K range only;
+//   * epilogue, no split: ~300 + 6.5 per tile column (dequant and ~26 B/clk/SM of stores overlap);
+//   * epilogue, split-K: 8.6 per column to write the INT32 partial tile, ~900 for the cluster
+//     barrier, 350 + 0.4 per owned element to sum the partials, 300 to store;
+//   * clusters of 4 / 8 CTAs with one CTA per SM fit ~132 / ~120 CTAs per wave.
+// Batch-1 layers with K <= 2048 come out unsplit with 64-wide tiles, long-K layers (ff.net.2,
+// 3x3 convolutions at 16x16 / 32x32) split 4-8 ways with 128/256-wide tiles, large-M layers get
+// 128x256 tiles.
+// ------------------------------------------------------------------------------------------
+static int g_force_bn = -1;
+static int g_force_splits = 0;
+int g_use_pdl_fwd = 1;
+extern "C" void mixdq_debug_set_pdl(int on) { g_use_pdl_fwd = on; }
+
+// split-K exchange workspace (registered by the host side; one per device)
+static int32_t* g_ws[64] = {nullptr};
+static int64_t g_ws_bytes[64] = {0};
+extern "C" int mixdq_set_workspace(int device, void* ptr, int64_t bytes) {
+  if (device < 0 || device >= 64 || bytes < 0) return MIXDQ_ERR_INVALID_ARG;
+  g_ws[device] = static_cast<int32_t*>(ptr);
+  g_ws_bytes[device] = ptr ? bytes : 0;
+  return MIXDQ_OK;
+}
+static int64_t current_ws(int32_t** ptr) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { *ptr = nullptr; return 0; }
+  *ptr = g_ws[dev];
+  return g_ws_bytes[dev];
+}
+extern "C" void mixdq_debug_force_bn(int bn) { g_force_bn = bn; }
+extern "C" void mixdq_debug_force_splits(int s) { g_force_splits = s; }
+static int g_dbg_mode = 0;
+extern "C" void mixdq_debug_set_mode(int mode) { g_dbg_mode = mode; }
+static unsigned long long* g_dbg = nullptr;
+extern "C" void mixdq_debug_set_timing_buffer(void* dev_ptr) {
+  g_dbg = static_cast<unsigned long long*>(dev_ptr);
+}
+
+static inline bool valid_bn(int bn) {
+  return bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256;
+}
+
+static void pick_tile(int m_tiles, int N, int total_kb, bool allow_split, int* bn_out,
+                      int* splits_out) {
+  int32_t* ws_ptr = nullptr;
+  const int64_t ws_bytes = current_ws(&ws_ptr);
+  if (g_force_bn < 0) {
     const char* e = getenv("MIXDQ_FORCE_BN");
-    env_bn = e ? atoi(e) : 0;
+    g_force_bn = e ? atoi(e) : 0;
+    const char* f = getenv("MIXDQ_FORCE_SPLITS");
+    if (f) g_force_splits = atoi(f);
   }
-  if (env_bn == 16 || env_bn == 32 || env_bn == 64 || env_bn == 128 || env_bn == 256) return env_bn;
+  const int kNumSm = 148;
+  double best = 1e30;
+  int best_bn = 32, best_s = 1;
   const int cands[5] = {256, 128, 64, 32, 16};
   for (int i = 0; i < 5; ++i) {
     const int bn = cands[i];
-    if (bn > 16 && bn / 2 >= N) continue;  // do not pick a tile twice as wide as the problem
-    const long ctas = static_cast<long>(m_tiles) * ((N + bn - 1) / bn);
-    if (ctas >= 132) return bn;
+    if (valid_bn(g_force_bn) && bn != g_force_bn) continue;
+    if (!valid_bn(g_force_bn) && bn > 16 && bn / 2 >= N) continue;  // tile twice as wide as N
+    const long tiles = static_cast<long>(m_tiles) * ((N + bn - 1) / bn);
+    for (int s = 1; s <= 8; s *= 2) {
+      if (g_force_splits > 0 && s != g_force_splits) continue;
+      if (s > 1 && (!allow_split || s > total_kb)) continue;
+      if (s > 1 && tiles * s * (128L * bn * 4) > ws_bytes) continue;   // needs the workspace
+      const long ctas = tiles * s;
+      const int cap = (s <= 2) ? kNumSm : (s == 4 ? 132 : 120);
+      const long waves = (ctas + cap - 1) / cap;
+      const int kb_per = (total_kb + s - 1) / s;
+      const double main = kb_per * (bn == 256 ? 440.0 : 340.0);
+      const double epi = (s == 1) ? 300.0 + 6.5 * bn
+                                  : 8.6 * bn + 900.0 + 350.0 + 0.4 * (128.0 / s) * bn + 300.0;
+      const double t = waves * (1400.0 + main + epi);
+      if (t < best) { best = t; best_bn = bn; best_s = s; }
+    }
   }
-  return (N >= 32) ? 32 : 16;
+  if (best >= 1e30) {  // forced combination not admissible: fall back to no split
+    best_bn = valid_bn(g_force_bn) ? g_force_bn : 32;
+    best_s = 1;
+  }
+  *bn_out = best_bn;
+  *splits_out = best_s;
 }
 
 template <int KIND>
@@ -162,17 +248,23 @@ static int gemm_common(const int8_t* A, int64_t lda, const int8_t* W, const floa
   }
 
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-  const int bn = pick_bn(m_tiles, N);
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  int bn, splits;
+  pick_tile(m_tiles, N, num_kb, true, &bn, &splits);
   CUtensorMap tmA, tmW;
   if (!make_tmap_2d(&tmA, A, K, M, lda, BLOCK_M)) return MIXDQ_ERR_CUDA;
   if (!make_tmap_2d(&tmW, W, K, N, K, bn)) return MIXDQ_ERR_CUDA;
   TcParams p{};
-  p.M = M; p.N = N; p.num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  p.dbg = g_dbg;
+  p.dbg_mode = g_dbg_mode;
+  p.splits = splits;
+  current_ws(&p.ws);
+  p.M = M; p.N = N; p.num_kb = num_kb;
   p.scale = p_scale; p.bias0 = p_bias0; p.a_scale = a_scale; p.a_zp = a_zp;
   p.bias = reinterpret_cast<const __half*>(bias);
   p.D = reinterpret_cast<__half*>(D); p.ldd = ldd; p.acc_out = acc_out;
-  dim3 grid(m_tiles, (N + bn - 1) / bn);
-  g_last_path = "tcgen05";
+  dim3 grid(m_tiles, (N + bn - 1) / bn, splits);
+  g_last_path = splits > 1 ? "tcgen05-splitk" : "tcgen05";
   return dispatch_tc<KIND_GEMM>(bn, grid, tmA, tmW, tmA, tmW, p, st);
 }
 
@@ -254,7 +346,9 @@ extern "C" int mixdq_conv_w8a8_f16(const int8_t* x, int64_t x_cpitch, const int8
   if (boxH == P) { boxN = BLOCK_M / (boxW * boxH); if (boxN > N) boxN = N; if (boxN < 1) boxN = 1; }
   const int tilesQ = 1, tilesP = (P + boxH - 1) / boxH, tilesN = (N + boxN - 1) / boxN;
   const int m_tiles = tilesQ * tilesP * tilesN;
-  const int bn = pick_bn(m_tiles, K);
+  const int kb_per_tap = (C + BLOCK_K - 1) / BLOCK_K;
+  int bn, splits;
+  pick_tile(m_tiles, K, R * S * kb_per_tap, true, &bn, &splits);
 
   CUtensorMap tmA, tmW;
   {
@@ -274,8 +368,12 @@ extern "C" int mixdq_conv_w8a8_f16(const int8_t* x, int64_t x_cpitch, const int8
     if (!make_tmap(&tmW, w, 3, dims, strides, box)) return MIXDQ_ERR_CUDA;
   }
   TcParams p{};
+  p.dbg = g_dbg;
+  p.dbg_mode = g_dbg_mode;
+  p.splits = splits;
+  current_ws(&p.ws);
   p.M = N * P * Q; p.N = K;
-  p.kb_per_tap = (C + BLOCK_K - 1) / BLOCK_K;
+  p.kb_per_tap = kb_per_tap;
   p.num_kb = R * S * p.kb_per_tap;
   p.S = S; p.pad = pad; p.NB = N; p.H = H; p.W = W; p.P = P; p.Q = Q;
   p.boxW = boxW; p.boxH = boxH; p.boxN = boxN; p.tilesQ = tilesQ; p.tilesP = tilesP;
@@ -284,8 +382,8 @@ extern "C" int mixdq_conv_w8a8_f16(const int8_t* x, int64_t x_cpitch, const int8
   p.scale = scale; p.bias0 = pad > 0 ? wsum_krs : bias0_k; p.a_zp = zp;
   p.bias = reinterpret_cast<const __half*>(bias);
   p.D = reinterpret_cast<__half*>(y); p.ldd = K; p.acc_out = acc_out;
-  dim3 grid(m_tiles, (K + bn - 1) / bn);
-  g_last_path = "tcgen05";
+  dim3 grid(m_tiles, (K + bn - 1) / bn, splits);
+  g_last_path = splits > 1 ? "tcgen05-splitk" : "tcgen05";
   return dispatch_tc<KIND_CONV>(bn, grid, tmA, tmW, tmA, tmW, p, st);
 }
 
@@ -319,13 +417,18 @@ extern "C" int mixdq_conv1x1_split_w8a8_f16(const int8_t* xa, int64_t lda, const
     return simt_gemm_launch(g, st) == 0 ? MIXDQ_OK : MIXDQ_ERR_CUDA;
   }
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-  int bn = pick_bn(m_tiles, K);
+  int bn, splits_unused;
+  pick_tile(m_tiles, K, (Ca + BLOCK_K - 1) / BLOCK_K + (Cb + BLOCK_K - 1) / BLOCK_K, false, &bn,
+            &splits_unused);
   if (bn > 128) bn = 128;  // two accumulators: 2 x BN TMEM columns, keep smem params small
   CUtensorMap tmA, tmW, tmA1, tmW1;
   if (!make_tmap_2d(&tmA, xa, Ca, M, lda, BLOCK_M) || !make_tmap_2d(&tmW, wa, Ca, K, Ca, bn) ||
       !make_tmap_2d(&tmA1, xb, Cb, M, ldb, BLOCK_M) || !make_tmap_2d(&tmW1, wb, Cb, K, Cb, bn))
     return MIXDQ_ERR_CUDA;
   TcParams p{};
+  p.dbg = g_dbg;
+  p.dbg_mode = g_dbg_mode;
+  p.splits = 1;
   p.M = M; p.N = K;
   p.num_kb = (Ca + BLOCK_K - 1) / BLOCK_K;
   p.num_kb1 = (Cb + BLOCK_K - 1) / BLOCK_K;

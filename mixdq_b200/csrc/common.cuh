@@ -30,6 +30,49 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ------------------------------------------------------------------------------------------
+// thread-block clusters / distributed shared memory
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// full cluster barrier with release/acquire ordering (covers st.shared::cluster traffic)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `local_smem_addr` in the shared memory of CTA `cta` of this cluster
+__device__ __forceinline__ uint32_t dsmem_map(uint32_t local_smem_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void dsmem_st_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                            uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b),
+               "r"(c), "r"(d)
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// programmatic dependent launch
+// ------------------------------------------------------------------------------------------
+// Block until the preceding kernel of the stream (the programmatic-dependency primary) has
+// completed and flushed its memory; a no-op when the launch carries no programmatic dependency.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+// Allow the dependent (next PDL-enabled) kernel to be scheduled.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// named barrier among the 256 epilogue threads of the tcgen05 kernels
+__device__ __forceinline__ void epi_bar_sync() {
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

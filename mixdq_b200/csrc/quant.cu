@@ -72,6 +72,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kQuantThreads)
 quant_flat_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int64_t numel,
                   const float* __restrict__ pa, const float* __restrict__ pb) {
+  pdl_launch_dependents();   // the GEMM/conv that consumes q may start its weight prefetch now
   const QParams p = load_qparams<MODE>(pa, pb);
   const int64_t nvec = numel >> 3;
   const int4* xv = reinterpret_cast<const int4*>(x);
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(kQuantThreads)
 quant_strided_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int64_t rows,
                      int64_t d1, int64_t cols, int64_t s0, int64_t s1, int64_t out_pitch,
                      const float* __restrict__ pa, const float* __restrict__ pb) {
+  pdl_launch_dependents();
   const QParams p = load_qparams<MODE>(pa, pb);
   const int64_t cpr = VEC ? (cols >> 3) : cols;  // work items per row
   const int64_t total = rows * cpr;
@@ -140,6 +142,7 @@ quant_nchw2nhwc_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int
                        int H, int W, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
                        const float* __restrict__ pa, const float* __restrict__ pb) {
   __shared__ int8_t tile[kTrP][kTrC + 4];
+  pdl_launch_dependents();
   const QParams p = load_qparams<MODE>(pa, pb);
   const int HW = H * W;
   const int n = blockIdx.z;
@@ -180,37 +183,68 @@ quant_nchw2nhwc_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int
   }
 }
 
-// ---- dynamic: min/max reduction + qparam computation ----------------------------------------
+// ---- dynamic: ONE kernel = min/max reduction -> grid barrier -> quantise ---------------------
+// All CTAs are co-resident (grid <= 2 per SM), so a flag-based grid barrier is safe: every CTA
+// publishes its partial min/max, the last one to arrive computes (delta, z) and raises the flag,
+// the others spin on it with an acquire load. Each thread keeps its first kDynCache 16-byte
+// vectors in registers, so tensors up to 296*256*kDynCache*8 elements (4.8 M: every layer of the
+// batch-1 SDXL step) are read from memory exactly once; larger tensors are re-read (L2 hits).
 constexpr int kMaxPartials = 1024;
+constexpr int kDynCache = 8;
 struct DynWs {
-  unsigned int counter;
-  unsigned int pad[3];
+  unsigned int counter;   // arrivals at the barrier
+  unsigned int flag;      // raised by the last arriver once scale/zp are published
+  unsigned int done;      // CTAs that have consumed the flag (last one resets the workspace)
+  unsigned int pad;
   float2 partial[kMaxPartials];
 };
 
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void minmax_vec8(const int4& raw, float& mn, float& mx) {
+  const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 f = __half22float2(h2[j]);
+    mn = fminf(mn, fminf(f.x, f.y));
+    mx = fmaxf(mx, fmaxf(f.x, f.y));
+  }
+}
+
 __global__ void __launch_bounds__(kQuantThreads)
-minmax_kernel(const __half* __restrict__ x, int64_t numel, DynWs* __restrict__ ws,
-              float* __restrict__ scale_out, float* __restrict__ zp_out) {
+quant_dynamic_fused_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int64_t numel,
+                           DynWs* __restrict__ ws, float* __restrict__ scale_out,
+                           float* __restrict__ zp_out) {
+  pdl_launch_dependents();
   float mn = 0.0f, mx = 0.0f;  // qdiff clamps x_min <= 0 <= x_max (base_quantizer.py:155-158)
   const int64_t nvec = numel >> 3;
   const int4* xv = reinterpret_cast<const int4*>(x);
+  uint2* qv = reinterpret_cast<uint2*>(q);
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kQuantThreads;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kQuantThreads + threadIdx.x; i < nvec;
-       i += stride) {
-    int4 raw = __ldg(xv + i);
-    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * kQuantThreads + threadIdx.x;
+  int4 cache[kDynCache];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 f = __half22float2(h2[j]);
-      mn = fminf(mn, fminf(f.x, f.y));
-      mx = fmaxf(mx, fmaxf(f.x, f.y));
-    }
+  for (int u = 0; u < kDynCache; ++u) {
+    const int64_t i = i0 + u * stride;
+    if (i < nvec) { cache[u] = ld_stream16(xv + i); }
   }
-  const int64_t t = (nvec << 3) + static_cast<int64_t>(blockIdx.x) * kQuantThreads + threadIdx.x;
+#pragma unroll
+  for (int u = 0; u < kDynCache; ++u)
+    if (i0 + u * stride < nvec) minmax_vec8(cache[u], mn, mx);
+  for (int64_t i = i0 + kDynCache * stride; i < nvec; i += stride) minmax_vec8(__ldg(xv + i), mn, mx);
+  const int64_t t = (nvec << 3) + i0;   // scalar tail (numel % 8)
+  float tailv = 0.0f;
   if (t < numel) {
-    float f = __half2float(x[t]);
-    mn = fminf(mn, f);
-    mx = fmaxf(mx, f);
+    tailv = __half2float(x[t]);
+    mn = fminf(mn, tailv);
+    mx = fmaxf(mx, tailv);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -218,45 +252,78 @@ minmax_kernel(const __half* __restrict__ x, int64_t numel, DynWs* __restrict__ w
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   }
   __shared__ float smn[kQuantThreads / 32], smx[kQuantThreads / 32];
-  __shared__ bool is_last;
+  __shared__ float s_delta, s_z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) { smn[warp] = mn; smx[warp] = mx; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < kQuantThreads / 32; ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
-    ws->partial[blockIdx.x] = make_float2(mn, mx);
-    __threadfence();
-    const unsigned int done = atomicAdd(&ws->counter, 1u);
-    is_last = (done == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  mn = 0.0f; mx = 0.0f;
-  for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += kQuantThreads) {
-    float2 v = __ldcg(&ws->partial[i]);
-    mn = fminf(mn, v.x);
-    mx = fmaxf(mx, v.y);
-  }
+  if (warp == 0) {
+    mn = lane < kQuantThreads / 32 ? smn[lane] : 0.0f;
+    mx = lane < kQuantThreads / 32 ? smx[lane] : 0.0f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int o = 4; o > 0; o >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    unsigned int last = 0;
+    if (lane == 0) {
+      ws->partial[blockIdx.x] = make_float2(mn, mx);
+      __threadfence();
+      last = (atomicAdd(&ws->counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      __threadfence();
+      mn = 0.0f; mx = 0.0f;
+      for (int i = lane; i < static_cast<int>(gridDim.x); i += 32) {
+        const float2 v = __ldcg(&ws->partial[i]);
+        mn = fminf(mn, v.x);
+        mx = fmaxf(mx, v.y);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      if (lane == 0) {
+        // delta = (x_max - x_min) / (n_levels - 1); eps clamp (base_quantizer.py:178-182)
+        float delta = __fdiv_rn(__fsub_rn(mx, mn), 255.0f);
+        if (delta < 1e-6f) delta = 1e-6f;
+        // zero_point = round(-x_min / delta) (base_quantizer.py:187)
+        const float z = rintf(__fdiv_rn(-mn, delta));
+        *scale_out = delta;
+        *zp_out = z - 128.0f;
+        __threadfence();
+        st_release_u32(&ws->flag, 1u);
+      }
+    }
+    if (lane == 0) {
+      unsigned int spins = 0;
+      while (ld_acquire_u32(&ws->flag) == 0u) {
+        __nanosleep(40);
+        if (++spins > (1u << 24)) __trap();   // protocol bug: fail instead of hanging the device
+      }
+      s_delta = __ldcg(scale_out);
+      s_z = __ldcg(zp_out) + 128.0f;
+      // the last CTA to consume the flag leaves the workspace ready for the next call
+      if (atomicAdd(&ws->done, 1u) == gridDim.x - 1) {
+        ws->counter = 0; ws->done = 0;
+        __threadfence();
+        st_release_u32(&ws->flag, 0u);
+      }
+    }
   }
   __syncthreads();
-  if (lane == 0) { smn[warp] = mn; smx[warp] = mx; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < kQuantThreads / 32; ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
-    // delta = (x_max - x_min) / (n_levels - 1); eps clamp (base_quantizer.py:178-182)
-    float delta = __fdiv_rn(__fsub_rn(mx, mn), 255.0f);
-    if (delta < 1e-6f) delta = 1e-6f;
-    // zero_point = round(-x_min / delta) (base_quantizer.py:187)
-    const float z = rintf(__fdiv_rn(-mn, delta));
-    *scale_out = delta;
-    *zp_out = z - 128.0f;
-    ws->counter = 0;  // leave the workspace ready for the next call
+  QParams p;
+  p.a = s_delta;
+  p.b = s_z;
+#pragma unroll
+  for (int u = 0; u < kDynCache; ++u) {
+    const int64_t i = i0 + u * stride;
+    if (i < nvec) qv[i] = quant_vec8<kDynamicDiv>(cache[u], p);
   }
+  for (int64_t i = i0 + kDynCache * stride; i < nvec; i += stride)
+    qv[i] = quant_vec8<kDynamicDiv>(__ldg(xv + i), p);
+  if (t < numel) q[t] = static_cast<int8_t>(quant_one<kDynamicDiv>(tailv, p));
 }
 
 static inline int grid_for(int64_t items, int per_block, int max_blocks) {
@@ -356,12 +423,13 @@ extern "C" int mixdq_quant_i8_dynamic(const mixdq_half_t* x, int64_t numel, floa
                                       float* zp_out, int8_t* q, void* ws,
                                       mixdq_stream_t stream) {
   if (numel <= 0 || !x || !q || !scale_out || !zp_out || !ws) return MIXDQ_ERR_INVALID_ARG;
-  if (!aligned16(x)) return MIXDQ_ERR_ALIGNMENT;
+  if (!aligned16(x) || !aligned8(q)) return MIXDQ_ERR_ALIGNMENT;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __half* xh = reinterpret_cast<const __half*>(x);
-  int grid = grid_for(numel >> 3, kQuantThreads * 2, kMaxPartials);
-  minmax_kernel<<<grid, kQuantThreads, 0, st>>>(xh, numel, static_cast<DynWs*>(ws), scale_out,
-                                               zp_out);
+  // co-resident grid: at most 2 CTAs per SM (see quant_dynamic_fused_kernel)
+  int grid = grid_for(numel >> 3, kQuantThreads * 2, 148 * 2);
+  quant_dynamic_fused_kernel<<<grid, kQuantThreads, 0, st>>>(xh, q, numel, static_cast<DynWs*>(ws),
+                                                            scale_out, zp_out);
   MIXDQ_CHECK_LAUNCH();
-  return launch_flat<kDynamicDiv>(xh, numel, scale_out, zp_out, q, st);
+  return MIXDQ_OK;
 }

@@ -3,7 +3,8 @@
 //   tcgen05.mma.cta_group::1.kind::i8, 128 x BN x 32 per instruction, s32 accumulators in TMEM,
 //   A (activations) and W (weights) tiles staged by TMA into 128B-swizzled shared memory through
 //   a STAGES-deep mbarrier ring, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM
-//   allocator + single-thread MMA issuer, warps 2..5 = epilogue (tcgen05.ld -> dequant -> fp16).
+//   allocator + single-thread MMA issuer, warps 2..9 = epilogue (tcgen05.ld -> dequant -> fp16;
+//   two warps per TMEM lane quarter, each taking half of the tile's columns).
 //
 //   KIND_GEMM : A is a 2-D [M][K] matrix                       (reference qlinear, A2)
 //   KIND_CONV : A is the NHWC activation tensor; each k-block is one (r,s) filter tap x 128
@@ -13,6 +14,29 @@
 //               16-class x BN table built in shared memory by the epilogue warps
 //   KIND_SPLIT: two K-phases (two A/W operand pairs) into two TMEM accumulators, combined in the
 //               epilogue exactly like the reference's two fp16 convs + fp16 add (A6)
+//
+// Split-K over a thread-block cluster (p.splits > 1, cluster dims (1,1,splits)).
+//   Measured on B200 (tools/phase_timing.py): with both operands in shared memory one
+//   tcgen05.mma (M=128, K=32) occupies the tensor pipe ~160 cycles whatever N is — the A slab
+//   (128 rows x 32 B) is streamed from shared memory at one row per cycle — so a CTA's mainloop
+//   costs ~5 cycles per byte of K regardless of the tile width. Batch-1 UNet layers (M = 256)
+//   have far fewer output tiles than SMs and long K, hence: wide tiles (BN up to 256) for work
+//   per A-read, and the K range split across the CTAs of a cluster so that every SM streams a
+//   K-slice of A and W. The partial INT32 accumulators are reduce-scattered through an
+//   L2-resident global workspace (coalesced stores, one cluster barrier, coalesced .cg loads; a
+//   first version exchanged them with st.shared::cluster and measured ~8 B/clk — 4.8 us per
+//   128x128 tile): each CTA owns 128/splits rows of the tile, sums the partials exactly in
+//   int32 and applies the dequant epilogue — no atomics, bit-exact.
+//
+// Epilogue: TMEM rows are owned by lanes (lane == tile row), so storing straight to global memory
+//   is one 32-line scatter per instruction (measured 4.8 us for a 128x256 tile). Results are
+//   therefore staged as fp16 in shared memory (aliased onto the drained stage ring) and copied
+//   out with consecutive threads writing consecutive 16-byte chunks of a row.
+//
+// Programmatic dependent launch: the kernel is launched with programmatic stream serialization;
+//   barrier/TMEM setup and the weight (W) loads of the first STAGES k-blocks are issued before
+//   griddepcontrol.wait, so they overlap the tail of the preceding kernel (normally the
+//   activation-quantize kernel, which triggers launch_dependents at its entry).
 #pragma once
 #include "common.cuh"
 
@@ -23,13 +47,15 @@ enum { KIND_GEMM = 0, KIND_CONV = 1, KIND_SPLIT = 2 };
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 128;  // int8 elements = bytes = one 128B swizzle row
 constexpr int UMMA_K = 32;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;      // warp 0 TMA, warp 1 MMA/TMEM, warps 2..9 epilogue
+constexpr int EPI_THREADS = 256;
 
 struct TcParams {
   // problem
   int M, N;             // GEMM rows (conv: informational), output channels
   int num_kb;           // k-blocks of phase 0
   int num_kb1;          // k-blocks of phase 1 (KIND_SPLIT only)
+  int splits;           // split-K factor == cluster size along z (1 = no cluster reduction)
   // conv geometry (KIND_CONV)
   int kb_per_tap, S, pad;
   int NB, H, W, P, Q;   // batch, input H/W, output P/Q
@@ -48,13 +74,29 @@ struct TcParams {
   __half* D;
   int64_t ldd;
   int32_t* acc_out;       // optional raw accumulator dump [rows][N]
+  int32_t* ws;            // split-K exchange workspace: [CTA][BN/4][128][4] int32 (splits > 1)
+  unsigned long long* dbg; // optional phase timestamps (globaltimer ns), 8 slots per CTA
+  int dbg_mode;            // profiling only: bit0 = skip MMA issue, bit1 = skip TMA loads
 };
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// every CTA stamps its own 16 slots: dbg[(linear CTA id) * 16 + slot] (buffer sized by the caller)
+#define MIXDQ_DBG(slot)                                                                   \
+  do {                                                                                    \
+    if (p.dbg != nullptr)                                                                 \
+      p.dbg[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = \
+          gtime_ns();                                                                     \
+  } while (0)
 
 template <int BN, int STAGES, int KIND>
 struct TcSmem {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K;
   static constexpr int W_BYTES = BN * BLOCK_K;
-  static constexpr int TAB_PITCH = BN + 1;
+  static constexpr int TAB_PITCH = BN + 4;   // float4-aligned rows, classes land in different banks
   static constexpr int TAB_FLOATS = (KIND == KIND_CONV) ? 16 * TAB_PITCH : 0;
   static constexpr int PARAM_FLOATS = (KIND == KIND_SPLIT ? 5 : 3) * BN + TAB_FLOATS;
   static constexpr int OFF_A = 0;
@@ -65,7 +107,44 @@ struct TcSmem {
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024 B alignment
+  // fp16 output staging tile: 128 rows x (BN halves + 16 B pad), aliased onto the drained ring
+  static constexpr int OUT_PITCH = BN * 2 + 16;
+  static constexpr int OUT_BYTES = BLOCK_M * OUT_PITCH;
+  static_assert(OUT_BYTES <= OFF_PARAM, "staging tile must fit in the stage ring");
 };
+
+// Per-row geometry of the output tile (which output row / border class a tile row maps to).
+struct RowInfo {
+  bool ok;
+  int64_t out_row;
+  int cls;
+};
+
+template <int KIND>
+__device__ __forceinline__ RowInfo row_info(const TcParams& p, int row, int m0, int tn0, int tp0,
+                                            int tq0) {
+  RowInfo r;
+  r.cls = 0;
+  if (KIND == KIND_CONV) {
+    const int per_img = p.boxH * p.boxW;
+    const int dn = row / per_img;
+    const int rem = row - dn * per_img;
+    const int dh = rem / p.boxW, dw = rem - dh * p.boxW;
+    const int n = tn0 + dn, pp = tp0 + dh, qq = tq0 + dw;
+    r.ok = (dn < p.boxN) && (n < p.NB) && (pp < p.P) && (qq < p.Q);
+    r.out_row = (static_cast<int64_t>(n) * p.P + pp) * p.Q + qq;
+    if (p.has_table) {
+      const int h0 = pp - p.pad, w0 = qq - p.pad;
+      const int rc = (h0 < 0 ? 1 : 0) | (h0 + 2 >= p.H ? 2 : 0);
+      const int sc4 = (w0 < 0 ? 1 : 0) | (w0 + 2 >= p.W ? 2 : 0);
+      r.cls = rc * 4 + sc4;
+    }
+  } else {
+    r.ok = (m0 + row) < p.M;
+    r.out_row = m0 + row;
+  }
+  return r;
+}
 
 template <int BN, int STAGES, int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -95,6 +174,16 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tile0 = blockIdx.y * BN;
+  if (threadIdx.x == 0) MIXDQ_DBG(0);   // kernel entry
+  // let the next PDL-enabled kernel of the stream start its own prologue right away
+  pdl_launch_dependents();
+
+  // K range of this CTA (split-K rank == blockIdx.z == rank in the (1,1,splits) cluster)
+  const int splits = (KIND == KIND_SPLIT) ? 1 : p.splits;
+  const int krank = (splits > 1) ? static_cast<int>(blockIdx.z) : 0;
+  const int total_kb = p.num_kb + (KIND == KIND_SPLIT ? p.num_kb1 : 0);
+  const int kb_begin = (splits > 1) ? (krank * total_kb) / splits : 0;
+  const int kb_end = (splits > 1) ? ((krank + 1) * total_kb) / splits : total_kb;
 
   // tile origin
   int m0 = 0, tn0 = 0, tp0 = 0, tq0 = 0;
@@ -123,76 +212,109 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) MIXDQ_DBG(1);   // setup done (barriers, TMEM)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      const int total_kb = p.num_kb + (KIND == KIND_SPLIT ? p.num_kb1 : 0);
-      for (int kb = 0; kb < total_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* a_dst = sA + stage * L::A_BYTES;
+      const uint32_t a_bytes = (KIND == KIND_CONV) ? p.a_tx_bytes : static_cast<uint32_t>(L::A_BYTES);
+      auto load_w = [&](int kb, int stage) {
         uint8_t* w_dst = sW + stage * L::W_BYTES;
-        if (KIND == KIND_GEMM) {
-          mbar_expect_tx(&full_bar[stage], L::A_BYTES + L::W_BYTES);
-          tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BLOCK_K, m0);
-          tma_load_2d(w_dst, &tmW, &full_bar[stage], kb * BLOCK_K, n_tile0);
-        } else if (KIND == KIND_SPLIT) {
-          mbar_expect_tx(&full_bar[stage], L::A_BYTES + L::W_BYTES);
-          if (kb < p.num_kb) {
-            tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BLOCK_K, m0);
-            tma_load_2d(w_dst, &tmW, &full_bar[stage], kb * BLOCK_K, n_tile0);
-          } else {
-            const int k1 = kb - p.num_kb;
-            tma_load_2d(a_dst, &tmA1, &full_bar[stage], k1 * BLOCK_K, m0);
-            tma_load_2d(w_dst, &tmW1, &full_bar[stage], k1 * BLOCK_K, n_tile0);
-          }
+        if (KIND == KIND_CONV) {
+          const int tap = kb / p.kb_per_tap;
+          const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
+          tma_load_3d(w_dst, &tmW, &full_bar[stage], c0, tap, n_tile0);
+        } else if (KIND == KIND_SPLIT && kb >= p.num_kb) {
+          tma_load_2d(w_dst, &tmW1, &full_bar[stage], (kb - p.num_kb) * BLOCK_K, n_tile0);
         } else {
+          tma_load_2d(w_dst, &tmW, &full_bar[stage], kb * BLOCK_K, n_tile0);
+        }
+      };
+      auto load_a = [&](int kb, int stage) {
+        uint8_t* a_dst = sA + stage * L::A_BYTES;
+        if (KIND == KIND_CONV) {
           const int tap = kb / p.kb_per_tap;
           const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
           const int r = tap / p.S, s = tap - r * p.S;
-          mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + L::W_BYTES);
           tma_load_4d(a_dst, &tmA, &full_bar[stage], c0, tq0 - p.pad + s, tp0 - p.pad + r, tn0);
-          tma_load_3d(w_dst, &tmW, &full_bar[stage], c0, tap, n_tile0);
+        } else if (KIND == KIND_SPLIT && kb >= p.num_kb) {
+          tma_load_2d(a_dst, &tmA1, &full_bar[stage], (kb - p.num_kb) * BLOCK_K, m0);
+        } else {
+          tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BLOCK_K, m0);
+        }
+      };
+      const bool skip = (p.dbg_mode & 2) != 0;
+      // prologue: weights of the first ring-full of k-blocks do not depend on the preceding
+      // kernel -> issue them before the programmatic-dependency wait
+      const int npre = (kb_end - kb_begin) < STAGES ? (kb_end - kb_begin) : STAGES;
+      if (!skip) {
+        for (int i = 0; i < npre; ++i) {
+          mbar_expect_tx(&full_bar[i], a_bytes + L::W_BYTES);
+          load_w(kb_begin + i, i);
+        }
+      }
+      MIXDQ_DBG(2);                        // first TMA (weights) issued
+      pdl_wait();                          // activations / quantisation scalars are ready
+      for (int i = 0; i < npre; ++i) {
+        if (skip) mbar_arrive(&full_bar[i]);
+        else load_a(kb_begin + i, i);
+      }
+      int stage = (npre == STAGES) ? 0 : npre;
+      uint32_t phase = (npre == STAGES) ? 1 : 0;
+      for (int kb = kb_begin + npre; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (skip) {
+          mbar_arrive(&full_bar[stage]);
+        } else {
+          mbar_expect_tx(&full_bar[stage], a_bytes + L::W_BYTES);
+          load_w(kb, stage);
+          load_a(kb, stage);
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      MIXDQ_DBG(3);                        // last TMA issued
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const int total_kb = p.num_kb + (KIND == KIND_SPLIT ? p.num_kb1 : 0);
-      for (int kb = 0; kb < total_kb; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
+        if (kb == kb_begin) MIXDQ_DBG(4);  // first stage landed
         tc_fence_after();
         const uint32_t a_addr = smem_u32(sA + stage * L::A_BYTES);
         const uint32_t w_addr = smem_u32(sW + stage * L::W_BYTES);
         uint32_t d_tmem = tmem_base;
-        int kb_in_phase = kb;
+        int kb_in_phase = kb - kb_begin;
         if (KIND == KIND_SPLIT && kb >= p.num_kb) { d_tmem += BN; kb_in_phase = kb - p.num_kb; }
+        if (p.dbg_mode & 1) {
+          mbar_arrive(&empty_bar[stage]);
+        } else {
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          umma_i8(d_tmem, umma_desc_sw128(a_addr + k * UMMA_K), umma_desc_sw128(w_addr + k * UMMA_K),
-                  IDESC, (kb_in_phase | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            umma_i8(d_tmem, umma_desc_sw128(a_addr + k * UMMA_K),
+                    umma_desc_sw128(w_addr + k * UMMA_K), IDESC,
+                    (kb_in_phase | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tmem_full_bar);        // accumulators complete
+      umma_commit(tmem_full_bar);          // accumulators complete
+      MIXDQ_DBG(5);                        // last MMA issued
     }
   } else {
-    // ===================== epilogue warps 2..5 =====================
-    const int et = threadIdx.x - 64;  // 0..127
-    // stage per-column epilogue operands in shared memory while the mainloop runs
-    for (int j = et; j < BN; j += 128) {
+    // ============ epilogue warps 2..9: stage the per-column operands, wait for the MMAs ========
+    pdl_wait();                            // dynamic-quantisation scalars come from the predecessor
+    const int et = threadIdx.x - 64;  // 0..255
+    for (int j = et; j < BN; j += EPI_THREADS) {
       const int n = n_tile0 + j;
       const bool ok = n < p.N;
       float sc = 0.f, b0 = 0.f, bs = 0.f;
       if (ok) {
         if (p.a_scale != nullptr) {           // dynamic: fold the activation scalars here
-          sc = __fmul_rn(__ldg(p.scale + n), __ldg(p.a_scale));
-          b0 = __fmul_rn(__ldg(p.bias0 + n), __ldg(p.a_zp));
+          sc = __fmul_rn(__ldg(p.scale + n), __ldcg(p.a_scale));
+          b0 = __fmul_rn(__ldg(p.bias0 + n), __ldcg(p.a_zp));
         } else {
           sc = __ldg(p.scale + n);
           if (!(KIND == KIND_CONV) || !p.has_table) b0 = __ldg(p.bias0 + n);
@@ -209,7 +331,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         float w9[9];
 #pragma unroll
         for (int t = 0; t < 9; ++t) w9[t] = ok ? __ldg(p.bias0 + static_cast<int64_t>(n) * 9 + t) : 0.f;
-        const float zp = __ldg(p.a_zp);
+        const float zp = __ldcg(p.a_zp);
 #pragma unroll
         for (int rc = 0; rc < 4; ++rc)
 #pragma unroll
@@ -227,91 +349,223 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
       }
     }
-    // named barrier among the 128 epilogue threads (id 1)
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-
-    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;   // row of the 128-row tile
-    bool row_ok;
-    int64_t out_row;                       // row index into D / acc_out
-    int cls = 0;
-    if (KIND == KIND_CONV) {
-      const int per_img = p.boxH * p.boxW;
-      const int dn = row / per_img;
-      const int rem = row - dn * per_img;
-      const int dh = rem / p.boxW, dw = rem - dh * p.boxW;
-      const int n = tn0 + dn, pp = tp0 + dh, qq = tq0 + dw;
-      row_ok = (dn < p.boxN) && (n < p.NB) && (pp < p.P) && (qq < p.Q);
-      out_row = (static_cast<int64_t>(n) * p.P + pp) * p.Q + qq;
-      if (p.has_table) {
-        const int h0 = pp - p.pad, w0 = qq - p.pad;
-        const int rc = (h0 < 0 ? 1 : 0) | (h0 + 2 >= p.H ? 2 : 0);
-        const int sc4 = (w0 < 0 ? 1 : 0) | (w0 + 2 >= p.W ? 2 : 0);
-        cls = rc * 4 + sc4;
-      }
-    } else {
-      row_ok = (m0 + row) < p.M;
-      out_row = m0 + row;
-    }
-
+    epi_bar_sync();                        // named barrier among the 256 epilogue threads
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) MIXDQ_DBG(6);  // accumulators ready
+  }
 
-    const bool has_bias = p.bias != nullptr;
-    constexpr int CH = (BN >= 32) ? 32 : 16;
-#pragma unroll 1
-    for (int c = 0; c < BN / CH; ++c) {
-      uint32_t v[CH], v1[CH];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * CH;
-      if (CH == 32) {
-        tmem_ld_32x32(taddr, reinterpret_cast<uint32_t(&)[32]>(v));
-        if (KIND == KIND_SPLIT) tmem_ld_32x32(taddr + BN, reinterpret_cast<uint32_t(&)[32]>(v1));
-      } else {
-        tmem_ld_32x16(taddr, reinterpret_cast<uint32_t(&)[16]>(v));
-        if (KIND == KIND_SPLIT) tmem_ld_32x16(taddr + BN, reinterpret_cast<uint32_t(&)[16]>(v1));
+  __syncwarp();
+  const bool has_bias = p.bias != nullptr;
+  const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+  const int ehalf = (warp - 2) >> 2;     // which half of the tile's columns this epilogue warp takes
+  uint8_t* stage_out = smem;             // fp16 staging tile (ring is drained once tmem_full fired)
+
+  // dequantise NV (4 or 8) consecutive columns of one row; returns packed halves
+  auto dequant_pack = [&](int cls, int col, const int32_t* a0, const int32_t* a1, __half* h,
+                          int nv) {
+#pragma unroll
+    for (int j0 = 0; j0 < 8; j0 += 4) {
+      if (j0 >= nv) break;
+      const float4 sc = *reinterpret_cast<const float4*>(s_scale + col + j0);
+      const float* b0src = (KIND == KIND_CONV && p.has_table)
+                               ? (s_extra + cls * L::TAB_PITCH + col + j0)
+                               : (s_bias0 + col + j0);
+      const float4 b0 = *reinterpret_cast<const float4*>(b0src);
+      float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_bias) bs = *reinterpret_cast<const float4*>(s_bias + col + j0);
+      const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
+      const float b0v[4] = {b0.x, b0.y, b0.z, b0.w};
+      const float bsv[4] = {bs.x, bs.y, bs.z, bs.w};
+      float sc1v[4], b01v[4];
+      if (KIND == KIND_SPLIT) {
+        const float4 s1 = *reinterpret_cast<const float4*>(s_extra + col + j0);
+        const float4 b1 = *reinterpret_cast<const float4*>(s_extra + BN + col + j0);
+        sc1v[0] = s1.x; sc1v[1] = s1.y; sc1v[2] = s1.z; sc1v[3] = s1.w;
+        b01v[0] = b1.x; b01v[1] = b1.y; b01v[2] = b1.z; b01v[3] = b1.w;
       }
-      tmem_ld_wait();
-      if (row_ok) {
-        const int ncol0 = n_tile0 + c * CH;
-        if (p.acc_out != nullptr) {
-          int32_t* arow = p.acc_out + out_row * p.N + ncol0;
 #pragma unroll
-          for (int j = 0; j < CH; j += 4)
-            if (ncol0 + j + 4 <= p.N)
-              *reinterpret_cast<int4*>(arow + j) =
-                  make_int4(static_cast<int>(v[j]), static_cast<int>(v[j + 1]),
-                            static_cast<int>(v[j + 2]), static_cast<int>(v[j + 3]));
+      for (int j = 0; j < 4; ++j) {
+        float f = dequant_f32(a0[j0 + j], b0v[j], scv[j]);
+        if (has_bias) f = __fadd_rn(f, bsv[j]);
+        if (KIND == KIND_SPLIT) {
+          // reference: two fp16 conv outputs added in fp16 (nn/Conv2d.py:346)
+          // (torch adds halves in fp32 opmath and rounds once more to fp16)
+          const float f1 = dequant_f32(a1[j0 + j], b01v[j], sc1v[j]);
+          h[j0 + j] = __float2half_rn(__fadd_rn(__half2float(__float2half_rn(f)),
+                                               __half2float(__float2half_rn(f1))));
+        } else {
+          h[j0 + j] = __float2half_rn(f);
         }
-        __half* drow = p.D + out_row * p.ldd + ncol0;
+      }
+    }
+  };
+
+  int rows_here = BLOCK_M;               // tile rows whose results this CTA stages and stores
+  int row_base = 0;
+  if (splits == 1) {
+    if (warp >= 2) {
+      // ---- TMEM (lane == row) -> dequant -> fp16 -> staging tile -> global, chunk by chunk.
+      //      Each warp owns 32 rows x its column half and copies a chunk out (4 lanes x 16 B per
+      //      row, 8 rows per instruction) right after staging it, so the stores of chunk c drain
+      //      while chunk c+1 is being dequantised. Only __syncwarp is needed.
+      const int row = quarter * 32 + lane;
+      const RowInfo ri = row_info<KIND>(p, row, m0, tn0, tp0, tq0);
+      constexpr int CH = (BN >= 32) ? 32 : 16;
+      constexpr int NCH = BN / CH;
+      constexpr int LPR = CH / 8;                  // lanes (16-byte chunks) per row of a chunk
+      constexpr int RPI = 32 / LPR;                // rows per copy-out instruction
+      const int c_lo = (NCH >= 2) ? ehalf * (NCH / 2) : 0;
+      const int c_hi = (NCH >= 2) ? c_lo + NCH / 2 : (ehalf == 0 ? 1 : 0);
+      RowInfo ro[LPR];                             // rows this lane copies out
 #pragma unroll
-        for (int j8 = 0; j8 < CH; j8 += 8) {
-          if (ncol0 + j8 + 8 <= p.N) {
-            __align__(16) __half h[8];
+      for (int i = 0; i < LPR; ++i)
+        ro[i] = row_info<KIND>(p, quarter * 32 + i * RPI + lane / LPR, m0, tn0, tp0, tq0);
+#pragma unroll 1
+      for (int c = c_lo; c < c_hi; ++c) {
+        uint32_t v[CH], v1[CH];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * CH;
+        if (CH == 32) {
+          tmem_ld_32x32(taddr, reinterpret_cast<uint32_t(&)[32]>(v));
+          if (KIND == KIND_SPLIT) tmem_ld_32x32(taddr + BN, reinterpret_cast<uint32_t(&)[32]>(v1));
+        } else {
+          tmem_ld_32x16(taddr, reinterpret_cast<uint32_t(&)[16]>(v));
+          if (KIND == KIND_SPLIT) tmem_ld_32x16(taddr + BN, reinterpret_cast<uint32_t(&)[16]>(v1));
+        }
+        tmem_ld_wait();
+        if (ri.ok) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int col = c * CH + j8 + j;
-              float b0;
-              if (KIND == KIND_CONV) b0 = p.has_table ? s_extra[cls * L::TAB_PITCH + col] : s_bias0[col];
-              else b0 = s_bias0[col];
-              float f = dequant_f32(static_cast<int32_t>(v[j8 + j]), b0, s_scale[col]);
-              if (has_bias) f = __fadd_rn(f, s_bias[col]);
-              if (KIND == KIND_SPLIT) {
-                // reference: two fp16 conv outputs added in fp16 (nn/Conv2d.py:346)
-                const float f1 = dequant_f32(static_cast<int32_t>(v1[j8 + j]), s_extra[BN + col], s_extra[col]);
-                // (torch adds halves in fp32 opmath and rounds once more to fp16)
-                h[j] = __float2half_rn(__fadd_rn(__half2float(__float2half_rn(f)),
-                                                 __half2float(__float2half_rn(f1))));
-              } else {
-                h[j] = __float2half_rn(f);
-              }
+          for (int j8 = 0; j8 < CH; j8 += 8) {
+            const int col = c * CH + j8;
+            if (p.acc_out != nullptr && n_tile0 + col + 8 <= p.N) {
+              int32_t* arow = p.acc_out + ri.out_row * p.N + n_tile0 + col;
+              *reinterpret_cast<int4*>(arow) = make_int4(v[j8], v[j8 + 1], v[j8 + 2], v[j8 + 3]);
+              *reinterpret_cast<int4*>(arow + 4) = make_int4(v[j8 + 4], v[j8 + 5], v[j8 + 6], v[j8 + 7]);
             }
-            *reinterpret_cast<uint4*>(drow + j8) = *reinterpret_cast<const uint4*>(h);
+            __align__(16) __half h[8];
+            dequant_pack(ri.cls, col, reinterpret_cast<const int32_t*>(v) + j8,
+                         reinterpret_cast<const int32_t*>(v1) + j8, h, 8);
+            *reinterpret_cast<uint4*>(stage_out + row * L::OUT_PITCH + col * 2) =
+                *reinterpret_cast<const uint4*>(h);
+          }
+        }
+        __syncwarp();
+        const int ccol = c * CH + (lane % LPR) * 8;
+        if (n_tile0 + ccol + 8 <= p.N) {
+#pragma unroll
+          for (int i = 0; i < LPR; ++i) {
+            if (!ro[i].ok) continue;
+            const int r = quarter * 32 + i * RPI + lane / LPR;
+            *reinterpret_cast<uint4*>(p.D + ro[i].out_row * p.ldd + n_tile0 + ccol) =
+                *reinterpret_cast<const uint4*>(stage_out + r * L::OUT_PITCH + ccol * 2);
           }
         }
       }
+      tc_fence_before();
+      if (threadIdx.x == 64) MIXDQ_DBG(8);  // epilogue of this warp done
     }
-    tc_fence_before();
+  } else {
+    // ===================== split-K: reduce-scatter through the L2-resident workspace =========
+    // workspace slab of one CTA: [BN/4][128 rows][4] int32 -> lanes (rows) write adjacent 16 B
+    const int64_t tile_lin = static_cast<int64_t>(blockIdx.y) * gridDim.x + blockIdx.x;
+    int32_t* ws_tile = p.ws + tile_lin * splits * (BLOCK_M * BN);
+    if (warp >= 2) {
+      const int row = quarter * 32 + lane;
+      int32_t* my = ws_tile + static_cast<int64_t>(krank) * (BLOCK_M * BN);
+      constexpr int CH = (BN >= 32) ? 32 : 16;
+      constexpr int NCH = BN / CH;
+      const int c_lo = (NCH >= 2) ? ehalf * (NCH / 2) : 0;
+      const int c_hi = (NCH >= 2) ? c_lo + NCH / 2 : (ehalf == 0 ? 1 : 0);
+#pragma unroll 1
+      for (int c = c_lo; c < c_hi; ++c) {
+        uint32_t v[CH];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * CH;
+        if (CH == 32) tmem_ld_32x32(taddr, reinterpret_cast<uint32_t(&)[32]>(v));
+        else tmem_ld_32x16(taddr, reinterpret_cast<uint32_t(&)[16]>(v));
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < CH; j += 4) {
+          const int c4 = (c * CH + j) >> 2;
+          *reinterpret_cast<int4*>(my + (static_cast<int64_t>(c4) * BLOCK_M + row) * 4) =
+              make_int4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+      tc_fence_before();
+    }
+    __syncwarp();
+    if (threadIdx.x == 64) MIXDQ_DBG(8);    // partial tile written
+    // all partial tiles of the cluster are in the workspace (release/acquire at cluster scope)
+    cluster_sync_all();
+    if (threadIdx.x == 64) MIXDQ_DBG(9);    // cluster barrier passed
+    rows_here = BLOCK_M / splits;
+    row_base = krank * rows_here;
+    if (warp >= 2) {
+      // ---- phase A': owner sums the partials of its rows (coalesced .cg loads, all `splits`
+      //      loads of an item in flight together) ----
+      const int et = threadIdx.x - 64;
+      constexpr int C4 = BN / 4;
+      const int n_items = rows_here * C4;
+      // two items per iteration: 2 x splits independent 16-byte L2 loads in flight per thread
+      for (int it0 = et; it0 < n_items; it0 += 2 * EPI_THREADS) {
+        int4 x[2][8];
+        RowInfo ri2[2];
+        int rl[2], cc[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int it = it0 + u * EPI_THREADS;
+          const bool live = it < n_items;
+          const int c4 = live ? it / rows_here : 0;
+          rl[u] = live ? it - c4 * rows_here : 0;
+          cc[u] = c4 * 4;
+          ri2[u] = row_info<KIND>(p, row_base + rl[u], m0, tn0, tp0, tq0);
+          ri2[u].ok = ri2[u].ok && live;
+          const int4* src = reinterpret_cast<const int4*>(
+              ws_tile + (static_cast<int64_t>(c4) * BLOCK_M + row_base + rl[u]) * 4);
+#pragma unroll
+          for (int s = 0; s < 8; ++s)
+            x[u][s] = (ri2[u].ok && s < splits)
+                          ? __ldcg(src + static_cast<int64_t>(s) * (BLOCK_M * BN / 4))
+                          : make_int4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (!ri2[u].ok) continue;
+          int32_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {
+            acc[0] += x[u][s].x; acc[1] += x[u][s].y; acc[2] += x[u][s].z; acc[3] += x[u][s].w;
+          }
+          const int col = cc[u];
+          if (p.acc_out != nullptr && n_tile0 + col + 4 <= p.N)
+            *reinterpret_cast<int4*>(p.acc_out + ri2[u].out_row * p.N + n_tile0 + col) =
+                make_int4(acc[0], acc[1], acc[2], acc[3]);
+          __align__(8) __half h[8];
+          dequant_pack(ri2[u].cls, col, acc, acc, h, 4);
+          *reinterpret_cast<uint2*>(stage_out + rl[u] * L::OUT_PITCH + col * 2) =
+              *reinterpret_cast<const uint2*>(h);
+        }
+      }
+      if (threadIdx.x == 64) MIXDQ_DBG(10);   // partials summed
+    }
   }
+
+  if (warp >= 2 && splits > 1) {
+    // ---- phase B: staging tile -> global, consecutive threads along a row (coalesced) ----
+    epi_bar_sync();
+    if (threadIdx.x == 64) MIXDQ_DBG(11);     // staging complete
+    const int et = threadIdx.x - 64;
+    constexpr int G = BN / 8;            // 16-byte chunks per row
+    for (int g = et; g < rows_here * G; g += EPI_THREADS) {
+      const int row_local = g / G;
+      const int col = (g - row_local * G) * 8;
+      if (n_tile0 + col + 8 > p.N) continue;
+      const RowInfo ri = row_info<KIND>(p, row_base + row_local, m0, tn0, tp0, tq0);
+      if (!ri.ok) continue;
+      *reinterpret_cast<uint4*>(p.D + ri.out_row * p.ldd + n_tile0 + col) =
+          *reinterpret_cast<const uint4*>(stage_out + row_local * L::OUT_PITCH + col * 2);
+    }
+  }
+  if (threadIdx.x == 64) MIXDQ_DBG(7);    // epilogue done
 
   __syncthreads();
   if (warp == 1) {

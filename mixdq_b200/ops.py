@@ -55,10 +55,26 @@ def stop_recording() -> list:
     return rec
 
 
+_workspaces = {}
+WORKSPACE_BYTES = 64 << 20
+
+
+def _ensure_workspace(device: torch.device) -> None:
+    """Split-K scratch (stays L2-resident); allocated once per device through torch and handed
+    to the library, which never allocates."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _workspaces:
+        ws = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=torch.device("cuda", idx))
+        _lib.check(_lib.load().mixdq_set_workspace(idx, ws.data_ptr(), ws.numel()))
+        _workspaces[idx] = ws
+
+
 def _launch(family: str, fn, args: tuple, ref: torch.Tensor, kernels: int = 1, keep=(),
             algo_bytes: int = 0, algo_ops: int = 0) -> None:
     """Call one C-ABI entry point (stream appended as the last argument)."""
     global _launch_count
+    if family[0] in "gc":          # gemm / conv families may split K
+        _ensure_workspace(ref.device)
     _lib.check(fn(*args, _stream(ref)))
     _launch_count += kernels
     if _recorder is not None:
@@ -230,11 +246,29 @@ def _dynamic_workspace(device: torch.device) -> torch.Tensor:
     return ws
 
 
+# Layers that consume the SAME tensor (attn1.to_q/to_k/to_v share the normalised hidden state;
+# all 140 attn2.to_k/to_v of the SDXL UNet share `encoder_hidden_states`) would each recompute the
+# identical min/max and codes: a tiny identity-keyed cache returns the first result instead.
+# Keys are the tensor OBJECT (held strongly, so its storage cannot be recycled) and its version
+# counter (bumped by any in-place write).
+DYNAMIC_QUANT_CACHE = True
+_dyn_cache = []          # [(tensor, version, (q, scale, zp))], most recent last
+_DYN_CACHE_SLOTS = 3
+
+
+def clear_dynamic_quant_cache() -> None:
+    _dyn_cache.clear()
+
+
 def quantize_per_tensor_dynamic(input: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """qdiff asymmetric 8-bit min-max quantisation of one tensor (base_quantizer.py:155-190).
     Returns (q int8, scale fp32[], zero_point fp32[] (shifted by -128))."""
     _check(input.device.type == "cuda", "input should be on CUDA")
     _check(input.dtype == torch.float16, "input should be fp16")
+    if DYNAMIC_QUANT_CACHE:
+        for ref, ver, res in _dyn_cache:
+            if ref is input and ver == input._version:
+                return res
     lib = _lib.load()
     x = input if _is_dense(input) else input.contiguous()
     out = torch.empty_like(x, dtype=torch.int8)
@@ -243,8 +277,13 @@ def quantize_per_tensor_dynamic(input: torch.Tensor) -> Tuple[torch.Tensor, torc
         ws = _dynamic_workspace(x.device)
         _launch("quant_dyn", lib.mixdq_quant_i8_dynamic,
                 (x.data_ptr(), x.numel(), qp.data_ptr(), qp.data_ptr() + 4, out.data_ptr(),
-                 ws.data_ptr()), x, kernels=2, keep=(x, qp, out, ws), algo_bytes=3 * x.numel())
-    return out, qp[0], qp[1]
+                 ws.data_ptr()), x, kernels=1, keep=(x, qp, out, ws), algo_bytes=3 * x.numel())
+    res = (out, qp[0], qp[1])
+    if DYNAMIC_QUANT_CACHE:
+        _dyn_cache.append((input, input._version, res))
+        if len(_dyn_cache) > _DYN_CACHE_SLOTS:
+            _dyn_cache.pop(0)
+    return res
 
 
 # ---------------------------------------------------------------------------------------------

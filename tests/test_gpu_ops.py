@@ -232,7 +232,7 @@ LINEAR_SHAPES = [(256, 1280, 1280), (256, 10240, 1280), (256, 1280, 5120), (1024
 
 @pytest.mark.parametrize("M,N,K", LINEAR_SHAPES)
 def test_qlinear_tcgen05_bit_exact(ops, dev, M, N, K):
-    assert _linear_case(ops, dev, M, N, K, bias=(M % 2 == 0)) == "tcgen05"
+    assert _linear_case(ops, dev, M, N, K, bias=(M % 2 == 0)).startswith("tcgen05")
 
 
 @pytest.mark.parametrize("M,N,K", [(64, 16, 8), (33, 20, 36), (7, 4, 4), (256, 1280, 1280)])
@@ -255,20 +255,39 @@ def test_qlinear_batched_leading_dims_and_noncontiguous(ops, dev):
     assert torch.equal(bits(out), bits(ref))
 
 
-@pytest.mark.parametrize("bn", [16, 32, 64, 128, 256])
-def test_qlinear_every_tile_width(ops, dev, bn, monkeypatch):
-    """each BN instantiation of the tcgen05 kernel, incl. N and K tails"""
-    import subprocess, sys, os
-    code = (
-        "import torch,sys; sys.path.insert(0,'.'); sys.path.insert(0,'tests');"
-        "from test_gpu_ops import _linear_case; from mixdq_b200 import ops;"
-        "d=torch.device('cuda:0');"
-        "assert _linear_case(ops,d,260,328,400)=='tcgen05';"
-        "assert _linear_case(ops,d,128,512,128,bias=False)=='tcgen05'; print('ok')")
-    env = dict(os.environ, MIXDQ_FORCE_BN=str(bn))
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
-                       cwd=str(__import__("pathlib").Path(__file__).resolve().parent.parent))
-    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+@pytest.mark.parametrize("bn,splits", [(16, 1), (16, 2), (32, 1), (32, 4), (64, 1), (64, 2), (64, 8),
+                                       (128, 1), (128, 4), (128, 8), (256, 1), (256, 2), (256, 8)])
+def test_qlinear_every_tile_width_and_split(ops, dev, bn, splits):
+    """each BN instantiation of the tcgen05 kernel x split-K cluster size, incl. M/N/K tails and
+    uneven k-block ranges (K = 400 -> 4 k-blocks, K = 1280 -> 10 k-blocks over 8 ranks)"""
+    from mixdq_b200 import _lib
+    lib = _lib.load()
+    lib.mixdq_debug_force_bn(bn)
+    lib.mixdq_debug_force_splits(splits)
+    try:
+        want = "tcgen05-splitk" if splits > 1 else "tcgen05"
+        assert _linear_case(ops, dev, 260, 328, 1280) == want
+        assert _linear_case(ops, dev, 128, 512, 1024, bias=False) == want
+        if splits <= 4:
+            assert _linear_case(ops, dev, 77, 640, 400 + 112) == want
+    finally:
+        lib.mixdq_debug_force_bn(0)
+        lib.mixdq_debug_force_splits(0)
+
+
+@pytest.mark.parametrize("bn,splits", [(64, 4), (128, 8), (256, 8), (32, 2)])
+def test_qconv2d_split_k_clusters(ops, dev, bn, splits):
+    from mixdq_b200 import _lib
+    lib = _lib.load()
+    lib.mixdq_debug_force_bn(bn)
+    lib.mixdq_debug_force_splits(splits)
+    try:
+        assert _conv_case(ops, dev, 1, 16, 16, 1280, 1280, 3, 3, 1, 1) == "tcgen05-splitk"
+        assert _conv_case(ops, dev, 2, 14, 14, 96, 200, 3, 3, 1, 1) == "tcgen05-splitk"
+        assert _conv_case(ops, dev, 1, 32, 32, 640, 320, 1, 1, 0, 1).startswith("tcgen05")
+    finally:
+        lib.mixdq_debug_force_bn(0)
+        lib.mixdq_debug_force_splits(0)
 
 
 def test_qlinear_dynamic_variant(ops, dev):
@@ -410,7 +429,7 @@ SDXL_CONVS = [  # (n,h,w,c,k,r,s,pad,stride)
 
 @pytest.mark.parametrize("n,h,w,c,k,r,s,pad,stride", SDXL_CONVS)
 def test_qconv2d_tcgen05_bit_exact(ops, dev, n, h, w, c, k, r, s, pad, stride):
-    assert _conv_case(ops, dev, n, h, w, c, k, r, s, pad, stride) == "tcgen05"
+    assert _conv_case(ops, dev, n, h, w, c, k, r, s, pad, stride).startswith("tcgen05")
 
 
 @pytest.mark.parametrize("n,h,w,c,k,r,s,pad,stride", [
