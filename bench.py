@@ -309,6 +309,8 @@ def main():
                     help="activation scales: dynamic per-tensor min-max (north star) or static ckpt")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp16", action="store_true")
+    ap.add_argument("--profile-fp16", action="store_true",
+                    help="with --profile-step: profile the FP16 baseline UNet instead")
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager quantized step between cudaProfilerStart/Stop and exit "
                          "(for `ncu --profile-from-start off`); prints no bench line")
@@ -336,7 +338,7 @@ def main():
     sampler = ClockSampler(local)
 
     if args.profile_step:
-        qunet = quantize_copy(unet16, args.mode)
+        qunet = unet16 if args.profile_fp16 else quantize_copy(unet16, args.mode)
         with torch.no_grad():
             for _ in range(2):
                 qunet(**inputs)

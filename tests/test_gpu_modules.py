@@ -188,13 +188,50 @@ def _tiny(dev, bos=False, protect=()):
 @pytest.mark.parametrize("bos", [False, True])
 def test_tiny_unet_vs_oracle(dev, bos):
     """W8A8 dynamic UNet (SDXL topology: split shortcuts, cross-attention, samplers) on the GPU in
-    fp16 vs the fp32 fake-quant oracle on the CPU; conv_in/conv_out protected as in act_8.00.yaml."""
+    fp16 vs the fp32 fake-quant oracle on the CPU; conv_in/conv_out protected as in act_8.00.yaml.
+
+    Two checks (measured on B200, tools/diag_unet.py):
+      * teacher-forced — every quantized layer, fed the ORACLE's input of that layer, reproduces
+        the oracle's output of that layer inside the north-star tolerance (max-abs/max <= 1e-2,
+        cosine >= 0.9999). This isolates the hot path from the stock fp16 ops around it.
+      * free-running — the final latents. Random-init weights make the UNet chaotic: 8-bit code
+        flips caused by the fp16 (GPU) vs fp32 (oracle) norms/attention between the layers grow to
+        ~3e-2 of the output range, the same size as the quantization noise itself (the un-quantized
+        fp16 UNet is 3.3e-2 away from the oracle). The bound is therefore tied to that noise:
+        the W8A8 output must be no further from the oracle than 1.5x the fp16 UNet is, and
+        cosine >= 0.999."""
+    from mixdq_b200.unet import build_unet
     unet, ref_unet, inputs = _tiny(dev, bos=bos, protect=("conv_in", "conv_out"))
+    fp_unet = build_unet("tiny", seed=3).half().to(dev).to(memory_format=torch.channels_last)
+    names = [n for n, _ in fp_unet.quantizable_layers()]
+    rec = {}
+
+    def hook(name):
+        def f(m, inp, out):
+            rec[name] = (inp[0].detach(), out.detach())
+        return f
+    handles = [ref_unet.get_submodule(n).register_forward_hook(hook(n)) for n in names]
     with torch.no_grad():
-        got = unet(**{k: v.to(dev) for k, v in inputs.items()})[0]
+        kw = {k: v.to(dev) for k, v in inputs.items()}
+        got = unet(**kw)[0]
+        fp = fp_unet(**kw)[0]
         ref = ref_unet(**{k: (v.float() if v.is_floating_point() else v) for k, v in inputs.items()})[0]
-    ok, stats = close(got, ref, abs_tol=2e-2, cos_tol=0.999, rel_to_max=True)
-    assert ok, stats
+        for h in handles:
+            h.remove()
+        assert len(rec) == len(names)
+        worst = (0.0, 1.0, None)
+        for n in names:
+            xi, yo = rec[n]
+            xin = xi.half().to(dev)
+            if xin.dim() == 4:
+                xin = xin.contiguous(memory_format=torch.channels_last)
+            ok, (err, cos) = close(unet.get_submodule(n)(xin), yo, rel_to_max=True)
+            assert ok, (n, err, cos)
+            if err > worst[0]:
+                worst = (err, cos, n)
+    _, (err_q, cos_q) = close(got, ref, rel_to_max=True)
+    _, (err_fp, _) = close(fp, ref, rel_to_max=True)
+    assert cos_q >= 0.999 and err_q <= 1.5 * err_fp, (err_q, cos_q, err_fp, worst)
 
 
 def test_unet_cuda_graph_replay(dev):
