@@ -177,6 +177,81 @@ int mixdq_conv1x1_split_w8a8_f16(const int8_t* xa, int64_t lda, const int8_t* wa
                                  const mixdq_half_t* bias, mixdq_half_t* y, int64_t ldy,
                                  int M, int K, mixdq_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Dynamic-scale variants with the fused elementwise tail. The reference model follows many
+ * quantized layers with an fp16 elementwise add (`x + attn(...)`, `x + ff(...)`, resnet
+ * `h + temb[:, :, None, None]` and `x + h`; diffusers modules around nn/Linear.py / nn/Conv2d.py
+ * outputs). Each such add is applied in the epilogue exactly as PyTorch would apply it to the
+ * layer's fp16 output: D = half(float(D) + float(other)), one rounding per add.
+ *   residual  fp16 [rows][N] with row pitch ldr (conv: dense NHWC [N*P*Q][K])
+ *   chan_add  fp16 [images][K] with row pitch ldca (conv only: per-image channel vector,
+ *             applied before residual)
+ * Dynamic mode: `w_scale`/`wsum*` are the per-output-channel weight scale and weight code sums;
+ * the epilogue forms scale = w_scale * (*a_scale) and the zero-point correction from *a_zp
+ * (device scalars written by a dynamic quantise call).
+ * These entry points require the tcgen05 path (16-byte aligned pointers, K % 16 == 0 (C for
+ * conv), N % 8 == 0): MIXDQ_ERR_ALIGNMENT otherwise.
+ * ---------------------------------------------------------------------------------------- */
+int mixdq_gemm_w8a8_f16_dyn_res(const int8_t* A, int64_t lda, const int8_t* W,
+                                const float* w_scale, const float* wsum,
+                                const float* a_scale, const float* a_zp, const mixdq_half_t* bias,
+                                const mixdq_half_t* residual, int64_t ldr,
+                                mixdq_half_t* D, int64_t ldd, int M, int N, int K,
+                                int32_t* acc_out, mixdq_stream_t stream);
+
+/* wsum_krs fp32 [K][R][S] iff pad > 0; wsum_k fp32 [K] (sum over taps and channels) iff pad == 0 */
+int mixdq_conv_w8a8_f16_dyn(const int8_t* x_nhwc, int64_t x_cpitch, const int8_t* w_krsc,
+                            const float* w_scale, const float* wsum_krs, const float* wsum_k,
+                            const float* a_scale, const float* a_zp, const mixdq_half_t* bias,
+                            const mixdq_half_t* chan_add, int64_t ldca,
+                            const mixdq_half_t* residual, mixdq_half_t* y_nhwc, int N, int H, int W, int C, int K, int R, int S,
+                            int stride, int pad, int32_t* acc_out, mixdq_stream_t stream);
+
+int mixdq_conv1x1_split_w8a8_f16_dyn(const int8_t* xa, int64_t lda, const int8_t* wa, int Ca,
+                                     const float* wsum_a, const float* w_scale_a,
+                                     const float* a_scale_a, const float* a_zp_a,
+                                     const int8_t* xb, int64_t ldb, const int8_t* wb, int Cb,
+                                     const float* wsum_b, const float* w_scale_b,
+                                     const float* a_scale_b, const float* a_zp_b,
+                                     const mixdq_half_t* bias, const mixdq_half_t* residual,
+                                     int64_t ldr, mixdq_half_t* y, int64_t ldy, int M, int K,
+                                     mixdq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Producer-side fusion of the dynamic quantise pass: the stock fp16 op that
+ * produces a quantized layer's input and the A10 quantisation of its result as ONE kernel.
+ * Each reproduces the unfused PyTorch sequence, rounding to fp16 wherever PyTorch materialises
+ * an fp16 tensor, then applies the A10 formula to those fp16 values (same outputs as
+ * mixdq_quant_i8_dynamic: q dense int8, *scale_out = delta, *zp_out = z - 128).
+ *   ln     : y = half(gamma * (rstd * (x - mean)) + beta), rows of C, biased variance, fp32 stats
+ *            (torch.nn.LayerNorm feeding attn1.to_q/k/v, attn2.to_q, ff.net.0.proj)
+ *   geglu  : hg = [M][2*I]; y = half(float(h) * float(half(gelu(g))))  exact-erf GELU
+ *            (diffusers GEGLU between ff.net.0.proj and ff.net.2)
+ *   gn     : NHWC x [NB][HW][C] (pixel pitch ldx), G groups; y = half(fma(x, a, b)),
+ *            a = rstd*gamma, b = beta - mean*a; silu != 0: y = half(y / (1 + exp(-y)))
+ *            (torch.nn.GroupNorm [+ SiLU] feeding resnet conv1/conv2 and Transformer2D.proj_in)
+ * `y_out` (nullable, dense fp16) additionally receives the fp16 values that were quantised —
+ * test hook / for an un-quantised consumer. `ws` as for mixdq_quant_i8_dynamic.
+ * Restrictions: C % 8 == 0, 16-byte aligned pointers; ln: C <= 2048; gn: C <= 2560, G <= 32,
+ * C/G >= 8 or == 4, NB <= 148 (MIXDQ_ERR_UNSUPPORTED otherwise: run the ops unfused).
+ * ---------------------------------------------------------------------------------------- */
+/* A10 on a row-pitched view: x fp16 [M][cols] with row pitch ldx -> dense int8 [M][cols]
+ * (channel slices of NHWC tensors for the split shortcuts nn/Conv2d.py:313-318, token slices
+ * nn/Linear.py:180, strided attention outputs). cols % 8 == 0, ldx % 8 == 0. */
+int mixdq_quant_i8_dynamic_rows(const mixdq_half_t* x, int64_t ldx, int M, int cols, int8_t* q,
+                                float* scale_out, float* zp_out, void* ws, mixdq_stream_t stream);
+int mixdq_ln_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int M, int C,
+                              const mixdq_half_t* gamma, const mixdq_half_t* beta, float eps,
+                              int8_t* q, mixdq_half_t* y_out, float* scale_out, float* zp_out,
+                              void* ws, mixdq_stream_t stream);
+int mixdq_geglu_quant_i8_dynamic(const mixdq_half_t* hg, int64_t ld, int M, int I, int8_t* q,
+                                 mixdq_half_t* y_out, float* scale_out, float* zp_out, void* ws,
+                                 mixdq_stream_t stream);
+int mixdq_gn_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int NB, int HW, int C, int G,
+                              const mixdq_half_t* gamma, const mixdq_half_t* beta, float eps,
+                              int silu, int8_t* q, mixdq_half_t* y_out, float* scale_out,
+                              float* zp_out, void* ws, mixdq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

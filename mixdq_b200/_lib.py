@@ -23,6 +23,8 @@ ABI_SYMBOLS = [
     "mixdq_quant_dynamic_ws_bytes", "mixdq_quant_i8_dynamic",
     "mixdq_gemm_w8a8_f16", "mixdq_gemm_w8a8_f16_dyn", "mixdq_gemm_w4a8_f16",
     "mixdq_conv_w8a8_f16", "mixdq_conv1x1_split_w8a8_f16",
+    "mixdq_gemm_w8a8_f16_dyn_res", "mixdq_conv_w8a8_f16_dyn", "mixdq_conv1x1_split_w8a8_f16_dyn",
+    "mixdq_quant_i8_dynamic_rows", "mixdq_ln_quant_i8_dynamic", "mixdq_geglu_quant_i8_dynamic", "mixdq_gn_quant_i8_dynamic",
 ]
 
 
@@ -83,6 +85,30 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mixdq_conv1x1_split_w8a8_f16.argtypes = [P, c_int64, P, c_int, P, P,
                                                  P, c_int64, P, c_int, P, P,
                                                  P, P, c_int64, c_int, c_int, P]
+
+
+    from ctypes import c_float
+    lib.mixdq_gemm_w8a8_f16_dyn_res.restype = c_int
+    lib.mixdq_gemm_w8a8_f16_dyn_res.argtypes = [P, c_int64, P, P, P, P, P, P, P, c_int64, P,
+                                                c_int64, c_int, c_int, c_int, P, P]
+    lib.mixdq_conv_w8a8_f16_dyn.restype = c_int
+    lib.mixdq_conv_w8a8_f16_dyn.argtypes = [P, c_int64, P, P, P, P, P, P, P, P, c_int64, P, P,
+                                            c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                            c_int, c_int, P, P]
+    lib.mixdq_conv1x1_split_w8a8_f16_dyn.restype = c_int
+    lib.mixdq_conv1x1_split_w8a8_f16_dyn.argtypes = [P, c_int64, P, c_int, P, P, P, P,
+                                                     P, c_int64, P, c_int, P, P, P, P,
+                                                     P, P, c_int64, P, c_int64, c_int, c_int, P]
+    lib.mixdq_quant_i8_dynamic_rows.restype = c_int
+    lib.mixdq_quant_i8_dynamic_rows.argtypes = [P, c_int64, c_int, c_int, P, P, P, P, P]
+    lib.mixdq_ln_quant_i8_dynamic.restype = c_int
+    lib.mixdq_ln_quant_i8_dynamic.argtypes = [P, c_int64, c_int, c_int, P, P, c_float, P, P, P, P,
+                                              P, P]
+    lib.mixdq_geglu_quant_i8_dynamic.restype = c_int
+    lib.mixdq_geglu_quant_i8_dynamic.argtypes = [P, c_int64, c_int, c_int, P, P, P, P, P, P]
+    lib.mixdq_gn_quant_i8_dynamic.restype = c_int
+    lib.mixdq_gn_quant_i8_dynamic.argtypes = [P, c_int64, c_int, c_int, c_int, c_int, P, P,
+                                              c_float, c_int, P, P, P, P, P, P]
 
 
 def load() -> ctypes.CDLL:

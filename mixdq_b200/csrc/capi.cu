@@ -60,10 +60,13 @@ static PFN_encodeTiled get_encode() {
 
 // rank-R uint8 tensor, dims/box innermost first, strides in bytes for dims 1..R-1.
 static bool make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides, const uint32_t* box) {
+                      const uint64_t* strides, const uint32_t* box,
+                      const uint32_t* elem_strides = nullptr) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return false;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (elem_strides)
+    for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, static_cast<cuuint32_t>(rank),
                    const_cast<void*>(base), reinterpret_cast<const cuuint64_t*>(dims),
                    reinterpret_cast<const cuuint64_t*>(strides),
@@ -227,17 +230,19 @@ static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) 
 // ------------------------------------------------------------------------------------------
 static int gemm_common(const int8_t* A, int64_t lda, const int8_t* W, const float* p_scale,
                        const float* p_bias0, const float* a_scale, const float* a_zp,
-                       const mixdq_half_t* bias, mixdq_half_t* D, int64_t ldd, int M, int N, int K,
+                       const mixdq_half_t* bias, const mixdq_half_t* residual, int64_t ldr,
+                       mixdq_half_t* D, int64_t ldd, int M, int N, int K,
                        int32_t* acc_out, cudaStream_t st) {
   if (M < 0 || N <= 0 || K <= 0 || !W || !p_scale || !p_bias0) return MIXDQ_ERR_INVALID_ARG;
   if (M == 0) return MIXDQ_OK;
-  if (!A || !D || lda < K || ldd < N) return MIXDQ_ERR_INVALID_ARG;
+  if (!A || !D || lda < K || ldd < N || (residual && ldr < N)) return MIXDQ_ERR_INVALID_ARG;
   if ((K & 3) || (N & 3)) return MIXDQ_ERR_ALIGNMENT;
 
   const bool tc_ok = !g_force_simt && (K % 16 == 0) && (N % 8 == 0) && (lda % 16 == 0) &&
                      (ldd % 8 == 0) && al16(A) && al16(W) && al16(D) &&
-                     (!acc_out || al16(acc_out));
+                     (!acc_out || al16(acc_out)) && (!residual || (al16(residual) && ldr % 8 == 0));
   if (!tc_ok) {
+    if (residual) return MIXDQ_ERR_ALIGNMENT;   // the fused tail exists on the tcgen05 path only
     SimtGemmArgs g{};
     g.A = A; g.lda = lda; g.W = W; g.K = K;
     g.scale = p_scale; g.bias0 = p_bias0; g.a_scale = a_scale; g.a_zp = a_zp;
@@ -263,6 +268,7 @@ static int gemm_common(const int8_t* A, int64_t lda, const int8_t* W, const floa
   p.scale = p_scale; p.bias0 = p_bias0; p.a_scale = a_scale; p.a_zp = a_zp;
   p.bias = reinterpret_cast<const __half*>(bias);
   p.D = reinterpret_cast<__half*>(D); p.ldd = ldd; p.acc_out = acc_out;
+  p.residual = reinterpret_cast<const __half*>(residual); p.ldr = ldr;
   dim3 grid(m_tiles, (N + bn - 1) / bn, splits);
   g_last_path = splits > 1 ? "tcgen05-splitk" : "tcgen05";
   return dispatch_tc<KIND_GEMM>(bn, grid, tmA, tmW, tmA, tmW, p, st);
@@ -272,8 +278,8 @@ extern "C" int mixdq_gemm_w8a8_f16(const int8_t* A, int64_t lda, const int8_t* W
                                    const float* bias0, const float* scale,
                                    const mixdq_half_t* bias, mixdq_half_t* D, int64_t ldd, int M,
                                    int N, int K, int32_t* acc_out, mixdq_stream_t stream) {
-  return gemm_common(A, lda, W, scale, bias0, nullptr, nullptr, bias, D, ldd, M, N, K, acc_out,
-                     static_cast<cudaStream_t>(stream));
+  return gemm_common(A, lda, W, scale, bias0, nullptr, nullptr, bias, nullptr, 0, D, ldd, M, N, K,
+                     acc_out, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mixdq_gemm_w8a8_f16_dyn(const int8_t* A, int64_t lda, const int8_t* W,
@@ -283,8 +289,19 @@ extern "C" int mixdq_gemm_w8a8_f16_dyn(const int8_t* A, int64_t lda, const int8_
                                        int M, int N, int K, int32_t* acc_out,
                                        mixdq_stream_t stream) {
   if (!a_scale || !a_zp) return MIXDQ_ERR_INVALID_ARG;
-  return gemm_common(A, lda, W, w_scale, wsum, a_scale, a_zp, bias, D, ldd, M, N, K, acc_out,
-                     static_cast<cudaStream_t>(stream));
+  return gemm_common(A, lda, W, w_scale, wsum, a_scale, a_zp, bias, nullptr, 0, D, ldd, M, N, K,
+                     acc_out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mixdq_gemm_w8a8_f16_dyn_res(const int8_t* A, int64_t lda, const int8_t* W,
+                                           const float* w_scale, const float* wsum,
+                                           const float* a_scale, const float* a_zp,
+                                           const mixdq_half_t* bias, const mixdq_half_t* residual,
+                                           int64_t ldr, mixdq_half_t* D, int64_t ldd, int M, int N,
+                                           int K, int32_t* acc_out, mixdq_stream_t stream) {
+  if (!a_scale || !a_zp) return MIXDQ_ERR_INVALID_ARG;
+  return gemm_common(A, lda, W, w_scale, wsum, a_scale, a_zp, bias, residual, ldr, D, ldd, M, N, K,
+                     acc_out, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mixdq_gemm_w4a8_f16(const int8_t* A, int64_t lda, const uint8_t* W_packed,
@@ -306,13 +323,12 @@ extern "C" int mixdq_gemm_w4a8_f16(const int8_t* A, int64_t lda, const uint8_t* 
 // ------------------------------------------------------------------------------------------
 // conv (A3 + A4)
 // ------------------------------------------------------------------------------------------
-extern "C" int mixdq_conv_w8a8_f16(const int8_t* x, int64_t x_cpitch, const int8_t* w,
-                                   const float* scale, const float* wsum_krs,
-                                   const float* bias0_k, const float* zp,
-                                   const mixdq_half_t* bias, mixdq_half_t* y, int N, int H, int W,
-                                   int C, int K, int R, int S, int stride, int pad,
-                                   int32_t* acc_out, mixdq_stream_t stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const float* scale,
+                       const float* wsum_krs, const float* bias0_k, const float* zp,
+                       const float* a_scale, const mixdq_half_t* bias,
+                       const mixdq_half_t* chan_add, int64_t ldca, const mixdq_half_t* residual,
+                       mixdq_half_t* y, int N, int H, int W, int C, int K, int R, int S,
+                       int stride, int pad, int32_t* acc_out, cudaStream_t st) {
   if (N < 0 || H <= 0 || W <= 0 || C <= 0 || K <= 0 || R <= 0 || S <= 0 || stride <= 0 ||
       pad < 0 || !w || !scale)
     return MIXDQ_ERR_INVALID_ARG;
@@ -325,10 +341,17 @@ extern "C" int mixdq_conv_w8a8_f16(const int8_t* x, int64_t x_cpitch, const int8
   if (N == 0) return MIXDQ_OK;
   if (!x || !y) return MIXDQ_ERR_INVALID_ARG;
 
-  const bool geom_ok = (stride == 1) && (pad == 0 || (pad == 1 && R == 3 && S == 3)) && Q <= 128;
+  // stride 2 (the down-samplers): the A box is fetched with TMA element strides (traversal
+  // stride 2 along W and H), so the tile rows are still consecutive OUTPUT pixels
+  const bool geom_ok = (stride == 1 || stride == 2) &&
+                       (pad == 0 || (pad == 1 && R == 3 && S == 3)) && Q <= 128;
   const bool tc_ok = !g_force_simt && geom_ok && (C % 16 == 0) && (x_cpitch % 16 == 0) &&
-                     (K % 8 == 0) && al16(x) && al16(w) && al16(y) && (!acc_out || al16(acc_out));
+                     (K % 8 == 0) && al16(x) && al16(w) && al16(y) && (!acc_out || al16(acc_out)) &&
+                     (!chan_add || (al16(chan_add) && ldca % 8 == 0 && ldca >= K)) &&
+                     (!residual || al16(residual));
   if (!tc_ok) {
+    // dynamic scalars and the fused tails exist on the tcgen05 path only
+    if (a_scale || chan_add || residual) return MIXDQ_ERR_ALIGNMENT;
     SimtConvArgs c{};
     c.x = x; c.x_cpitch = x_cpitch; c.w = w; c.scale = scale;
     c.wsum_krs = pad > 0 ? wsum_krs : nullptr; c.bias0_k = bias0_k; c.zp = zp;
@@ -356,9 +379,10 @@ extern "C" int mixdq_conv_w8a8_f16(const int8_t* x, int64_t x_cpitch, const int8
                         static_cast<uint64_t>(N)};
     uint64_t strides[3] = {static_cast<uint64_t>(x_cpitch), static_cast<uint64_t>(x_cpitch) * W,
                            static_cast<uint64_t>(x_cpitch) * W * H};
-    uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(boxW), static_cast<uint32_t>(boxH),
-                       static_cast<uint32_t>(boxN)};
-    if (!make_tmap(&tmA, x, 4, dims, strides, box)) return MIXDQ_ERR_CUDA;
+    uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(boxW * stride),
+                       static_cast<uint32_t>(boxH * stride), static_cast<uint32_t>(boxN)};
+    uint32_t estr[4] = {1, static_cast<uint32_t>(stride), static_cast<uint32_t>(stride), 1};
+    if (!make_tmap(&tmA, x, 4, dims, strides, box, estr)) return MIXDQ_ERR_CUDA;
   }
   {
     uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(R) * S,
@@ -375,28 +399,56 @@ extern "C" int mixdq_conv_w8a8_f16(const int8_t* x, int64_t x_cpitch, const int8
   p.M = N * P * Q; p.N = K;
   p.kb_per_tap = kb_per_tap;
   p.num_kb = R * S * p.kb_per_tap;
-  p.S = S; p.pad = pad; p.NB = N; p.H = H; p.W = W; p.P = P; p.Q = Q;
+  p.S = S; p.pad = pad; p.stride = stride; p.NB = N; p.H = H; p.W = W; p.P = P; p.Q = Q;
   p.boxW = boxW; p.boxH = boxH; p.boxN = boxN; p.tilesQ = tilesQ; p.tilesP = tilesP;
   p.a_tx_bytes = static_cast<uint32_t>(boxW) * boxH * boxN * BLOCK_K;
   p.has_table = pad > 0 ? 1 : 0;
-  p.scale = scale; p.bias0 = pad > 0 ? wsum_krs : bias0_k; p.a_zp = zp;
+  p.scale = scale; p.bias0 = pad > 0 ? wsum_krs : bias0_k; p.a_zp = zp; p.a_scale = a_scale;
   p.bias = reinterpret_cast<const __half*>(bias);
   p.D = reinterpret_cast<__half*>(y); p.ldd = K; p.acc_out = acc_out;
+  p.chan_add = reinterpret_cast<const __half*>(chan_add); p.ldca = ldca;
+  p.rows_per_img = static_cast<int64_t>(P) * Q;
+  p.residual = reinterpret_cast<const __half*>(residual); p.ldr = K;
   dim3 grid(m_tiles, (K + bn - 1) / bn, splits);
   g_last_path = splits > 1 ? "tcgen05-splitk" : "tcgen05";
   return dispatch_tc<KIND_CONV>(bn, grid, tmA, tmW, tmA, tmW, p, st);
 }
 
+extern "C" int mixdq_conv_w8a8_f16(const int8_t* x, int64_t x_cpitch, const int8_t* w,
+                                   const float* scale, const float* wsum_krs,
+                                   const float* bias0_k, const float* zp,
+                                   const mixdq_half_t* bias, mixdq_half_t* y, int N, int H, int W,
+                                   int C, int K, int R, int S, int stride, int pad,
+                                   int32_t* acc_out, mixdq_stream_t stream) {
+  return conv_common(x, x_cpitch, w, scale, wsum_krs, bias0_k, zp, nullptr, bias, nullptr, 0,
+                     nullptr, y, N, H, W, C, K, R, S, stride, pad, acc_out,
+                     static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mixdq_conv_w8a8_f16_dyn(const int8_t* x, int64_t x_cpitch, const int8_t* w,
+                                       const float* w_scale, const float* wsum_krs,
+                                       const float* wsum_k, const float* a_scale,
+                                       const float* a_zp, const mixdq_half_t* bias,
+                                       const mixdq_half_t* chan_add, int64_t ldca,
+                                       const mixdq_half_t* residual, mixdq_half_t* y, int N, int H,
+                                       int W, int C, int K, int R, int S, int stride, int pad,
+                                       int32_t* acc_out, mixdq_stream_t stream) {
+  if (!a_scale || !a_zp) return MIXDQ_ERR_INVALID_ARG;
+  return conv_common(x, x_cpitch, w, w_scale, wsum_krs, wsum_k, a_zp, a_scale, bias, chan_add, ldca,
+                     residual, y, N, H, W, C, K, R, S, stride, pad, acc_out,
+                     static_cast<cudaStream_t>(stream));
+}
+
 // ------------------------------------------------------------------------------------------
 // split 1x1 shortcut (A6)
 // ------------------------------------------------------------------------------------------
-extern "C" int mixdq_conv1x1_split_w8a8_f16(const int8_t* xa, int64_t lda, const int8_t* wa, int Ca,
-                                            const float* bias0_a, const float* scale_a,
-                                            const int8_t* xb, int64_t ldb, const int8_t* wb, int Cb,
-                                            const float* bias0_b, const float* scale_b,
-                                            const mixdq_half_t* bias, mixdq_half_t* y, int64_t ldy,
-                                            int M, int K, mixdq_stream_t stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int split_common(const int8_t* xa, int64_t lda, const int8_t* wa, int Ca,
+                        const float* bias0_a, const float* scale_a, const float* a_scale_a,
+                        const float* a_zp_a, const int8_t* xb, int64_t ldb, const int8_t* wb,
+                        int Cb, const float* bias0_b, const float* scale_b,
+                        const float* a_scale_b, const float* a_zp_b, const mixdq_half_t* bias,
+                        const mixdq_half_t* residual, int64_t ldr, mixdq_half_t* y, int64_t ldy,
+                        int M, int K, cudaStream_t st) {
   if (M < 0 || K <= 0 || Ca <= 0 || Cb <= 0 || !wa || !wb || !bias0_a || !scale_a || !bias0_b ||
       !scale_b)
     return MIXDQ_ERR_INVALID_ARG;
@@ -407,6 +459,7 @@ extern "C" int mixdq_conv1x1_split_w8a8_f16(const int8_t* xa, int64_t lda, const
                      (lda % 16 == 0) && (ldb % 16 == 0) && (ldy % 8 == 0) && al16(xa) && al16(xb) &&
                      al16(wa) && al16(wb) && al16(y);
   if (!tc_ok) {
+    if (a_scale_a || a_scale_b || residual) return MIXDQ_ERR_ALIGNMENT;  // tcgen05 path only
     SimtGemmArgs g{};
     g.A = xa; g.lda = lda; g.W = wa; g.K = Ca;
     g.A1 = xb; g.lda1 = ldb; g.W1 = wb; g.K1 = Cb;
@@ -433,9 +486,35 @@ extern "C" int mixdq_conv1x1_split_w8a8_f16(const int8_t* xa, int64_t lda, const
   p.num_kb = (Ca + BLOCK_K - 1) / BLOCK_K;
   p.num_kb1 = (Cb + BLOCK_K - 1) / BLOCK_K;
   p.scale = scale_a; p.bias0 = bias0_a; p.scale1 = scale_b; p.bias0_1 = bias0_b;
+  p.a_scale = a_scale_a; p.a_zp = a_zp_a; p.a_scale1 = a_scale_b; p.a_zp1 = a_zp_b;
   p.bias = reinterpret_cast<const __half*>(bias);
   p.D = reinterpret_cast<__half*>(y); p.ldd = ldy;
+  p.residual = reinterpret_cast<const __half*>(residual); p.ldr = ldr;
   dim3 grid(m_tiles, (K + bn - 1) / bn);
   g_last_path = "tcgen05";
   return dispatch_tc<KIND_SPLIT>(bn, grid, tmA, tmW, tmA1, tmW1, p, st);
+}
+
+extern "C" int mixdq_conv1x1_split_w8a8_f16(const int8_t* xa, int64_t lda, const int8_t* wa, int Ca,
+                                            const float* bias0_a, const float* scale_a,
+                                            const int8_t* xb, int64_t ldb, const int8_t* wb, int Cb,
+                                            const float* bias0_b, const float* scale_b,
+                                            const mixdq_half_t* bias, mixdq_half_t* y, int64_t ldy,
+                                            int M, int K, mixdq_stream_t stream) {
+  return split_common(xa, lda, wa, Ca, bias0_a, scale_a, nullptr, nullptr, xb, ldb, wb, Cb, bias0_b,
+                      scale_b, nullptr, nullptr, bias, nullptr, 0, y, ldy, M, K,
+                      static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mixdq_conv1x1_split_w8a8_f16_dyn(
+    const int8_t* xa, int64_t lda, const int8_t* wa, int Ca, const float* wsum_a,
+    const float* w_scale_a, const float* a_scale_a, const float* a_zp_a, const int8_t* xb,
+    int64_t ldb, const int8_t* wb, int Cb, const float* wsum_b, const float* w_scale_b,
+    const float* a_scale_b, const float* a_zp_b, const mixdq_half_t* bias,
+    const mixdq_half_t* residual, int64_t ldr, mixdq_half_t* y, int64_t ldy, int M, int K,
+    mixdq_stream_t stream) {
+  if (!a_scale_a || !a_zp_a || !a_scale_b || !a_zp_b) return MIXDQ_ERR_INVALID_ARG;
+  return split_common(xa, lda, wa, Ca, wsum_a, w_scale_a, a_scale_a, a_zp_a, xb, ldb, wb, Cb, wsum_b,
+                      w_scale_b, a_scale_b, a_zp_b, bias, residual, ldr, y, ldy, M, K,
+                      static_cast<cudaStream_t>(stream));
 }

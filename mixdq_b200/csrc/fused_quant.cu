@@ -1,0 +1,569 @@
+// fused_quant.cu — producer-side fusion of the dynamic activation-quantise pass:
+// the op that PRODUCES a quantized layer's input and the qdiff min-max quantisation of its result
+// run as ONE kernel, so the fp16 intermediate never travels to HBM and back:
+//
+//   LayerNorm            -> int8   feeds attn1.to_q/k/v, attn2.to_q, ff.net.0.proj
+//   GEGLU  h * gelu(g)   -> int8   feeds ff.net.2
+//   GroupNorm [+ SiLU]   -> int8   feeds resnet conv1 / conv2 (NHWC) and Transformer2D.proj_in
+//
+// Arithmetic contract. Each kernel reproduces the UNFUSED sequence the reference runs (stock
+// PyTorch fp16 op(s), then quantisation): the op is evaluated in fp32 and ROUNDED TO FP16 at
+// every point where PyTorch materialises an fp16 tensor (LayerNorm output; GroupNorm output, SiLU
+// output; GELU output, the h*gelu product); min/max and the codes are then taken from those fp16
+// values with the qdiff formula in fp32 (quant_ws.cuh) — bit-exact given the fp16 values. The
+// fp32 op itself (mean/variance summation order) is a floating-point restatement, compared with
+// a stated tolerance in tests/.
+//
+// Structure of every kernel: phase 1 computes the fp16 values of the CTA's rows into a shared
+// memory stash (up to ~200 KB per CTA) while tracking min/max; a grid barrier (all CTAs
+// co-resident: grid <= 148, one CTA per SM) turns the partial min/max into (delta, z); phase 2
+// quantises from the stash with 8-byte coalesced stores. Rows that do not fit the stash are
+// recomputed in phase 2 (their inputs are L2-resident by then). GroupNorm has one more barrier in
+// front for the per-(image, group) statistics, accumulated as fixed-point integers so the result
+// does not depend on the arrival order of the CTAs.
+#include "common.cuh"
+#include "quant_ws.cuh"
+#include "../../include/mixdq_b200.h"
+
+namespace mixdq {
+
+constexpr int kFqThreads = 512;
+constexpr int kFqWarps = kFqThreads / 32;
+constexpr int kFqMaxSmem = 200 * 1024;     // stash budget per CTA
+constexpr int kNumSm = 148;
+
+__device__ __forceinline__ int4 ldg16(const void* p) {
+  return __ldg(reinterpret_cast<const int4*>(p));
+}
+
+__device__ __forceinline__ void unpack8(const int4& raw, float (&f)[8]) {
+  const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h2[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ int4 pack8(const float (&f)[8]) {
+  int4 r;
+  __half2* h2 = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h2[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return r;
+}
+
+// =============================================================================================
+// LayerNorm -> int8
+// =============================================================================================
+constexpr int kLnMaxChunks = 8;   // 16-byte chunks per lane: C <= 8 * 32 * 8 = 2048
+                                  // (instantiated for 5 -> C <= 1280, every UNet here, and 8)
+
+// y[row] (8 halves per chunk, chunks lane, lane+32, ...) of one row held by one warp.
+// PyTorch: out = half(gamma * (rstd * (x - mean)) + beta), statistics in fp32, biased variance.
+template <int MAXCH>
+__device__ __forceinline__ void ln_row(const __half* __restrict__ xrow, int nchunks, int C,
+                                       const __half* __restrict__ gamma,
+                                       const __half* __restrict__ beta, float eps, int lane,
+                                       int4 (&y)[MAXCH]) {
+  float v[MAXCH][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) {
+      unpack8(ldg16(xrow + 8 * c), v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[i][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / static_cast<float>(C);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; ss += d * d; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / static_cast<float>(C) + eps);
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) {
+      float g[8], b[8], o[8];
+      unpack8(ldg16(gamma + 8 * c), g);
+      unpack8(ldg16(beta + 8 * c), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(g[j], rstd * (v[i][j] - mean), b[j]);
+      y[i] = pack8(o);
+    }
+  }
+}
+
+template <int MAXCH>
+__global__ void __launch_bounds__(kFqThreads, 1)
+ln_quant_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
+                const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps,
+                int8_t* __restrict__ q, __half* __restrict__ y_out, DynWs* __restrict__ ws,
+                float* __restrict__ scale_out, float* __restrict__ zp_out, int rows_per_cta,
+                int stash_rows) {
+  extern __shared__ int4 stash[];   // [stash_rows][C/8]
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = C >> 3;
+  const int row0 = blockIdx.x * rows_per_cta;
+  const int row1 = min(M, row0 + rows_per_cta);
+  float mn = 0.f, mx = 0.f;
+  for (int r = row0 + warp; r < row1; r += kFqWarps) {
+    int4 y[MAXCH];
+    ln_row<MAXCH>(x + static_cast<int64_t>(r) * ldx, nchunks, C, gamma, beta, eps, lane, y);
+    const int lr = r - row0;
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) {
+        minmax_vec8(y[i], mn, mx);
+        if (lr < stash_rows) stash[lr * nchunks + c] = y[i];
+        if (y_out) reinterpret_cast<int4*>(y_out + static_cast<int64_t>(r) * C)[c] = y[i];
+      }
+    }
+  }
+  float delta, z;
+  grid_minmax_params<kFqThreads>(ws, mn, mx, scale_out, zp_out, delta, z);
+  for (int r = row0 + warp; r < row1; r += kFqWarps) {
+    const int lr = r - row0;
+    uint2* qrow = reinterpret_cast<uint2*>(q + static_cast<int64_t>(r) * C);
+    if (lr < stash_rows) {
+      for (int c = lane; c < nchunks; c += 32) qrow[c] = qdiff_vec8(stash[lr * nchunks + c], delta, z);
+    } else {
+      int4 y[MAXCH];
+      ln_row<MAXCH>(x + static_cast<int64_t>(r) * ldx, nchunks, C, gamma, beta, eps, lane, y);
+#pragma unroll
+      for (int i = 0; i < MAXCH; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nchunks) qrow[c] = qdiff_vec8(y[i], delta, z);
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// GEGLU -> int8      hg = [M][2*I] fp16 (first half h, second half gate)
+// PyTorch: gelu = half(0.5 * g * (1 + erf(g / sqrt(2))))   (F.gelu, approximate='none', fp32 math)
+//          y    = half(float(h) * float(gelu))
+// =============================================================================================
+__device__ __forceinline__ int4 geglu_vec8(const int4& hraw, const int4& graw) {
+  float h[8], g[8], o[8];
+  unpack8(hraw, h);
+  unpack8(graw, g);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float ge = 0.5f * g[j] * (1.0f + erff(g[j] * 0.70710678118654752440f));
+    o[j] = h[j] * __half2float(__float2half_rn(ge));
+  }
+  return pack8(o);
+}
+
+__global__ void __launch_bounds__(kFqThreads, 1)
+geglu_quant_kernel(const __half* __restrict__ hg, int64_t ld, int M, int I,
+                   int8_t* __restrict__ q, __half* __restrict__ y_out, DynWs* __restrict__ ws,
+                   float* __restrict__ scale_out, float* __restrict__ zp_out, int rows_per_cta,
+                   int stash_rows) {
+  extern __shared__ int4 stash[];   // [stash_rows][I/8]
+  pdl_launch_dependents();
+  const int nchunks = I >> 3;
+  const int row0 = blockIdx.x * rows_per_cta;
+  const int row1 = min(M, row0 + rows_per_cta);
+  const int64_t items = static_cast<int64_t>(row1 - row0) * nchunks;
+  float mn = 0.f, mx = 0.f;
+  for (int64_t it = threadIdx.x; it < items; it += kFqThreads) {
+    const int lr = static_cast<int>(it / nchunks);
+    const int c = static_cast<int>(it - static_cast<int64_t>(lr) * nchunks);
+    const __half* row = hg + static_cast<int64_t>(row0 + lr) * ld;
+    const int4 y = geglu_vec8(ldg16(row + 8 * c), ldg16(row + I + 8 * c));
+    minmax_vec8(y, mn, mx);
+    if (lr < stash_rows) stash[it] = y;
+    if (y_out) reinterpret_cast<int4*>(y_out + static_cast<int64_t>(row0 + lr) * I)[c] = y;
+  }
+  float delta, z;
+  grid_minmax_params<kFqThreads>(ws, mn, mx, scale_out, zp_out, delta, z);
+  for (int64_t it = threadIdx.x; it < items; it += kFqThreads) {
+    const int lr = static_cast<int>(it / nchunks);
+    const int c = static_cast<int>(it - static_cast<int64_t>(lr) * nchunks);
+    int4 y;
+    if (lr < stash_rows) {
+      y = stash[it];
+    } else {
+      const __half* row = hg + static_cast<int64_t>(row0 + lr) * ld;
+      y = geglu_vec8(ldg16(row + 8 * c), ldg16(row + I + 8 * c));
+    }
+    reinterpret_cast<uint2*>(q + static_cast<int64_t>(row0 + lr) * I)[c] = qdiff_vec8(y, delta, z);
+  }
+}
+
+// =============================================================================================
+// plain dynamic quantisation of a row-pitched view [M][cols] (pitch ldx) -> dense int8 [M][cols]:
+// channel slices of NHWC tensors (split shortcuts), attention outputs, token slices.
+// =============================================================================================
+__global__ void __launch_bounds__(kFqThreads, 1)
+rows_quant_kernel(const __half* __restrict__ x, int64_t ldx, int M, int cols,
+                  int8_t* __restrict__ q, DynWs* __restrict__ ws, float* __restrict__ scale_out,
+                  float* __restrict__ zp_out, int rows_per_cta, int stash_rows) {
+  extern __shared__ int4 stash[];   // [stash_rows][cols/8]
+  pdl_launch_dependents();
+  const int nchunks = cols >> 3;
+  const int row0 = blockIdx.x * rows_per_cta;
+  const int row1 = min(M, row0 + rows_per_cta);
+  const int64_t items = static_cast<int64_t>(row1 - row0) * nchunks;
+  float mn = 0.f, mx = 0.f;
+  for (int64_t it = threadIdx.x; it < items; it += kFqThreads) {
+    const int lr = static_cast<int>(it / nchunks);
+    const int c = static_cast<int>(it - static_cast<int64_t>(lr) * nchunks);
+    const int4 y = ldg16(x + static_cast<int64_t>(row0 + lr) * ldx + 8 * c);
+    minmax_vec8(y, mn, mx);
+    if (lr < stash_rows) stash[it] = y;
+  }
+  float delta, z;
+  grid_minmax_params<kFqThreads>(ws, mn, mx, scale_out, zp_out, delta, z);
+  for (int64_t it = threadIdx.x; it < items; it += kFqThreads) {
+    const int lr = static_cast<int>(it / nchunks);
+    const int c = static_cast<int>(it - static_cast<int64_t>(lr) * nchunks);
+    const int4 y = (lr < stash_rows) ? stash[it]
+                                     : ldg16(x + static_cast<int64_t>(row0 + lr) * ldx + 8 * c);
+    reinterpret_cast<uint2*>(q + static_cast<int64_t>(row0 + lr) * cols)[c] = qdiff_vec8(y, delta, z);
+  }
+}
+
+// =============================================================================================
+// GroupNorm [+ SiLU] -> int8, NHWC:  x = [NB][HW][C] fp16 (pixel pitch ldx), G groups of C/G
+// consecutive channels.
+// PyTorch: mean/rstd per (n, group) in fp32; y = half(fma(x, a, b)), a = rstd*gamma[c],
+//          b = beta[c] - mean*a; SiLU: half(y / (1 + exp(-y))) on the fp16 y.
+// Each CTA works on rows (pixels) of ONE image; a lane owns the same channel chunks in every row,
+// so its per-group partial sums live in registers across the CTA's rows.
+// =============================================================================================
+constexpr int kGnMaxChunks = 10;  // chunks per lane: C <= 10 * 32 * 8 = 2560
+constexpr double kFixSum = 16777216.0;   // 2^24
+constexpr double kFixSq = 4096.0;        // 2^12
+
+__device__ __forceinline__ float silu_half(float y) {
+  const float yh = __half2float(__float2half_rn(y));          // GroupNorm output tensor (fp16)
+  return yh / (1.0f + expf(-yh));
+}
+
+template <bool SILU>
+__device__ __forceinline__ int4 gn_vec8(const int4& raw, int c8, int cpg,
+                                        const float* __restrict__ s_mean,
+                                        const float* __restrict__ s_rstd,
+                                        const __half* __restrict__ gamma,
+                                        const __half* __restrict__ beta) {
+  float v[8], g[8], b[8], o[8];
+  unpack8(raw, v);
+  unpack8(ldg16(gamma + c8), g);
+  unpack8(ldg16(beta + c8), b);
+  const int g0 = c8 / cpg;
+  const int split = (g0 + 1) * cpg - c8;      // elements [0, split) belong to group g0
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int gi = j < split ? g0 : g0 + 1;
+    const float a = s_rstd[gi] * g[j];
+    const float bb = fmaf(-s_mean[gi], a, b[j]);
+    const float y = fmaf(v[j], a, bb);
+    o[j] = SILU ? silu_half(y) : y;
+  }
+  return pack8(o);
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(kFqThreads, 1)
+gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C, int G,
+                const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps,
+                int8_t* __restrict__ q, __half* __restrict__ y_out, DynWs* __restrict__ ws,
+                float* __restrict__ scale_out, float* __restrict__ zp_out, int ctas_per_image,
+                int rows_per_cta, int stash_rows) {
+  extern __shared__ int4 stash[];   // [stash_rows][C/8]
+  __shared__ float s_mean[32], s_rstd[32];
+  __shared__ int s_last;
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = C >> 3;
+  const int cpg = C / G;
+  const int n = blockIdx.x / ctas_per_image;
+  const int row0 = (blockIdx.x - n * ctas_per_image) * rows_per_cta;
+  const int row1 = min(HW, row0 + rows_per_cta);
+  const __half* ximg = x + static_cast<int64_t>(n) * HW * ldx;
+
+  // ---- phase 0: per-(n, group) sum / sum of squares ----
+  float acc[kGnMaxChunks][4];   // per owned chunk: (sum, sq) of its low group, (sum, sq) of its high group
+#pragma unroll
+  for (int i = 0; i < kGnMaxChunks; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  for (int r = row0 + warp; r < row1; r += kFqWarps) {
+    const __half* xrow = ximg + static_cast<int64_t>(r) * ldx;
+#pragma unroll
+    for (int i = 0; i < kGnMaxChunks; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) {
+        float v[8];
+        unpack8(ldg16(xrow + 8 * c), v);
+        const int c8 = 8 * c;
+        const int split = (c8 / cpg + 1) * cpg - c8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < split) { acc[i][0] += v[j]; acc[i][1] = fmaf(v[j], v[j], acc[i][1]); }
+          else           { acc[i][2] += v[j]; acc[i][3] = fmaf(v[j], v[j], acc[i][3]); }
+        }
+      }
+    }
+  }
+  // fixed-order (deterministic) reduction inside the CTA, using the not-yet-needed stash as
+  // scratch: lanes publish their chunk partials [warp][chunk] -> one thread per chunk sums the
+  // warps -> one thread per (group, quantity) sums the chunks that overlap the group.
+  float4* part = reinterpret_cast<float4*>(stash);          // [kFqWarps][nchunks]
+#pragma unroll
+  for (int i = 0; i < kGnMaxChunks; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) part[warp * nchunks + c] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < nchunks; c += kFqThreads) {
+    float4 t = part[c];
+#pragma unroll
+    for (int w = 1; w < kFqWarps; ++w) {
+      const float4 u = part[w * nchunks + c];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    part[c] = t;     // only this thread touches column c
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * G) {
+    const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
+    const int c_lo = (g * cpg) >> 3, c_hi = ((g + 1) * cpg - 1) >> 3;
+    float t = 0.f;
+    for (int c = c_lo; c <= c_hi; ++c) {
+      const float4 u = part[c];
+      const int g0 = (8 * c) / cpg;
+      if (g0 == g) t += k ? u.y : u.x;
+      else if (g0 + 1 == g) t += k ? u.w : u.z;
+    }
+    const long long fixed = __double2ll_rn(static_cast<double>(t) * (k ? kFixSq : kFixSum));
+    atomicAdd(&ws->gsum[(n * G) * 2 + threadIdx.x], static_cast<unsigned long long>(fixed));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&ws->counter2, 1u) == gridDim.x - 1) {
+      __threadfence();
+      st_release_u32(&ws->flag2, 1u);
+    }
+    spin_until_set(&ws->flag2);
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const long long fs = static_cast<long long>(__ldcg(&ws->gsum[(n * G + threadIdx.x) * 2]));
+    const long long fq = static_cast<long long>(__ldcg(&ws->gsum[(n * G + threadIdx.x) * 2 + 1]));
+    const double cnt = static_cast<double>(HW) * cpg;
+    const double mean = static_cast<double>(fs) / kFixSum / cnt;
+    double var = static_cast<double>(fq) / kFixSq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = rsqrtf(static_cast<float>(var) + eps);
+  }
+  __syncthreads();
+  // the last CTA to have read the statistics re-zeroes them for the next call
+  if (threadIdx.x == 0) s_last = (atomicAdd(&ws->done2, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (s_last) {
+    for (int i = threadIdx.x; i < NB * G * 2; i += kFqThreads) ws->gsum[i] = 0ull;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ws->counter2 = 0; ws->done2 = 0;
+      __threadfence();
+      st_release_u32(&ws->flag2, 0u);
+    }
+  }
+
+  // ---- phase 1: normalise (+SiLU) -> fp16 -> stash, min/max ----
+  float mn = 0.f, mx = 0.f;
+  for (int r = row0 + warp; r < row1; r += kFqWarps) {
+    const __half* xrow = ximg + static_cast<int64_t>(r) * ldx;
+    const int lr = r - row0;
+    for (int c = lane; c < nchunks; c += 32) {
+      const int4 y = gn_vec8<SILU>(ldg16(xrow + 8 * c), 8 * c, cpg, s_mean, s_rstd, gamma, beta);
+      minmax_vec8(y, mn, mx);
+      if (lr < stash_rows) stash[lr * nchunks + c] = y;
+      if (y_out)
+        reinterpret_cast<int4*>(y_out + (static_cast<int64_t>(n) * HW + r) * C)[c] = y;
+    }
+  }
+  float delta, z;
+  grid_minmax_params<kFqThreads>(ws, mn, mx, scale_out, zp_out, delta, z);
+  // ---- phase 2: quantise ----
+  for (int r = row0 + warp; r < row1; r += kFqWarps) {
+    const int lr = r - row0;
+    uint2* qrow = reinterpret_cast<uint2*>(q + (static_cast<int64_t>(n) * HW + r) * C);
+    const __half* xrow = ximg + static_cast<int64_t>(r) * ldx;
+    for (int c = lane; c < nchunks; c += 32) {
+      const int4 y = (lr < stash_rows)
+                         ? stash[lr * nchunks + c]
+                         : gn_vec8<SILU>(ldg16(xrow + 8 * c), 8 * c, cpg, s_mean, s_rstd, gamma, beta);
+      qrow[c] = qdiff_vec8(y, delta, z);
+    }
+  }
+}
+
+template <typename K>
+static int set_smem(K kern, int bytes) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) ==
+                 cudaSuccess
+             ? 0
+             : -1;
+}
+
+}  // namespace mixdq
+
+using namespace mixdq;
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+#define MIXDQ_CHECK_LAUNCH()                                   \
+  do {                                                         \
+    if (cudaGetLastError() != cudaSuccess) return MIXDQ_ERR_CUDA; \
+  } while (0)
+
+// rows of `row_bytes` fp16-stash bytes each, distributed over <= 148 co-resident CTAs
+static void plan_rows(int64_t rows, int64_t row_bytes, int min_rows_per_cta, int* grid,
+                      int* rows_per_cta, int* stash_rows, int* smem) {
+  int64_t g = (rows + min_rows_per_cta - 1) / min_rows_per_cta;
+  if (g > kNumSm) g = kNumSm;
+  if (g < 1) g = 1;
+  const int64_t rpc = (rows + g - 1) / g;
+  g = (rows + rpc - 1) / rpc;
+  int64_t srows = kFqMaxSmem / row_bytes;
+  if (srows > rpc) srows = rpc;
+  *grid = static_cast<int>(g);
+  *rows_per_cta = static_cast<int>(rpc);
+  *stash_rows = static_cast<int>(srows);
+  *smem = static_cast<int>(srows * row_bytes);
+}
+
+extern "C" int mixdq_ln_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int M, int C,
+                                         const mixdq_half_t* gamma, const mixdq_half_t* beta,
+                                         float eps, int8_t* q, mixdq_half_t* y_out,
+                                         float* scale_out, float* zp_out, void* ws,
+                                         mixdq_stream_t stream) {
+  if (M <= 0 || C <= 0 || !x || !gamma || !beta || !q || !scale_out || !zp_out || !ws || ldx < C)
+    return MIXDQ_ERR_INVALID_ARG;
+  if ((C & 7) || (ldx & 7) || !al16(x) || !al16(gamma) || !al16(beta) || !al16(q) ||
+      (y_out && !al16(y_out)))
+    return MIXDQ_ERR_ALIGNMENT;
+  if (C > kLnMaxChunks * 256) return MIXDQ_ERR_UNSUPPORTED;
+  static bool attr = false;
+  if (!attr) {
+    if (set_smem(ln_quant_kernel<5>, kFqMaxSmem) || set_smem(ln_quant_kernel<8>, kFqMaxSmem))
+      return MIXDQ_ERR_CUDA;
+    attr = true;
+  }
+  int grid, rpc, srows, smem;
+  plan_rows(M, static_cast<int64_t>(C) * 2, 8, &grid, &rpc, &srows, &smem);
+  auto kern = (C <= 5 * 256) ? ln_quant_kernel<5> : ln_quant_kernel<8>;
+  kern<<<grid, kFqThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), ldx, M, C, reinterpret_cast<const __half*>(gamma),
+      reinterpret_cast<const __half*>(beta), eps, q, reinterpret_cast<__half*>(y_out),
+      static_cast<DynWs*>(ws), scale_out, zp_out, rpc, srows);
+  MIXDQ_CHECK_LAUNCH();
+  return MIXDQ_OK;
+}
+
+extern "C" int mixdq_geglu_quant_i8_dynamic(const mixdq_half_t* hg, int64_t ld, int M, int I,
+                                            int8_t* q, mixdq_half_t* y_out, float* scale_out,
+                                            float* zp_out, void* ws, mixdq_stream_t stream) {
+  if (M <= 0 || I <= 0 || !hg || !q || !scale_out || !zp_out || !ws || ld < 2 * static_cast<int64_t>(I))
+    return MIXDQ_ERR_INVALID_ARG;
+  if ((I & 7) || (ld & 7) || !al16(hg) || !al16(q) || (y_out && !al16(y_out)))
+    return MIXDQ_ERR_ALIGNMENT;
+  static bool attr = false;
+  if (!attr) { if (set_smem(geglu_quant_kernel, kFqMaxSmem)) return MIXDQ_ERR_CUDA; attr = true; }
+  int grid, rpc, srows, smem;
+  plan_rows(M, static_cast<int64_t>(I) * 2, 1, &grid, &rpc, &srows, &smem);
+  geglu_quant_kernel<<<grid, kFqThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(hg), ld, M, I, q, reinterpret_cast<__half*>(y_out),
+      static_cast<DynWs*>(ws), scale_out, zp_out, rpc, srows);
+  MIXDQ_CHECK_LAUNCH();
+  return MIXDQ_OK;
+}
+
+extern "C" int mixdq_quant_i8_dynamic_rows(const mixdq_half_t* x, int64_t ldx, int M, int cols,
+                                           int8_t* q, float* scale_out, float* zp_out, void* ws,
+                                           mixdq_stream_t stream) {
+  if (M <= 0 || cols <= 0 || !x || !q || !scale_out || !zp_out || !ws || ldx < cols)
+    return MIXDQ_ERR_INVALID_ARG;
+  if ((cols & 7) || (ldx & 7) || !al16(x) || !al16(q)) return MIXDQ_ERR_ALIGNMENT;
+  static bool attr = false;
+  if (!attr) { if (set_smem(rows_quant_kernel, kFqMaxSmem)) return MIXDQ_ERR_CUDA; attr = true; }
+  int grid, rpc, srows, smem;
+  // >= 64 KB of fp16 per CTA keeps small tensors on few CTAs (cheap barrier)
+  int min_rows = static_cast<int>((32768 + cols - 1) / cols);
+  if (min_rows < 1) min_rows = 1;
+  plan_rows(M, static_cast<int64_t>(cols) * 2, min_rows, &grid, &rpc, &srows, &smem);
+  rows_quant_kernel<<<grid, kFqThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), ldx, M, cols, q, static_cast<DynWs*>(ws), scale_out,
+      zp_out, rpc, srows);
+  MIXDQ_CHECK_LAUNCH();
+  return MIXDQ_OK;
+}
+
+extern "C" int mixdq_gn_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int NB, int HW, int C,
+                                         int G, const mixdq_half_t* gamma,
+                                         const mixdq_half_t* beta, float eps, int silu, int8_t* q,
+                                         mixdq_half_t* y_out, float* scale_out, float* zp_out,
+                                         void* ws, mixdq_stream_t stream) {
+  if (NB <= 0 || HW <= 0 || C <= 0 || G <= 0 || !x || !gamma || !beta || !q || !scale_out ||
+      !zp_out || !ws || ldx < C)
+    return MIXDQ_ERR_INVALID_ARG;
+  if ((C & 7) || (ldx & 7) || !al16(x) || !al16(gamma) || !al16(beta) || !al16(q) ||
+      (y_out && !al16(y_out)))
+    return MIXDQ_ERR_ALIGNMENT;
+  const int cpg = C / G;
+  // a 16-byte chunk of 8 channels must touch at most two groups
+  const bool two_groups = (C % G == 0) && (cpg >= 8 || cpg == 4);
+  if (!two_groups || G > 32 || C > kGnMaxChunks * 256 || NB > kNumSm ||
+      static_cast<int64_t>(NB) * G > kMaxStatGroups)
+    return MIXDQ_ERR_UNSUPPORTED;
+  static bool attr = false;
+  if (!attr) {
+    if (set_smem(gn_quant_kernel<true>, kFqMaxSmem) || set_smem(gn_quant_kernel<false>, kFqMaxSmem))
+      return MIXDQ_ERR_CUDA;
+    attr = true;
+  }
+  int cpi = kNumSm / NB;                       // CTAs per image, all co-resident
+  const int max_useful = (HW + 3) / 4;         // >= 4 rows per CTA
+  if (cpi > max_useful) cpi = max_useful;
+  if (cpi < 1) cpi = 1;
+  int rpc = (HW + cpi - 1) / cpi;
+  cpi = (HW + rpc - 1) / rpc;
+  int64_t srows = kFqMaxSmem / (static_cast<int64_t>(C) * 2);
+  if (srows > rpc) srows = rpc;
+  int smem = static_cast<int>(srows * C * 2);
+  const int scratch = kFqWarps * (C / 8) * 16;   // phase-0 partials [warps][chunks] float4
+  if (smem < scratch) smem = scratch;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (silu)
+    gn_quant_kernel<true><<<NB * cpi, kFqThreads, smem, st>>>(
+        reinterpret_cast<const __half*>(x), ldx, NB, HW, C, G, reinterpret_cast<const __half*>(gamma),
+        reinterpret_cast<const __half*>(beta), eps, q, reinterpret_cast<__half*>(y_out),
+        static_cast<DynWs*>(ws), scale_out, zp_out, cpi, rpc, static_cast<int>(srows));
+  else
+    gn_quant_kernel<false><<<NB * cpi, kFqThreads, smem, st>>>(
+        reinterpret_cast<const __half*>(x), ldx, NB, HW, C, G, reinterpret_cast<const __half*>(gamma),
+        reinterpret_cast<const __half*>(beta), eps, q, reinterpret_cast<__half*>(y_out),
+        static_cast<DynWs*>(ws), scale_out, zp_out, cpi, rpc, static_cast<int>(srows));
+  MIXDQ_CHECK_LAUNCH();
+  return MIXDQ_OK;
+}

@@ -8,6 +8,7 @@
 // Layout variants: flat dense, 3-D strided view -> dense rows, NCHW(strided) -> NHWC transpose.
 // All loads are 16-byte (8 halves), all stores 8-byte (8 codes) on the vector paths.
 #include "common.cuh"
+#include "quant_ws.cuh"
 #include "../../include/mixdq_b200.h"
 
 namespace mixdq {
@@ -189,34 +190,7 @@ quant_nchw2nhwc_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int
 // the others spin on it with an acquire load. Each thread keeps its first kDynCache 16-byte
 // vectors in registers, so tensors up to 296*256*kDynCache*8 elements (4.8 M: every layer of the
 // batch-1 SDXL step) are read from memory exactly once; larger tensors are re-read (L2 hits).
-constexpr int kMaxPartials = 1024;
 constexpr int kDynCache = 8;
-struct DynWs {
-  unsigned int counter;   // arrivals at the barrier
-  unsigned int flag;      // raised by the last arriver once scale/zp are published
-  unsigned int done;      // CTAs that have consumed the flag (last one resets the workspace)
-  unsigned int pad;
-  float2 partial[kMaxPartials];
-};
-
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__device__ __forceinline__ void minmax_vec8(const int4& raw, float& mn, float& mx) {
-  const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float2 f = __half22float2(h2[j]);
-    mn = fminf(mn, fminf(f.x, f.y));
-    mx = fmaxf(mx, fmaxf(f.x, f.y));
-  }
-}
 
 __global__ void __launch_bounds__(kQuantThreads)
 quant_dynamic_fused_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int64_t numel,
@@ -246,76 +220,8 @@ quant_dynamic_fused_kernel(const __half* __restrict__ x, int8_t* __restrict__ q,
     mn = fminf(mn, tailv);
     mx = fmaxf(mx, tailv);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  }
-  __shared__ float smn[kQuantThreads / 32], smx[kQuantThreads / 32];
-  __shared__ float s_delta, s_z;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { smn[warp] = mn; smx[warp] = mx; }
-  __syncthreads();
-  if (warp == 0) {
-    mn = lane < kQuantThreads / 32 ? smn[lane] : 0.0f;
-    mx = lane < kQuantThreads / 32 ? smx[lane] : 0.0f;
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    }
-    unsigned int last = 0;
-    if (lane == 0) {
-      ws->partial[blockIdx.x] = make_float2(mn, mx);
-      __threadfence();
-      last = (atomicAdd(&ws->counter, 1u) == gridDim.x - 1) ? 1u : 0u;
-    }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {
-      __threadfence();
-      mn = 0.0f; mx = 0.0f;
-      for (int i = lane; i < static_cast<int>(gridDim.x); i += 32) {
-        const float2 v = __ldcg(&ws->partial[i]);
-        mn = fminf(mn, v.x);
-        mx = fmaxf(mx, v.y);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      }
-      if (lane == 0) {
-        // delta = (x_max - x_min) / (n_levels - 1); eps clamp (base_quantizer.py:178-182)
-        float delta = __fdiv_rn(__fsub_rn(mx, mn), 255.0f);
-        if (delta < 1e-6f) delta = 1e-6f;
-        // zero_point = round(-x_min / delta) (base_quantizer.py:187)
-        const float z = rintf(__fdiv_rn(-mn, delta));
-        *scale_out = delta;
-        *zp_out = z - 128.0f;
-        __threadfence();
-        st_release_u32(&ws->flag, 1u);
-      }
-    }
-    if (lane == 0) {
-      unsigned int spins = 0;
-      while (ld_acquire_u32(&ws->flag) == 0u) {
-        __nanosleep(40);
-        if (++spins > (1u << 24)) __trap();   // protocol bug: fail instead of hanging the device
-      }
-      s_delta = __ldcg(scale_out);
-      s_z = __ldcg(zp_out) + 128.0f;
-      // the last CTA to consume the flag leaves the workspace ready for the next call
-      if (atomicAdd(&ws->done, 1u) == gridDim.x - 1) {
-        ws->counter = 0; ws->done = 0;
-        __threadfence();
-        st_release_u32(&ws->flag, 0u);
-      }
-    }
-  }
-  __syncthreads();
   QParams p;
-  p.a = s_delta;
-  p.b = s_z;
+  grid_minmax_params<kQuantThreads>(ws, mn, mx, scale_out, zp_out, p.a, p.b);
 #pragma unroll
   for (int u = 0; u < kDynCache; ++u) {
     const int64_t i = i0 + u * stride;

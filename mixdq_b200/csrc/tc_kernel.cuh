@@ -57,7 +57,7 @@ struct TcParams {
   int num_kb1;          // k-blocks of phase 1 (KIND_SPLIT only)
   int splits;           // split-K factor == cluster size along z (1 = no cluster reduction)
   // conv geometry (KIND_CONV)
-  int kb_per_tap, S, pad;
+  int kb_per_tap, S, pad, stride;
   int NB, H, W, P, Q;   // batch, input H/W, output P/Q
   int boxW, boxH, boxN; // pixels covered by one A box: boxN x boxH x boxW (<= 128 rows)
   int tilesQ, tilesP;   // tiles along q and p (tiles along n = gridDim.x / (tilesQ*tilesP))
@@ -71,6 +71,15 @@ struct TcParams {
   const __half* bias;     // [N] or nullptr
   const float* scale1;    // KIND_SPLIT second half
   const float* bias0_1;
+  const float* a_scale1;  // KIND_SPLIT dyn: device scalars of the second half, else nullptr
+  const float* a_zp1;
+  // optional fused elementwise tail (each a separate fp16 op in the reference model, so each
+  // rounds to fp16): D = half(D + chan_add[row / rows_per_img][col] (row pitch ldca)); D = half(D + residual[row][col])
+  const __half* chan_add;
+  int64_t ldca;
+  int64_t rows_per_img;
+  const __half* residual;
+  int64_t ldr;
   __half* D;
   int64_t ldd;
   int32_t* acc_out;       // optional raw accumulator dump [rows][N]
@@ -134,7 +143,7 @@ __device__ __forceinline__ RowInfo row_info(const TcParams& p, int row, int m0, 
     r.ok = (dn < p.boxN) && (n < p.NB) && (pp < p.P) && (qq < p.Q);
     r.out_row = (static_cast<int64_t>(n) * p.P + pp) * p.Q + qq;
     if (p.has_table) {
-      const int h0 = pp - p.pad, w0 = qq - p.pad;
+      const int h0 = pp * p.stride - p.pad, w0 = qq * p.stride - p.pad;
       const int rc = (h0 < 0 ? 1 : 0) | (h0 + 2 >= p.H ? 2 : 0);
       const int sc4 = (w0 < 0 ? 1 : 0) | (w0 + 2 >= p.W ? 2 : 0);
       r.cls = rc * 4 + sc4;
@@ -144,6 +153,31 @@ __device__ __forceinline__ RowInfo row_info(const TcParams& p, int row, int m0, 
     r.out_row = m0 + row;
   }
   return r;
+}
+
+// 8 halves + 8 halves, each sum computed in fp32 and rounded to fp16 (what `a + b` on two fp16
+// tensors does in PyTorch)
+__device__ __forceinline__ uint4 add_half8(const uint4& a, const uint4& b) {
+  uint4 r;
+  const __half2* pa = reinterpret_cast<const __half2*>(&a);
+  const __half2* pb = reinterpret_cast<const __half2*>(&b);
+  __half2* pr = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fa = __half22float2(pa[i]), fb = __half22float2(pb[i]);
+    pr[i] = __floats2half2_rn(__fadd_rn(fa.x, fb.x), __fadd_rn(fa.y, fb.y));
+  }
+  return r;
+}
+// the fused elementwise tail on 8 consecutive output columns of one output row
+__device__ __forceinline__ uint4 epilogue_tail(const TcParams& p, uint4 v, int64_t out_row, int col) {
+  if (p.chan_add != nullptr) {
+    const int64_t img = out_row / p.rows_per_img;
+    v = add_half8(v, __ldcg(reinterpret_cast<const uint4*>(p.chan_add + img * p.ldca + col)));
+  }
+  if (p.residual != nullptr)
+    v = add_half8(v, __ldcg(reinterpret_cast<const uint4*>(p.residual + out_row * p.ldr + col)));
+  return v;
 }
 
 template <int BN, int STAGES, int KIND>
@@ -216,7 +250,10 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop with warp-uniform control flow and ONE elected lane issues
+    // (elect.sync): inside `if (lane == 0)` the compiler cannot prove uniformity and wraps every
+    // uniform-datapath instruction in a waterfall loop.
+    {
       const uint32_t a_bytes = (KIND == KIND_CONV) ? p.a_tx_bytes : static_cast<uint32_t>(L::A_BYTES);
       auto load_w = [&](int kb, int stage) {
         uint8_t* w_dst = sW + stage * L::W_BYTES;
@@ -236,7 +273,8 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int tap = kb / p.kb_per_tap;
           const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
           const int r = tap / p.S, s = tap - r * p.S;
-          tma_load_4d(a_dst, &tmA, &full_bar[stage], c0, tq0 - p.pad + s, tp0 - p.pad + r, tn0);
+          tma_load_4d(a_dst, &tmA, &full_bar[stage], c0, tq0 * p.stride - p.pad + s,
+                      tp0 * p.stride - p.pad + r, tn0);
         } else if (KIND == KIND_SPLIT && kb >= p.num_kb) {
           tma_load_2d(a_dst, &tmA1, &full_bar[stage], (kb - p.num_kb) * BLOCK_K, m0);
         } else {
@@ -247,61 +285,76 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // prologue: weights of the first ring-full of k-blocks do not depend on the preceding
       // kernel -> issue them before the programmatic-dependency wait
       const int npre = (kb_end - kb_begin) < STAGES ? (kb_end - kb_begin) : STAGES;
-      if (!skip) {
+      if (!skip && elect_one()) {
         for (int i = 0; i < npre; ++i) {
           mbar_expect_tx(&full_bar[i], a_bytes + L::W_BYTES);
           load_w(kb_begin + i, i);
         }
       }
-      MIXDQ_DBG(2);                        // first TMA (weights) issued
+      __syncwarp();
+      if (lane == 0) MIXDQ_DBG(2);         // first TMA (weights) issued
       pdl_wait();                          // activations / quantisation scalars are ready
-      for (int i = 0; i < npre; ++i) {
-        if (skip) mbar_arrive(&full_bar[i]);
-        else load_a(kb_begin + i, i);
+      if (elect_one()) {
+        for (int i = 0; i < npre; ++i) {
+          if (skip) mbar_arrive(&full_bar[i]);
+          else load_a(kb_begin + i, i);
+        }
       }
+      __syncwarp();
       int stage = (npre == STAGES) ? 0 : npre;
       uint32_t phase = (npre == STAGES) ? 1 : 0;
       for (int kb = kb_begin + npre; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (skip) {
-          mbar_arrive(&full_bar[stage]);
-        } else {
-          mbar_expect_tx(&full_bar[stage], a_bytes + L::W_BYTES);
-          load_w(kb, stage);
-          load_a(kb, stage);
+        if (elect_one()) {
+          if (skip) {
+            mbar_arrive(&full_bar[stage]);
+          } else {
+            mbar_expect_tx(&full_bar[stage], a_bytes + L::W_BYTES);
+            load_w(kb, stage);
+            load_a(kb, stage);
+          }
         }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      MIXDQ_DBG(3);                        // last TMA issued
+      if (lane == 0) MIXDQ_DBG(3);         // last TMA issued
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp loops, one elected lane issues) ===========
+    {
       int stage = 0; uint32_t phase = 0;
+      // descriptor of stage 0 / k-slice 0; stages and k-slices advance the 16-byte-unit start
+      // address field (the low word) by constants
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
+      const uint64_t w_desc0 = umma_desc_sw128(smem_u32(sW));
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
-        if (kb == kb_begin) MIXDQ_DBG(4);  // first stage landed
+        if (kb == kb_begin && lane == 0) MIXDQ_DBG(4);  // first stage landed
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + stage * L::A_BYTES);
-        const uint32_t w_addr = smem_u32(sW + stage * L::W_BYTES);
         uint32_t d_tmem = tmem_base;
         int kb_in_phase = kb - kb_begin;
         if (KIND == KIND_SPLIT && kb >= p.num_kb) { d_tmem += BN; kb_in_phase = kb - p.num_kb; }
-        if (p.dbg_mode & 1) {
-          mbar_arrive(&empty_bar[stage]);
-        } else {
+        if (elect_one()) {
+          if (p.dbg_mode & 1) {
+            mbar_arrive(&empty_bar[stage]);
+          } else {
+            const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(stage * (L::A_BYTES >> 4));
+            const uint64_t w_desc = w_desc0 + static_cast<uint64_t>(stage * (L::W_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma_i8(d_tmem, umma_desc_sw128(a_addr + k * UMMA_K),
-                    umma_desc_sw128(w_addr + k * UMMA_K), IDESC,
-                    (kb_in_phase | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              umma_i8(d_tmem, a_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)),
+                      w_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)), IDESC,
+                      (kb_in_phase | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
         }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tmem_full_bar);          // accumulators complete
-      MIXDQ_DBG(5);                        // last MMA issued
+      if (elect_one()) umma_commit(tmem_full_bar);   // accumulators complete
+      __syncwarp();
+      if (lane == 0) MIXDQ_DBG(5);         // last MMA issued
     }
   } else {
     // ============ epilogue warps 2..9: stage the per-column operands, wait for the MMAs ========
@@ -323,8 +376,14 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       s_scale[j] = sc; s_bias0[j] = b0; s_bias[j] = bs;
       if (KIND == KIND_SPLIT) {
-        s_extra[j] = ok ? __ldg(p.scale1 + n) : 0.f;
-        s_extra[BN + j] = ok ? __ldg(p.bias0_1 + n) : 0.f;
+        float s1 = ok ? __ldg(p.scale1 + n) : 0.f;
+        float b1 = ok ? __ldg(p.bias0_1 + n) : 0.f;
+        if (p.a_scale1 != nullptr) {
+          s1 = __fmul_rn(s1, __ldcg(p.a_scale1));
+          b1 = __fmul_rn(b1, __ldcg(p.a_zp1));
+        }
+        s_extra[j] = s1;
+        s_extra[BN + j] = b1;
       }
       if (KIND == KIND_CONV && p.has_table) {
         // 3x3 / pad 1: class = rcls*4 + scls, bit0 = first tap cut, bit1 = last tap cut
@@ -456,8 +515,9 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int i = 0; i < LPR; ++i) {
             if (!ro[i].ok) continue;
             const int r = quarter * 32 + i * RPI + lane / LPR;
-            *reinterpret_cast<uint4*>(p.D + ro[i].out_row * p.ldd + n_tile0 + ccol) =
-                *reinterpret_cast<const uint4*>(stage_out + r * L::OUT_PITCH + ccol * 2);
+            *reinterpret_cast<uint4*>(p.D + ro[i].out_row * p.ldd + n_tile0 + ccol) = epilogue_tail(
+                p, *reinterpret_cast<const uint4*>(stage_out + r * L::OUT_PITCH + ccol * 2),
+                ro[i].out_row, n_tile0 + ccol);
           }
         }
       }
@@ -561,8 +621,9 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (n_tile0 + col + 8 > p.N) continue;
       const RowInfo ri = row_info<KIND>(p, row_base + row_local, m0, tn0, tp0, tq0);
       if (!ri.ok) continue;
-      *reinterpret_cast<uint4*>(p.D + ri.out_row * p.ldd + n_tile0 + col) =
-          *reinterpret_cast<const uint4*>(stage_out + row_local * L::OUT_PITCH + col * 2);
+      *reinterpret_cast<uint4*>(p.D + ri.out_row * p.ldd + n_tile0 + col) = epilogue_tail(
+          p, *reinterpret_cast<const uint4*>(stage_out + row_local * L::OUT_PITCH + col * 2),
+          ri.out_row, n_tile0 + col);
     }
   }
   if (threadIdx.x == 64) MIXDQ_DBG(7);    // epilogue done

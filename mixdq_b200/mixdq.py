@@ -119,12 +119,23 @@ def convert_to_quantized(unet, ckpt):
             inplace=True, ckpt=ckpt)
 
 
-def quantize_unet(unet, args, ckpt, bos, bos_dict):
+def quantize_unet(unet, args, ckpt, bos, bos_dict, fuse: Optional[bool] = None):
     """Quantize `unet` in place. `ckpt` is the PTQ checkpoint dict in the kernel format
     (reference kernels/convert_ckpt.py:22-46) or None for dynamic activation quantisation with
-    min-max weight scales."""
+    min-max weight scales.
+
+    `fuse` (extension; the reference signature ends at `bos_dict`): also re-bind the block
+    forwards to the fused kernels (mixdq_b200.fused.fuse_unet). Default: when the model already
+    sits on a CUDA device and the quantisation is dynamic. The module tree, names and buffers of
+    the quantized leaves are the same either way."""
     register_qconfig_from_input_files(unet, args, bos=bos, bos_dict=bos_dict)
     convert_to_quantized(unet, ckpt)
+    if fuse is None:
+        p = next(iter(unet.buffers()), None)
+        fuse = ckpt is None and p is not None and p.device.type == "cuda"
+    if fuse:
+        from .fused import fuse_unet
+        fuse_unet(unet)
     return unet
 
 

@@ -194,6 +194,23 @@ class QuantizedConv2d(nn.Module):
         w_int = getattr(self, "weight_int" + sfx)
         if self.dynamic:
             xs = x if (c0 == 0 and c1 == x.shape[1]) else x[:, c0:c1]
+            ksel = c1 - c0
+            tc_ok = (ksel % 16 == 0 and self.out_channels % 8 == 0 and stride in (1, 2)
+                     and (pad == 0 or (pad == 1 and self.kernel_size[0] == 3)))
+            if tc_ok:
+                # activation scalars are folded inside the kernel epilogue; channel slices of an
+                # NHWC tensor are quantised in place (no slicing copy)
+                if xs is x:
+                    x_int, a_scale, a_zp = ops.quantize_per_tensor_dynamic(
+                        x.contiguous(memory_format=torch.channels_last))
+                else:
+                    x_int, a_scale, a_zp = ops.quantize_nhwc_slice_dynamic(
+                        x.contiguous(memory_format=torch.channels_last), c0, c1)
+                return ops.qconv2d_dynamic_fused(
+                    x_int, w_int, getattr(self, "weight_scales" + sfx), a_scale, a_zp,
+                    getattr(self, "weight_sum_by_input_channels" + sfx) if pad > 0 else None,
+                    getattr(self, "weight_sum_per_output_channel" + sfx) if pad == 0 else None,
+                    bias, stride, pad)
             x_int, a_scale, a_zp = ops.quantize_per_tensor_dynamic(
                 xs.contiguous(memory_format=torch.channels_last))
             scale = getattr(self, "weight_scales" + sfx) * a_scale
@@ -229,6 +246,17 @@ class QuantizedConv2d(nn.Module):
             return ops.qconv1x1_split_w8_a8_ohalf(xa, self.weight_int, self.scale, self.bias0,
                                                   xb, self.weight_int_0, self.scale_0,
                                                   self.bias0_0, self.bias)
+        fused_dyn = (self.dynamic and self.kernel_size[0] == 1 and self.kernel_size[1] == 1
+                     and self.padding[0] == 0 and self.stride[0] == 1 and self.split % 16 == 0
+                     and (C - self.split) % 16 == 0 and self.out_channels % 8 == 0)
+        if fused_dyn:
+            xc = x.contiguous(memory_format=torch.channels_last)
+            xa, sa, za = ops.quantize_nhwc_slice_dynamic(xc, 0, self.split)
+            xb, sb, zb = ops.quantize_nhwc_slice_dynamic(xc, self.split, C)
+            return ops.qconv1x1_split_dynamic_fused(
+                xa, self.weight_int, self.weight_scales, self.weight_sum_per_output_channel, sa, za,
+                xb, self.weight_int_0, self.weight_scales_0, self.weight_sum_per_output_channel_0,
+                sb, zb, self.bias)
         out = self._half(x, "", 0, self.split, self.bias)
         out_0 = self._half(x, "_0", self.split, C, None)   # bias applied once (Conv2d.py:337-339)
         return out + out_0

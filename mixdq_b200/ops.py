@@ -530,3 +530,223 @@ def qconv1x1_split_w8_a8_ohalf(xa_int8, wa_int8, scale_a, bias0_a, xb_int8, wb_i
                 algo_bytes=_gemm_bytes(m, k, ca + cb, k * (ca + cb)) + 8 * k,
                 algo_ops=2 * m * k * (ca + cb))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# dynamic-scale layers with the fused elementwise tail, and producer-fused quantisation
+# (include/mixdq_b200.h "Dynamic-scale variants" / "Producer-side fusion")
+# ---------------------------------------------------------------------------------------------
+def _qp_pair(device):
+    qp = torch.empty(2, dtype=torch.float32, device=device)
+    return qp, qp[0], qp[1]
+
+
+def qlinear_dynamic_fused(input_int8, weight_int8, weight_scale, input_scale, input_zero_point,
+                          weight_sum, bias=None, residual=None,
+                          _acc_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qlinear_w8_a8_ohalf_dynamic followed by `+ residual` (fp16, same shape as the output)
+    inside the epilogue: out = half(float(half(linear)) + float(residual))."""
+    N, K = weight_int8.shape
+    a = input_int8 if input_int8.is_contiguous() else input_int8.contiguous()
+    M = a.numel() // K
+    out = torch.empty((*input_int8.shape[:-1], N), dtype=torch.float16, device=a.device)
+    res_ptr, ldr = None, 0
+    if residual is not None:
+        _check(residual.dtype == torch.float16 and residual.numel() == M * N,
+               "residual should be fp16 of the output's shape")
+        r2 = residual.reshape(M, N)
+        if r2.stride(1) != 1:
+            r2 = r2.contiguous()
+        res_ptr, ldr = r2.data_ptr(), r2.stride(0) if M > 1 else N
+        residual = r2
+    lib = _lib.load()
+    with _DeviceGuard(a):
+        _launch("gemm", lib.mixdq_gemm_w8a8_f16_dyn_res,
+                (a.data_ptr(), K, weight_int8.data_ptr(), weight_scale.data_ptr(),
+                 weight_sum.data_ptr(), input_scale.data_ptr(), input_zero_point.data_ptr(),
+                 _ptr(bias), res_ptr, ldr, out.data_ptr(), N, M, N, K, _ptr(_acc_out)), a,
+                keep=(a, weight_int8, weight_scale, weight_sum, input_scale, input_zero_point,
+                      bias, residual, out, _acc_out),
+                algo_bytes=_gemm_bytes(M, N, K, N * K) + (2 * M * N if residual is not None else 0),
+                algo_ops=2 * M * N * K)
+    return out
+
+
+def qconv2d_dynamic_fused(input_int8, weight_int8, weight_scale, input_scale, input_zero_point,
+                          wsum_krs=None, wsum_k=None, bias=None, stride: int = 1, padding: int = 0,
+                          chan_add=None, residual=None,
+                          _acc_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Dynamic-scale conv (the activation scalars are folded in the epilogue) with the optional
+    fused tails: `+ chan_add[:, :, None, None]` (fp16 [N, K]) then `+ residual` (fp16 NHWC
+    [N, K, P, Q]). input_int8 / weight_int8 must be channels_last."""
+    n, c, h, w = input_int8.shape
+    k, _, r, s = weight_int8.shape
+    p = (h + 2 * padding - r) // stride + 1
+    q = (w + 2 * padding - s) // stride + 1
+    pitch = _nhwc_pitch(input_int8)
+    x = input_int8
+    if pitch is None:
+        x = input_int8.contiguous(memory_format=torch.channels_last)
+        pitch = c
+    wt = weight_int8.contiguous(memory_format=torch.channels_last)
+    out = torch.empty((n, k, p, q), dtype=torch.float16, device=x.device,
+                      memory_format=torch.channels_last)
+    if residual is not None:
+        _check(residual.shape == out.shape and residual.dtype == torch.float16,
+               "residual should be fp16 of the output's shape")
+        if not residual.is_contiguous(memory_format=torch.channels_last):
+            residual = residual.contiguous(memory_format=torch.channels_last)
+    ldca = 0
+    if chan_add is not None:
+        _check(chan_add.dtype == torch.float16 and tuple(chan_add.shape) == (n, k),
+               "chan_add should be fp16 [N, K]")
+        if chan_add.stride(1) != 1 or chan_add.stride(0) % 8 != 0 or chan_add.data_ptr() % 16:
+            chan_add = chan_add.contiguous()
+        ldca = chan_add.stride(0) if n > 1 else k
+    lib = _lib.load()
+    with _DeviceGuard(x):
+        _launch("conv", lib.mixdq_conv_w8a8_f16_dyn,
+                (x.data_ptr(), pitch, wt.data_ptr(), weight_scale.data_ptr(), _ptr(wsum_krs),
+                 _ptr(wsum_k), input_scale.data_ptr(), input_zero_point.data_ptr(), _ptr(bias),
+                 _ptr(chan_add), ldca, _ptr(residual), out.data_ptr(), n, h, w, c, k, r, s, stride,
+                 padding, _ptr(_acc_out)), x,
+                keep=(x, wt, weight_scale, wsum_krs, wsum_k, input_scale, input_zero_point, bias,
+                      chan_add, residual, out, _acc_out),
+                algo_bytes=_gemm_bytes(n * p * q, k, c * h * w // max(p * q, 1), k * c * r * s)
+                + (2 * n * p * q * k if residual is not None else 0),
+                algo_ops=2 * n * p * q * k * c * r * s)
+    return out
+
+
+def qconv1x1_split_dynamic_fused(xa_int8, wa_int8, w_scale_a, wsum_a, a_scale_a, a_zp_a,
+                                 xb_int8, wb_int8, w_scale_b, wsum_b, a_scale_b, a_zp_b,
+                                 bias=None, residual=None) -> torch.Tensor:
+    """Dynamic split shortcut: two channel halves with their own dynamic (scale, zp), one kernel,
+    two accumulators, combined as the reference combines its two fp16 convs."""
+    n, ca, h, w = xa_int8.shape
+    cb = xb_int8.shape[1]
+    k = wa_int8.shape[0]
+    pa, pb = _nhwc_pitch(xa_int8), _nhwc_pitch(xb_int8)
+    if pa is None:
+        xa_int8 = xa_int8.contiguous(memory_format=torch.channels_last); pa = ca
+    if pb is None:
+        xb_int8 = xb_int8.contiguous(memory_format=torch.channels_last); pb = cb
+    wa = wa_int8.reshape(k, ca)
+    wb = wb_int8.reshape(k, cb)
+    out = torch.empty((n, k, h, w), dtype=torch.float16, device=xa_int8.device,
+                      memory_format=torch.channels_last)
+    if residual is not None and not residual.is_contiguous(memory_format=torch.channels_last):
+        residual = residual.contiguous(memory_format=torch.channels_last)
+    lib = _lib.load()
+    with _DeviceGuard(xa_int8):
+        m = n * h * w
+        _launch("conv_split", lib.mixdq_conv1x1_split_w8a8_f16_dyn,
+                (xa_int8.data_ptr(), pa, wa.data_ptr(), ca, wsum_a.data_ptr(), w_scale_a.data_ptr(),
+                 a_scale_a.data_ptr(), a_zp_a.data_ptr(),
+                 xb_int8.data_ptr(), pb, wb.data_ptr(), cb, wsum_b.data_ptr(), w_scale_b.data_ptr(),
+                 a_scale_b.data_ptr(), a_zp_b.data_ptr(), _ptr(bias), _ptr(residual), k,
+                 out.data_ptr(), k, m, k), xa_int8,
+                keep=(xa_int8, wa, wsum_a, w_scale_a, a_scale_a, a_zp_a, xb_int8, wb, wsum_b,
+                      w_scale_b, a_scale_b, a_zp_b, bias, residual, out),
+                algo_bytes=_gemm_bytes(m, k, ca + cb, k * (ca + cb)) + 8 * k,
+                algo_ops=2 * m * k * (ca + cb))
+    return out
+
+
+def layernorm_quantize_dynamic(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
+                               eps: float, return_y: bool = False):
+    """LayerNorm over the last dim + qdiff dynamic quantisation in one kernel.
+    Returns (q int8 [..., C], scale, zero_point[, y fp16])."""
+    _check(x.dtype == torch.float16 and weight.dtype == torch.float16
+           and bias.dtype == torch.float16, "layernorm_quantize_dynamic expects fp16 tensors")
+    C = x.shape[-1]
+    x2 = x.reshape(-1, C)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    q = torch.empty(x.shape, dtype=torch.int8, device=x.device)
+    y = torch.empty(x.shape, dtype=torch.float16, device=x.device) if return_y else None
+    qp, sc, zp = _qp_pair(x.device)
+    lib = _lib.load()
+    with _DeviceGuard(x2):
+        ws = _dynamic_workspace(x2.device)
+        _launch("ln_quant", lib.mixdq_ln_quant_i8_dynamic,
+                (x2.data_ptr(), x2.stride(0) if M > 1 else C, M, C, weight.data_ptr(),
+                 bias.data_ptr(), float(eps), q.data_ptr(), _ptr(y), qp.data_ptr(),
+                 qp.data_ptr() + 4, ws.data_ptr()), x2, keep=(x2, weight, bias, q, y, qp, ws),
+                algo_bytes=3 * M * C)
+    return (q, sc, zp, y) if return_y else (q, sc, zp)
+
+
+def geglu_quantize_dynamic(hg: torch.Tensor, return_y: bool = False):
+    """GEGLU (h * gelu(gate), halves of the last dim) + dynamic quantisation in one kernel."""
+    _check(hg.dtype == torch.float16, "geglu_quantize_dynamic expects fp16")
+    I2 = hg.shape[-1]
+    I = I2 // 2
+    h2 = hg.reshape(-1, I2)
+    if h2.stride(1) != 1:
+        h2 = h2.contiguous()
+    M = h2.shape[0]
+    q = torch.empty((*hg.shape[:-1], I), dtype=torch.int8, device=hg.device)
+    y = torch.empty((*hg.shape[:-1], I), dtype=torch.float16, device=hg.device) if return_y else None
+    qp, sc, zp = _qp_pair(hg.device)
+    lib = _lib.load()
+    with _DeviceGuard(h2):
+        ws = _dynamic_workspace(h2.device)
+        _launch("geglu_quant", lib.mixdq_geglu_quant_i8_dynamic,
+                (h2.data_ptr(), h2.stride(0) if M > 1 else I2, M, I, q.data_ptr(), _ptr(y),
+                 qp.data_ptr(), qp.data_ptr() + 4, ws.data_ptr()), h2, keep=(h2, q, y, qp, ws),
+                algo_bytes=5 * M * I)
+    return (q, sc, zp, y) if return_y else (q, sc, zp)
+
+
+def groupnorm_quantize_dynamic(x: torch.Tensor, num_groups: int, weight: torch.Tensor,
+                               bias: torch.Tensor, eps: float, silu: bool, return_y: bool = False):
+    """GroupNorm [+ SiLU] + dynamic quantisation in one kernel. x: fp16 logical [N,C,H,W] in
+    channels_last memory. Returns (q int8 [N,C,H,W] channels_last, scale, zero_point[, y]).
+    Raises RuntimeError("unsupported configuration") for group shapes the kernel does not take."""
+    _check(x.dtype == torch.float16 and x.dim() == 4, "groupnorm_quantize_dynamic expects fp16 4-D")
+    n, c, h, w = x.shape
+    if _nhwc_pitch(x) != c:
+        x = x.contiguous(memory_format=torch.channels_last)
+    q = torch.empty((n, c, h, w), dtype=torch.int8, device=x.device,
+                    memory_format=torch.channels_last)
+    y = torch.empty((n, c, h, w), dtype=torch.float16, device=x.device,
+                    memory_format=torch.channels_last) if return_y else None
+    qp, sc, zp = _qp_pair(x.device)
+    lib = _lib.load()
+    with _DeviceGuard(x):
+        ws = _dynamic_workspace(x.device)
+        _launch("gn_quant", lib.mixdq_gn_quant_i8_dynamic,
+                (x.data_ptr(), c, n, h * w, c, num_groups, weight.data_ptr(), bias.data_ptr(),
+                 float(eps), 1 if silu else 0, q.data_ptr(), _ptr(y), qp.data_ptr(),
+                 qp.data_ptr() + 4, ws.data_ptr()), x, keep=(x, weight, bias, q, y, qp, ws),
+                algo_bytes=3 * x.numel())
+    return (q, sc, zp, y) if return_y else (q, sc, zp)
+
+
+def quantize_rows_dynamic(x2: torch.Tensor):
+    """A10 on a 2-D row-pitched fp16 view [M, cols] (stride(1) == 1) -> dense int8 [M, cols]."""
+    _check(x2.dtype == torch.float16 and x2.dim() == 2 and x2.stride(1) == 1,
+           "quantize_rows_dynamic expects a 2-D fp16 view with unit inner stride")
+    M, cols = x2.shape
+    q = torch.empty((M, cols), dtype=torch.int8, device=x2.device)
+    qp, sc, zp = _qp_pair(x2.device)
+    lib = _lib.load()
+    with _DeviceGuard(x2):
+        ws = _dynamic_workspace(x2.device)
+        _launch("quant_dyn", lib.mixdq_quant_i8_dynamic_rows,
+                (x2.data_ptr(), x2.stride(0) if M > 1 else cols, M, cols, q.data_ptr(),
+                 qp.data_ptr(), qp.data_ptr() + 4, ws.data_ptr()), x2, keep=(x2, q, qp, ws),
+                algo_bytes=3 * M * cols)
+    return q, sc, zp
+
+
+def quantize_nhwc_slice_dynamic(x: torch.Tensor, c0: int, c1: int):
+    """A10 on channels [c0, c1) of a channels_last fp16 tensor [N,C,H,W] -> dense int8
+    channels_last [N, c1-c0, H, W] (no slicing copy)."""
+    n, c, h, w = x.shape
+    _check(_nhwc_pitch(x) == c, "quantize_nhwc_slice_dynamic expects a dense channels_last tensor")
+    rows = x.permute(0, 2, 3, 1).reshape(n * h * w, c)[:, c0:c1]
+    q, sc, zp = quantize_rows_dynamic(rows)
+    return q.view(n, h, w, c1 - c0).permute(0, 3, 1, 2), sc, zp

@@ -264,3 +264,38 @@ def unpack_int4(packed: torch.Tensor) -> torch.Tensor:
     lo = p & 0xF
     both = torch.stack([hi, lo], dim=-1).reshape(*packed.shape[:-1], packed.shape[-1] * 2)
     return torch.where(both >= 8, both - 16, both).to(torch.int8)
+
+
+# ---------------------------------------------------------------------------------------------
+# Stock fp16 ops AROUND the quantized leaves (the model graph the reference quantizes comes from
+# diffusers / torch.nn, reference kernels/mixdq.py:4,35-41). On the GPU the model runs in fp16:
+# each op computes in fp32 and materialises an fp16 tensor. The fused producer kernels
+# (include/mixdq_b200.h "Producer-side fusion") and the fused epilogue tails must reproduce these
+# sequences; the restatements below are fp32 CPU math with the fp16 roundings at the same points.
+# ---------------------------------------------------------------------------------------------
+def layernorm_fp16(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float
+                   ) -> torch.Tensor:
+    """torch.nn.LayerNorm on an fp16 tensor: fp32 statistics, one rounding to fp16."""
+    return F.layer_norm(x.float(), (x.shape[-1],), weight.float(), bias.float(), eps).half()
+
+
+def geglu_fp16(hg: torch.Tensor) -> torch.Tensor:
+    """diffusers GEGLU on fp16: h, gate = chunk(2); gelu(gate) (exact erf) -> fp16; h * gelu -> fp16."""
+    h, gate = hg.chunk(2, dim=-1)
+    g = F.gelu(gate.float()).half()
+    return (h.float() * g.float()).half()
+
+
+def groupnorm_fp16(x: torch.Tensor, groups: int, weight: torch.Tensor, bias: torch.Tensor,
+                   eps: float, silu: bool) -> torch.Tensor:
+    """torch.nn.GroupNorm on fp16 (fp32 statistics, fp16 result) [+ torch.nn.SiLU on that fp16
+    tensor (fp32 math, fp16 result)]."""
+    y = F.group_norm(x.float(), groups, weight.float(), bias.float(), eps).half()
+    if silu:
+        y = F.silu(y.float()).half()
+    return y
+
+
+def add_fp16(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """`a + b` on two fp16 tensors: fp32 add, one rounding."""
+    return (a.float() + b.float()).half()

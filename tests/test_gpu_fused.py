@@ -1,0 +1,210 @@
+"""Producer-fused quantisation kernels (LayerNorm / GEGLU / GroupNorm[+SiLU] -> int8) and the fused
+elementwise epilogue tails (residual, per-image channel add) against the CPU oracle.
+
+Contract checked (include/mixdq_b200.h):
+  * the QUANTISATION is bit-exact: codes, scale and zero point equal the oracle's A10 formula
+    applied to the fp16 values the kernel itself produced (returned through the y_out hook);
+  * the fp16 values are a floating-point restatement of the stock PyTorch op: compared with the
+    oracle's fp32 CPU evaluation within 2 fp16 ulps, >= 99 % of elements identical;
+  * hence codes vs the fully-CPU pipeline differ by at most 1 step on a small fraction;
+  * the GEMM / conv tails are bit-exact (integer accumulate + separately rounded fp16 adds).
+"""
+import pytest
+import torch
+
+from oracle import qdiff_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from mixdq_b200 import build
+    build.build()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ops(dev):
+    from mixdq_b200 import ops as _ops
+    return _ops
+
+
+def bits(t):
+    return t.detach().cpu().contiguous().view(torch.int16)
+
+
+def check_fp16_restatement(y_gpu, y_ref, abs_floor=0.0, min_same=0.99, ulps=2):
+    """|gpu - ref| <= 2 fp16 ulps of the value (or `abs_floor`: GELU's negative tail is a
+    cancellation, 1 + erf(x) ~ 1e-6, where CUDA erff and the CPU's vectorised erf differ by many
+    RELATIVE ulps on values that are ~1e-5 of the quantisation step)."""
+    a, b = y_gpu.float().cpu(), y_ref.float()
+    ulp = torch.maximum(b.abs(), torch.tensor(6.1e-5)) * 2.0 ** -10
+    tol = torch.clamp(ulps * ulp, min=abs_floor)
+    assert ((a - b).abs() <= tol).all(), ((a - b).abs() / tol).max()
+    same = (bits(y_gpu) == bits(y_ref)).float().mean().item()
+    assert same >= min_same, same
+
+
+def check_quant(q, s, z, y_gpu, y_ref):
+    qr, sr, zr = O.quantize_dynamic_kernel(y_gpu.cpu())
+    assert torch.equal(s.cpu(), sr) and torch.equal(z.cpu(), zr)
+    assert torch.equal(q.cpu(), qr), "INT8 codes differ from the oracle on the kernel's fp16 values"
+    q2, _, _ = O.quantize_dynamic_kernel(y_ref)
+    d = (q.cpu().int() - q2.int()).abs()
+    assert d.max().item() <= 1 and (d != 0).float().mean().item() <= 0.02
+
+
+@pytest.mark.parametrize("M,C", [(256, 1280), (1024, 640), (77, 64), (8192, 640), (300, 2048),
+                                 (4, 1280), (4500, 1280)])
+def test_layernorm_quant(ops, dev, M, C):
+    g = torch.Generator().manual_seed(M + C)
+    x = (torch.randn(M, C, generator=g) * 2 + 0.3).half()
+    w = (1 + 0.2 * torch.randn(C, generator=g)).half()
+    b = (0.1 * torch.randn(C, generator=g)).half()
+    q, s, z, y = ops.layernorm_quantize_dynamic(x.to(dev), w.to(dev), b.to(dev), 1e-5, return_y=True)
+    y_ref = O.layernorm_fp16(x, w, b, 1e-5)
+    check_fp16_restatement(y, y_ref, abs_floor=3e-5)
+    check_quant(q, s, z, y, y_ref)
+    q1, s1, z1 = ops.layernorm_quantize_dynamic(x.to(dev), w.to(dev), b.to(dev), 1e-5)
+    assert torch.equal(q1, q) and torch.equal(s1, s) and torch.equal(z1, z)
+
+
+def test_layernorm_quant_3d_and_repeat(ops, dev):
+    """[B, T, C] input; repeated calls leave the workspace consistent (grid barrier reset)."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 1024, 640, generator=g).half()
+    w = torch.ones(640).half(); b = torch.zeros(640).half()
+    outs = [ops.layernorm_quantize_dynamic(x.to(dev), w.to(dev), b.to(dev), 1e-5) for _ in range(5)]
+    for q, s, z in outs[1:]:
+        assert torch.equal(q, outs[0][0]) and torch.equal(s, outs[0][1])
+    assert outs[0][0].shape == (2, 1024, 640)
+
+
+@pytest.mark.parametrize("M,I", [(256, 5120), (1024, 2560), (77, 128), (8192, 2560), (3, 64)])
+def test_geglu_quant(ops, dev, M, I):
+    g = torch.Generator().manual_seed(M + I)
+    hg = (torch.randn(M, 2 * I, generator=g) * 1.5).half()
+    q, s, z, y = ops.geglu_quantize_dynamic(hg.to(dev), return_y=True)
+    y_ref = O.geglu_fp16(hg)
+    check_fp16_restatement(y, y_ref, abs_floor=2e-4 * y_ref.float().abs().max().item(),
+                           min_same=0.97)
+    check_quant(q, s, z, y, y_ref)
+
+
+@pytest.mark.parametrize("N,C,H,W,G,silu", [
+    (1, 320, 64, 64, 32, True), (1, 640, 32, 32, 32, True), (1, 1280, 16, 16, 32, True),
+    (1, 2560, 16, 16, 32, True), (1, 960, 64, 64, 32, True), (1, 1920, 32, 32, 32, True),
+    (2, 1280, 16, 16, 32, False), (8, 640, 32, 32, 32, False), (3, 64, 8, 8, 16, True),
+    (2, 128, 16, 16, 16, True), (1, 320, 64, 64, 32, False)])
+def test_groupnorm_quant(ops, dev, N, C, H, W, G, silu):
+    g = torch.Generator().manual_seed(N * C + H)
+    x = (torch.randn(N, C, H, W, generator=g) * torch.linspace(0.5, 3.0, C).view(1, C, 1, 1)
+         + torch.linspace(-1, 1, C).view(1, C, 1, 1)).half()
+    w = (1 + 0.2 * torch.randn(C, generator=g)).half()
+    b = (0.1 * torch.randn(C, generator=g)).half()
+    xd = x.to(dev).contiguous(memory_format=torch.channels_last)
+    q, s, z, y = ops.groupnorm_quantize_dynamic(xd, G, w.to(dev), b.to(dev), 1e-5, silu, return_y=True)
+    assert q.is_contiguous(memory_format=torch.channels_last) and q.shape == x.shape
+    y_ref = O.groupnorm_fp16(x, G, w, b, 1e-5, silu)
+    # y = x*a + b cancels for |y| << |x*a|: fp32 evaluation-order differences (~1e-7 * |x*a|) are
+    # an absolute, not a relative, error there -> absolute floor of 3e-5 (1e-3 of a code step)
+    # with SiLU two fp16 roundings compose: a 1-ulp flip of the GroupNorm value moves the SiLU
+    # value by up to ~1.1 ulp more -> 3 ulps
+    check_fp16_restatement(y.contiguous(), y_ref, abs_floor=3e-5, ulps=3 if silu else 2)
+    check_quant(q.contiguous(), s, z, y.contiguous(), y_ref)
+    # deterministic across launches (fixed-point statistics do not depend on CTA arrival order)
+    q2, s2, z2 = ops.groupnorm_quantize_dynamic(xd, G, w.to(dev), b.to(dev), 1e-5, silu)
+    assert torch.equal(q2, q) and torch.equal(s2, s) and torch.equal(z2, z)
+
+
+def test_groupnorm_unsupported_group_shape_raises(ops, dev):
+    x = torch.randn(1, 96, 8, 8).half().to(dev).contiguous(memory_format=torch.channels_last)
+    w = torch.ones(96).half().to(dev)
+    with pytest.raises(RuntimeError):
+        ops.groupnorm_quantize_dynamic(x, 32, w, w, 1e-5, True)     # 3 channels per group
+
+
+@pytest.mark.parametrize("M,cols,pitch", [(4096, 640, 1920), (1024, 1280, 1280), (77, 2048, 2048),
+                                          (300, 64, 192)])
+def test_rows_quant(ops, dev, M, cols, pitch):
+    g = torch.Generator().manual_seed(M)
+    full = (torch.randn(M, pitch, generator=g) * 3).half()
+    view = full.to(dev)[:, pitch - cols:]
+    q, s, z = ops.quantize_rows_dynamic(view)
+    qr, sr, zr = O.quantize_dynamic_kernel(full[:, pitch - cols:].contiguous())
+    assert torch.equal(q.cpu(), qr) and torch.equal(s.cpu(), sr) and torch.equal(z.cpu(), zr)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 1280, 1280), (1024, 640, 2560), (77, 640, 2048),
+                                   (256, 1280, 5120), (2048, 1280, 1280)])
+def test_linear_residual_tail(ops, dev, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).half()
+    w = torch.randint(-127, 128, (N, K), dtype=torch.int8, generator=g)
+    ws = 0.001 + 0.01 * torch.rand(N, generator=g)
+    wsum = w.float().sum(1)
+    bias = torch.randn(N, generator=g).half()
+    res = torch.randn(M, N, generator=g).half()
+    q, s, z = ops.quantize_per_tensor_dynamic(x.to(dev))
+    acc = torch.empty(M, N, dtype=torch.int32, device=dev)
+    y = ops.qlinear_dynamic_fused(q, w.to(dev), ws.to(dev), s, z, wsum.to(dev), bias.to(dev),
+                                  residual=res.to(dev), _acc_out=acc)
+    qr, sr, zr = O.quantize_dynamic_kernel(x)
+    yr, accr = O.qlinear_kernel(qr, w, wsum * zr, ws * sr, bias)
+    assert torch.equal(acc.cpu().long(), accr)
+    assert torch.equal(bits(y), bits(O.add_fp16(yr, res)))
+
+
+@pytest.mark.parametrize("n,h,w_,c,k,r,pad,stride", [
+    (1, 32, 32, 320, 640, 3, 1, 1), (2, 16, 16, 640, 640, 3, 1, 1), (1, 64, 64, 320, 320, 3, 1, 2),
+    (1, 32, 32, 640, 320, 1, 0, 1), (1, 16, 16, 1280, 1280, 3, 1, 1)])
+def test_conv_dynamic_tails(ops, dev, n, h, w_, c, k, r, pad, stride):
+    g = torch.Generator().manual_seed(h + c + k)
+    x = torch.randn(n, c, h, w_, generator=g).half()
+    wt = torch.randint(-127, 128, (k, c, r, r), dtype=torch.int8, generator=g)
+    ws = 0.001 + 0.01 * torch.rand(k, generator=g)
+    bias = torch.randn(k, generator=g).half()
+    P = (h + 2 * pad - r) // stride + 1
+    Q = (w_ + 2 * pad - r) // stride + 1
+    chan = torch.randn(n, k, generator=g).half()
+    res = torch.randn(n, k, P, Q, generator=g).half()
+    xd = x.to(dev).contiguous(memory_format=torch.channels_last)
+    q, s, z = ops.quantize_per_tensor_dynamic(xd)
+    wd = wt.to(dev).contiguous(memory_format=torch.channels_last)
+    wsum_krs = wt.float().sum(1, keepdim=True) if pad > 0 else None
+    wsum_k = wt.float().sum(dim=[1, 2, 3]) if pad == 0 else None
+    y = ops.qconv2d_dynamic_fused(
+        q, wd, ws.to(dev), s, z, None if wsum_krs is None else wsum_krs.to(dev),
+        None if wsum_k is None else wsum_k.to(dev), bias.to(dev), stride, pad,
+        chan_add=chan.to(dev), residual=res.to(dev).contiguous(memory_format=torch.channels_last))
+    qr, sr, zr = O.quantize_dynamic_kernel(x)
+    yr, _ = O.qconv2d_kernel(qr, wt, ws * sr, wsum_krs, None if wsum_k is None else wsum_k * zr,
+                             zr, bias, stride, pad)
+    ref = O.add_fp16(O.add_fp16(yr, chan[:, :, None, None].expand_as(yr)), res)
+    assert torch.equal(bits(y.contiguous()), bits(ref))
+
+
+def test_split_shortcut_dynamic(ops, dev):
+    g = torch.Generator().manual_seed(9)
+    n, ca, cb, k, h = 1, 640, 320, 640, 32
+    x = torch.cat([torch.randn(n, ca, h, h, generator=g) * 2, torch.randn(n, cb, h, h, generator=g) * 0.5 + 0.3], 1).half()
+    wa = torch.randint(-127, 128, (k, ca, 1, 1), dtype=torch.int8, generator=g)
+    wb = torch.randint(-127, 128, (k, cb, 1, 1), dtype=torch.int8, generator=g)
+    wsa, wsb = 0.001 + 0.01 * torch.rand(k, generator=g), 0.001 + 0.01 * torch.rand(k, generator=g)
+    bias = torch.randn(k, generator=g).half()
+    res = torch.randn(n, k, h, h, generator=g).half()
+    xd = x.to(dev).contiguous(memory_format=torch.channels_last)
+    qa, sa, za = ops.quantize_nhwc_slice_dynamic(xd, 0, ca)
+    qb, sb, zb = ops.quantize_nhwc_slice_dynamic(xd, ca, ca + cb)
+    y = ops.qconv1x1_split_dynamic_fused(
+        qa, wa.to(dev), wsa.to(dev), wa.float().sum(dim=[1, 2, 3]).to(dev), sa, za,
+        qb, wb.to(dev), wsb.to(dev), wb.float().sum(dim=[1, 2, 3]).to(dev), sb, zb,
+        bias.to(dev), residual=res.to(dev).contiguous(memory_format=torch.channels_last))
+    qar, sar, zar = O.quantize_dynamic_kernel(x[:, :ca].contiguous())
+    qbr, sbr, zbr = O.quantize_dynamic_kernel(x[:, ca:].contiguous())
+    assert torch.equal(qa.cpu().contiguous(), qar) and torch.equal(qb.cpu().contiguous(), qbr)
+    o0, _ = O.qconv2d_kernel(qar, wa, wsa * sar, None, wa.float().sum(dim=[1, 2, 3]) * zar, 0.0, bias, 1, 0)
+    o1, _ = O.qconv2d_kernel(qbr, wb, wsb * sbr, None, wb.float().sum(dim=[1, 2, 3]) * zbr, 0.0, None, 1, 0)
+    ref = O.add_fp16(O.split_shortcut_kernel(o0, o1), res)
+    assert torch.equal(bits(y.contiguous()), bits(ref))

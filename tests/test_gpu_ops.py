@@ -424,6 +424,8 @@ SDXL_CONVS = [  # (n,h,w,c,k,r,s,pad,stride)
     (1, 32, 32, 320, 640, 1, 1, 0, 1), (1, 16, 16, 640, 1280, 1, 1, 0, 1),
     (2, 8, 8, 1280, 1280, 3, 3, 1, 1), (3, 16, 16, 640, 640, 3, 3, 1, 1),
     (2, 64, 64, 320, 320, 3, 3, 1, 1), (1, 1, 1, 64, 64, 3, 3, 1, 1), (1, 2, 3, 32, 16, 3, 3, 1, 1),
+    (1, 64, 64, 320, 320, 3, 3, 1, 2), (1, 32, 32, 640, 640, 3, 3, 1, 2),   # SDXL downsamplers
+    (2, 14, 14, 512, 1024, 3, 3, 1, 2), (1, 15, 13, 64, 64, 3, 3, 1, 2), (3, 14, 14, 128, 64, 3, 3, 0, 2),
 ]
 
 
@@ -433,7 +435,6 @@ def test_qconv2d_tcgen05_bit_exact(ops, dev, n, h, w, c, k, r, s, pad, stride):
 
 
 @pytest.mark.parametrize("n,h,w,c,k,r,s,pad,stride", [
-    (1, 64, 64, 320, 320, 3, 3, 1, 2), (1, 32, 32, 640, 640, 3, 3, 1, 2),   # SDXL downsamplers
     (1, 64, 64, 4, 320, 3, 3, 1, 1), (1, 64, 64, 320, 4, 3, 3, 1, 1),       # conv_in / conv_out
     (1, 9, 9, 32, 32, 5, 5, 2, 1)])
 def test_qconv2d_other_geometries_bit_exact(ops, dev, n, h, w, c, k, r, s, pad, stride):
