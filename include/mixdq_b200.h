@@ -61,6 +61,10 @@ void        mixdq_debug_set_timing_buffer(void* dev_ptr);
 void        mixdq_debug_set_pdl(int on);
 /* Profiling only (results are garbage): bit0 = skip the MMA issue, bit1 = skip the TMA loads. */
 void        mixdq_debug_set_mode(int mode);
+/* Enable (1, default) / disable (0) the single-cluster variants of the dynamic quantisers (DSMEM +
+   hardware cluster barrier + programmatic dependent launch); 0 = always the flag-barrier grid
+   kernels. Results are identical either way; A/B timing and test aid (env MIXDQ_NO_CLUSTER=1). */
+void        mixdq_debug_set_cluster(int on);
 
 /* ------------------------------------------------------------------------------------------
  * A1  static per-tensor activation quantisation, fp16 -> int8
@@ -198,6 +202,28 @@ int mixdq_gemm_w8a8_f16_dyn_res(const int8_t* A, int64_t lda, const int8_t* W,
                                 const mixdq_half_t* residual, int64_t ldr,
                                 mixdq_half_t* D, int64_t ldd, int M, int N, int K,
                                 int32_t* acc_out, mixdq_stream_t stream);
+
+/* GEGLU feed-forward input projection (diffusers GEGLU = Linear(d, 2*inner) then
+   hidden * gelu(gate); the reference runs it as QuantizedLinear nn/Linear.py:147-192 followed by
+   stock fp16 ops) with the GEGLU evaluated in the GEMM epilogue. The caller passes the weight
+   ROWS (and w_scale / wsum / bias entries) interleaved in groups of 16: rows 32g..32g+15 are
+   value rows 16g..16g+15, rows 32g+16..32g+31 the gate rows inner+16g..inner+16g+15, so that 32
+   adjacent accumulator columns hold both operands of 16 outputs. Y = fp16 [M][N2/2] (row pitch
+   ldy): half(h * half(gelu(g))) of the fp16-rounded linear outputs — identical to
+   mixdq_gemm_w8a8_f16_dyn followed by the stock GEGLU. The tensor's min(0, min Y) / max(0, max Y)
+   are folded into the dynamic-quantisation workspace `ws`, to be consumed by exactly one
+   mixdq_quant_i8_premm call on the same stream (which leaves the workspace clean again).
+   N2 % 32 == 0, K % 16 == 0; MIXDQ_ERR_UNSUPPORTED when the tcgen05 path is disabled. */
+int mixdq_gemm_w8a8_geglu_f16_dyn(const int8_t* A, int64_t lda, const int8_t* W_il,
+                                  const float* w_scale_il, const float* wsum_il,
+                                  const float* a_scale, const float* a_zp,
+                                  const mixdq_half_t* bias_il, mixdq_half_t* Y, int64_t ldy,
+                                  int M, int N2, int K, void* ws, mixdq_stream_t stream);
+/* A10 (qdiff min-max, base_quantizer.py:155-190) of a dense fp16 tensor whose min / max were
+   published into `ws` by the producing kernel (see above): single pass, no grid barrier.
+   numel % 8 == 0. Writes *scale_out = delta, *zp_out = z - 128, q = codes. */
+int mixdq_quant_i8_premm(const mixdq_half_t* x, int64_t numel, int8_t* q, float* scale_out,
+                         float* zp_out, void* ws, mixdq_stream_t stream);
 
 /* wsum_krs fp32 [K][R][S] iff pad > 0; wsum_k fp32 [K] (sum over taps and channels) iff pad == 0 */
 int mixdq_conv_w8a8_f16_dyn(const int8_t* x_nhwc, int64_t x_cpitch, const int8_t* w_krsc,

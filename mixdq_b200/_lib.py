@@ -18,13 +18,14 @@ LIB_PATH = Path(__file__).resolve().parent / "libmixdq_b200.so"
 ABI_SYMBOLS = [
     "mixdq_abi_version", "mixdq_set_workspace", "mixdq_debug_set_pdl", "mixdq_strerror", "mixdq_last_path", "mixdq_force_simt",
     "mixdq_debug_force_bn", "mixdq_debug_force_splits", "mixdq_debug_set_timing_buffer",
-    "mixdq_debug_set_mode",
+    "mixdq_debug_set_mode", "mixdq_debug_set_cluster",
     "mixdq_quant_i8_static", "mixdq_quant_i8_static_strided", "mixdq_quant_i8_nchw2nhwc",
     "mixdq_quant_dynamic_ws_bytes", "mixdq_quant_i8_dynamic",
     "mixdq_gemm_w8a8_f16", "mixdq_gemm_w8a8_f16_dyn", "mixdq_gemm_w4a8_f16",
     "mixdq_conv_w8a8_f16", "mixdq_conv1x1_split_w8a8_f16",
     "mixdq_gemm_w8a8_f16_dyn_res", "mixdq_conv_w8a8_f16_dyn", "mixdq_conv1x1_split_w8a8_f16_dyn",
     "mixdq_quant_i8_dynamic_rows", "mixdq_ln_quant_i8_dynamic", "mixdq_geglu_quant_i8_dynamic", "mixdq_gn_quant_i8_dynamic",
+    "mixdq_gemm_w8a8_geglu_f16_dyn", "mixdq_quant_i8_premm",
 ]
 
 
@@ -52,6 +53,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mixdq_debug_force_splits.argtypes = [c_int]
     lib.mixdq_debug_set_timing_buffer.restype = None
     lib.mixdq_debug_set_timing_buffer.argtypes = [P]
+    lib.mixdq_debug_set_cluster.restype = None
+    lib.mixdq_debug_set_cluster.argtypes = [c_int]
     lib.mixdq_debug_set_mode.restype = None
     lib.mixdq_debug_set_mode.argtypes = [c_int]
 
@@ -106,6 +109,11 @@ def _declare(lib: ctypes.CDLL) -> None:
                                               P, P]
     lib.mixdq_geglu_quant_i8_dynamic.restype = c_int
     lib.mixdq_geglu_quant_i8_dynamic.argtypes = [P, c_int64, c_int, c_int, P, P, P, P, P, P]
+    lib.mixdq_gemm_w8a8_geglu_f16_dyn.restype = c_int
+    lib.mixdq_gemm_w8a8_geglu_f16_dyn.argtypes = [P, c_int64, P, P, P, P, P, P, P, c_int64,
+                                                  c_int, c_int, c_int, P, P]
+    lib.mixdq_quant_i8_premm.restype = c_int
+    lib.mixdq_quant_i8_premm.argtypes = [P, c_int64, P, P, P, P, P]
     lib.mixdq_gn_quant_i8_dynamic.restype = c_int
     lib.mixdq_gn_quant_i8_dynamic.argtypes = [P, c_int64, c_int, c_int, c_int, c_int, P, P,
                                               c_float, c_int, P, P, P, P, P, P]

@@ -9,6 +9,7 @@
 #include "../../include/mixdq_b200.h"
 #include "simt.h"
 #include "tc_kernel.cuh"
+#include "quant_ws.cuh"
 
 using namespace mixdq;
 
@@ -291,6 +292,49 @@ extern "C" int mixdq_gemm_w8a8_f16_dyn(const int8_t* A, int64_t lda, const int8_
   if (!a_scale || !a_zp) return MIXDQ_ERR_INVALID_ARG;
   return gemm_common(A, lda, W, w_scale, wsum, a_scale, a_zp, bias, nullptr, 0, D, ldd, M, N, K,
                      acc_out, static_cast<cudaStream_t>(stream));
+}
+
+// ff.net.0.proj + GEGLU (KIND_GEGLU): W / w_scale / wsum / bias rows interleaved in groups of
+// 16 value rows followed by their 16 gate rows; Y = [M][N2/2] fp16; min/max -> ws (DynWs::mm)
+extern "C" int mixdq_gemm_w8a8_geglu_f16_dyn(const int8_t* A, int64_t lda, const int8_t* W_il,
+                                             const float* w_scale_il, const float* wsum_il,
+                                             const float* a_scale, const float* a_zp,
+                                             const mixdq_half_t* bias_il, mixdq_half_t* Y,
+                                             int64_t ldy, int M, int N2, int K, void* ws,
+                                             mixdq_stream_t stream) {
+  if (M < 0 || N2 <= 0 || K <= 0 || !W_il || !w_scale_il || !wsum_il || !a_scale || !a_zp || !ws)
+    return MIXDQ_ERR_INVALID_ARG;
+  if (M == 0) return MIXDQ_OK;
+  if (!A || !Y || lda < K || ldy < N2 / 2) return MIXDQ_ERR_INVALID_ARG;
+  if ((K % 16) || (N2 % 32) || (lda % 16) || (ldy % 8) || !al16(A) || !al16(W_il) || !al16(Y))
+    return MIXDQ_ERR_ALIGNMENT;
+  if (g_force_simt) return MIXDQ_ERR_UNSUPPORTED;
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  int bn, splits;
+  pick_tile(m_tiles, N2, num_kb, false, &bn, &splits);
+  if (bn < 32) bn = 32;
+  CUtensorMap tmA, tmW;
+  if (!make_tmap_2d(&tmA, A, K, M, lda, BLOCK_M)) return MIXDQ_ERR_CUDA;
+  if (!make_tmap_2d(&tmW, W_il, K, N2, K, bn)) return MIXDQ_ERR_CUDA;
+  TcParams p{};
+  p.dbg = g_dbg;
+  p.dbg_mode = g_dbg_mode;
+  p.splits = 1;
+  p.M = M; p.N = N2; p.num_kb = num_kb;
+  p.scale = w_scale_il; p.bias0 = wsum_il; p.a_scale = a_scale; p.a_zp = a_zp;
+  p.bias = reinterpret_cast<const __half*>(bias_il);
+  p.D = reinterpret_cast<__half*>(Y); p.ldd = ldy;
+  p.mm = static_cast<DynWs*>(ws)->mm;     // address arithmetic only: ws is a device pointer
+  dim3 grid(m_tiles, (N2 + bn - 1) / bn, 1);
+  g_last_path = "tcgen05-geglu";
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 256: return launch_tc<256, 4, KIND_GEGLU>(grid, tmA, tmW, tmA, tmW, p, st);
+    case 128: return launch_tc<128, 6, KIND_GEGLU>(grid, tmA, tmW, tmA, tmW, p, st);
+    case 64: return launch_tc<64, 8, KIND_GEGLU>(grid, tmA, tmW, tmA, tmW, p, st);
+    default: return launch_tc<32, 8, KIND_GEGLU>(grid, tmA, tmW, tmA, tmW, p, st);
+  }
 }
 
 extern "C" int mixdq_gemm_w8a8_f16_dyn_res(const int8_t* A, int64_t lda, const int8_t* W,

@@ -251,4 +251,14 @@ __device__ __forceinline__ float dequant_f32(int32_t acc, float bias0, float sca
   return __fmul_rn(__fsub_rn(static_cast<float>(acc), bias0), scale);
 }
 
+// GEGLU on fp16 operands exactly as the stock module evaluates it (diffusers GEGLU: hidden *
+// F.gelu(gate), approximate='none'): gelu in fp32 rounded to fp16, product in fp32 rounded to fp16
+__device__ __forceinline__ float geglu_f32(float h, float g) {
+  const float ge = 0.5f * g * (1.0f + erff(g * 0.70710678118654752440f));
+  return h * __half2float(__float2half_rn(ge));
+}
+__device__ __forceinline__ __half geglu_half(__half h, __half g) {
+  return __float2half_rn(geglu_f32(__half2float(h), __half2float(g)));
+}
+
 }  // namespace mixdq

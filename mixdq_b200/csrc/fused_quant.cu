@@ -106,7 +106,10 @@ __device__ __forceinline__ void ln_row(const __half* __restrict__ xrow, int nchu
   }
 }
 
-template <int MAXCH>
+// CLUSTER (all three row kernels below): the launch is ONE thread-block cluster whose stashes
+// hold the whole tensor; min/max through DSMEM + the cluster barrier (quant_ws.cuh) and a
+// programmatic dependency on the producer instead of a full launch gap.
+template <int MAXCH, bool CLUSTER>
 __global__ void __launch_bounds__(kFqThreads, 1)
 ln_quant_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
                 const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps,
@@ -115,6 +118,8 @@ ln_quant_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
                 int stash_rows) {
   extern __shared__ int4 stash[];   // [stash_rows][C/8]
   pdl_launch_dependents();
+  if (CLUSTER) cluster_enter();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = C >> 3;
   const int row0 = blockIdx.x * rows_per_cta;
@@ -135,7 +140,8 @@ ln_quant_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
     }
   }
   float delta, z;
-  grid_minmax_params<kFqThreads>(ws, mn, mx, scale_out, zp_out, delta, z);
+  if (CLUSTER) cluster_minmax_params<kFqThreads>(mn, mx, scale_out, zp_out, delta, z);
+  else grid_minmax_params<kFqThreads>(ws, mn, mx, scale_out, zp_out, delta, z);
   for (int r = row0 + warp; r < row1; r += kFqWarps) {
     const int lr = r - row0;
     uint2* qrow = reinterpret_cast<uint2*>(q + static_cast<int64_t>(r) * C);
@@ -163,10 +169,7 @@ __device__ __forceinline__ int4 geglu_vec8(const int4& hraw, const int4& graw) {
   unpack8(hraw, h);
   unpack8(graw, g);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float ge = 0.5f * g[j] * (1.0f + erff(g[j] * 0.70710678118654752440f));
-    o[j] = h[j] * __half2float(__float2half_rn(ge));
-  }
+  for (int j = 0; j < 8; ++j) o[j] = geglu_f32(h[j], g[j]);
   return pack8(o);
 }
 
@@ -177,6 +180,7 @@ geglu_quant_kernel(const __half* __restrict__ hg, int64_t ld, int M, int I,
                    int stash_rows) {
   extern __shared__ int4 stash[];   // [stash_rows][I/8]
   pdl_launch_dependents();
+  pdl_wait();
   const int nchunks = I >> 3;
   const int row0 = blockIdx.x * rows_per_cta;
   const int row1 = min(M, row0 + rows_per_cta);
@@ -211,12 +215,15 @@ geglu_quant_kernel(const __half* __restrict__ hg, int64_t ld, int M, int I,
 // plain dynamic quantisation of a row-pitched view [M][cols] (pitch ldx) -> dense int8 [M][cols]:
 // channel slices of NHWC tensors (split shortcuts), attention outputs, token slices.
 // =============================================================================================
+template <bool CLUSTER>
 __global__ void __launch_bounds__(kFqThreads, 1)
 rows_quant_kernel(const __half* __restrict__ x, int64_t ldx, int M, int cols,
                   int8_t* __restrict__ q, DynWs* __restrict__ ws, float* __restrict__ scale_out,
                   float* __restrict__ zp_out, int rows_per_cta, int stash_rows) {
   extern __shared__ int4 stash[];   // [stash_rows][cols/8]
   pdl_launch_dependents();
+  if (CLUSTER) cluster_enter();
+  pdl_wait();
   const int nchunks = cols >> 3;
   const int row0 = blockIdx.x * rows_per_cta;
   const int row1 = min(M, row0 + rows_per_cta);
@@ -230,7 +237,8 @@ rows_quant_kernel(const __half* __restrict__ x, int64_t ldx, int M, int cols,
     if (lr < stash_rows) stash[it] = y;
   }
   float delta, z;
-  grid_minmax_params<kFqThreads>(ws, mn, mx, scale_out, zp_out, delta, z);
+  if (CLUSTER) cluster_minmax_params<kFqThreads>(mn, mx, scale_out, zp_out, delta, z);
+  else grid_minmax_params<kFqThreads>(ws, mn, mx, scale_out, zp_out, delta, z);
   for (int64_t it = threadIdx.x; it < items; it += kFqThreads) {
     const int lr = static_cast<int>(it / nchunks);
     const int c = static_cast<int>(it - static_cast<int64_t>(lr) * nchunks);
@@ -291,6 +299,7 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
   __shared__ float s_mean[32], s_rstd[32];
   __shared__ int s_last;
   pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = C >> 3;
   const int cpg = C / G;
@@ -357,11 +366,12 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    if (atomicAdd(&ws->counter2, 1u) == gridDim.x - 1) {
-      __threadfence();
-      st_release_u32(&ws->flag2, 1u);
+    atomicAdd(&ws->counter2, 1u);
+    unsigned int spins = 0;
+    while (ld_acquire_u32(&ws->counter2) < gridDim.x) {
+      __nanosleep(20);
+      if (++spins > (1u << 24)) __trap();
     }
-    spin_until_set(&ws->flag2);
   }
   __syncthreads();
   if (threadIdx.x < G) {
@@ -383,9 +393,9 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-      ws->counter2 = 0; ws->done2 = 0;
+      ws->done2 = 0;
       __threadfence();
-      st_release_u32(&ws->flag2, 0u);
+      st_release_u32(&ws->counter2, 0u);
     }
   }
 
@@ -453,6 +463,22 @@ static void plan_rows(int64_t rows, int64_t row_bytes, int min_rows_per_cta, int
   *smem = static_cast<int>(srows * row_bytes);
 }
 
+// one cluster of <= ncl CTAs whose stashes hold ALL rows; false if the tensor does not fit
+static bool plan_rows_cluster(int64_t rows, int64_t row_bytes, int min_rows_per_cta, int ncl,
+                              int* grid, int* rows_per_cta, int* smem) {
+  if (ncl <= 0 || !cluster_enabled() || rows * row_bytes > 2 * kClusterMaxElems) return false;
+  int64_t g = (rows + min_rows_per_cta - 1) / min_rows_per_cta;
+  if (g > ncl) g = ncl;
+  if (g < 1) g = 1;
+  const int64_t rpc = (rows + g - 1) / g;
+  g = (rows + rpc - 1) / rpc;
+  if (rpc * row_bytes > kFqMaxSmem) return false;
+  *grid = static_cast<int>(g);
+  *rows_per_cta = static_cast<int>(rpc);
+  *smem = static_cast<int>(rpc * row_bytes);
+  return true;
+}
+
 extern "C" int mixdq_ln_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int M, int C,
                                          const mixdq_half_t* gamma, const mixdq_half_t* beta,
                                          float eps, int8_t* q, mixdq_half_t* y_out,
@@ -466,18 +492,40 @@ extern "C" int mixdq_ln_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int
   if (C > kLnMaxChunks * 256) return MIXDQ_ERR_UNSUPPORTED;
   static bool attr = false;
   if (!attr) {
-    if (set_smem(ln_quant_kernel<5>, kFqMaxSmem) || set_smem(ln_quant_kernel<8>, kFqMaxSmem))
+    if (set_smem(ln_quant_kernel<5, false>, kFqMaxSmem) ||
+        set_smem(ln_quant_kernel<8, false>, kFqMaxSmem) ||
+        set_smem(ln_quant_kernel<5, true>, kFqMaxSmem) ||
+        set_smem(ln_quant_kernel<8, true>, kFqMaxSmem))
       return MIXDQ_ERR_CUDA;
     attr = true;
   }
   int grid, rpc, srows, smem;
-  plan_rows(M, static_cast<int64_t>(C) * 2, 8, &grid, &rpc, &srows, &smem);
-  auto kern = (C <= 5 * 256) ? ln_quant_kernel<5> : ln_quant_kernel<8>;
-  kern<<<grid, kFqThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __half*>(x), ldx, M, C, reinterpret_cast<const __half*>(gamma),
-      reinterpret_cast<const __half*>(beta), eps, q, reinterpret_cast<__half*>(y_out),
-      static_cast<DynWs*>(ws), scale_out, zp_out, rpc, srows);
-  MIXDQ_CHECK_LAUNCH();
+  static int ncl = -1;
+  if (ncl < 0) {
+    const int a = max_cluster_ctas(ln_quant_kernel<5, true>, kFqThreads, kFqMaxSmem);
+    const int b = max_cluster_ctas(ln_quant_kernel<8, true>, kFqThreads, kFqMaxSmem);
+    ncl = a < b ? a : b;
+  }
+  if (plan_rows_cluster(M, static_cast<int64_t>(C) * 2, 1, ncl, &grid, &rpc, &smem)) {
+    auto kc = (C <= 5 * 256) ? ln_quant_kernel<5, true> : ln_quant_kernel<8, true>;
+    if (launch_cluster_pdl(kc, grid, kFqThreads, smem, static_cast<cudaStream_t>(stream),
+                           reinterpret_cast<const __half*>(x), ldx, M, C,
+                           reinterpret_cast<const __half*>(gamma),
+                           reinterpret_cast<const __half*>(beta), eps, q,
+                           reinterpret_cast<__half*>(y_out), static_cast<DynWs*>(ws), scale_out,
+                           zp_out, rpc, rpc) != cudaSuccess)
+      return MIXDQ_ERR_CUDA;
+    return MIXDQ_OK;
+  }
+  // one row per warp; >= 2 rows per CTA keeps the grid <= 128 CTAs for the batch-1 blocks
+  plan_rows(M, static_cast<int64_t>(C) * 2, 2, &grid, &rpc, &srows, &smem);
+  auto kern = (C <= 5 * 256) ? ln_quant_kernel<5, false> : ln_quant_kernel<8, false>;
+  if (launch_pdl(kern, grid, kFqThreads, smem, static_cast<cudaStream_t>(stream),
+                 reinterpret_cast<const __half*>(x), ldx, M, C,
+                 reinterpret_cast<const __half*>(gamma), reinterpret_cast<const __half*>(beta), eps,
+                 q, reinterpret_cast<__half*>(y_out), static_cast<DynWs*>(ws), scale_out, zp_out,
+                 rpc, srows) != cudaSuccess)
+    return MIXDQ_ERR_CUDA;
   return MIXDQ_OK;
 }
 
@@ -492,10 +540,10 @@ extern "C" int mixdq_geglu_quant_i8_dynamic(const mixdq_half_t* hg, int64_t ld, 
   if (!attr) { if (set_smem(geglu_quant_kernel, kFqMaxSmem)) return MIXDQ_ERR_CUDA; attr = true; }
   int grid, rpc, srows, smem;
   plan_rows(M, static_cast<int64_t>(I) * 2, 1, &grid, &rpc, &srows, &smem);
-  geglu_quant_kernel<<<grid, kFqThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __half*>(hg), ld, M, I, q, reinterpret_cast<__half*>(y_out),
-      static_cast<DynWs*>(ws), scale_out, zp_out, rpc, srows);
-  MIXDQ_CHECK_LAUNCH();
+  if (launch_pdl(geglu_quant_kernel, grid, kFqThreads, smem, static_cast<cudaStream_t>(stream),
+                 reinterpret_cast<const __half*>(hg), ld, M, I, q, reinterpret_cast<__half*>(y_out),
+                 static_cast<DynWs*>(ws), scale_out, zp_out, rpc, srows) != cudaSuccess)
+    return MIXDQ_ERR_CUDA;
   return MIXDQ_OK;
 }
 
@@ -506,16 +554,30 @@ extern "C" int mixdq_quant_i8_dynamic_rows(const mixdq_half_t* x, int64_t ldx, i
     return MIXDQ_ERR_INVALID_ARG;
   if ((cols & 7) || (ldx & 7) || !al16(x) || !al16(q)) return MIXDQ_ERR_ALIGNMENT;
   static bool attr = false;
-  if (!attr) { if (set_smem(rows_quant_kernel, kFqMaxSmem)) return MIXDQ_ERR_CUDA; attr = true; }
+  if (!attr) {
+    if (set_smem(rows_quant_kernel<false>, kFqMaxSmem) || set_smem(rows_quant_kernel<true>, kFqMaxSmem))
+      return MIXDQ_ERR_CUDA;
+    attr = true;
+  }
   int grid, rpc, srows, smem;
-  // >= 64 KB of fp16 per CTA keeps small tensors on few CTAs (cheap barrier)
-  int min_rows = static_cast<int>((32768 + cols - 1) / cols);
+  static int ncl = -1;
+  if (ncl < 0) ncl = max_cluster_ctas(rows_quant_kernel<true>, kFqThreads, kFqMaxSmem);
+  if (plan_rows_cluster(M, static_cast<int64_t>(cols) * 2, 1, ncl, &grid, &rpc, &smem)) {
+    if (launch_cluster_pdl(rows_quant_kernel<true>, grid, kFqThreads, smem,
+                           static_cast<cudaStream_t>(stream), reinterpret_cast<const __half*>(x),
+                           ldx, M, cols, q, static_cast<DynWs*>(ws), scale_out, zp_out, rpc,
+                           rpc) != cudaSuccess)
+      return MIXDQ_ERR_CUDA;
+    return MIXDQ_OK;
+  }
+  // >= 16 KB of fp16 (two 16-byte vectors per thread) per CTA
+  int min_rows = static_cast<int>((8192 + cols - 1) / cols);
   if (min_rows < 1) min_rows = 1;
   plan_rows(M, static_cast<int64_t>(cols) * 2, min_rows, &grid, &rpc, &srows, &smem);
-  rows_quant_kernel<<<grid, kFqThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __half*>(x), ldx, M, cols, q, static_cast<DynWs*>(ws), scale_out,
-      zp_out, rpc, srows);
-  MIXDQ_CHECK_LAUNCH();
+  if (launch_pdl(rows_quant_kernel<false>, grid, kFqThreads, smem,
+                 static_cast<cudaStream_t>(stream), reinterpret_cast<const __half*>(x), ldx, M,
+                 cols, q, static_cast<DynWs*>(ws), scale_out, zp_out, rpc, srows) != cudaSuccess)
+    return MIXDQ_ERR_CUDA;
   return MIXDQ_OK;
 }
 
@@ -554,16 +616,11 @@ extern "C" int mixdq_gn_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int
   const int scratch = kFqWarps * (C / 8) * 16;   // phase-0 partials [warps][chunks] float4
   if (smem < scratch) smem = scratch;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (silu)
-    gn_quant_kernel<true><<<NB * cpi, kFqThreads, smem, st>>>(
-        reinterpret_cast<const __half*>(x), ldx, NB, HW, C, G, reinterpret_cast<const __half*>(gamma),
-        reinterpret_cast<const __half*>(beta), eps, q, reinterpret_cast<__half*>(y_out),
-        static_cast<DynWs*>(ws), scale_out, zp_out, cpi, rpc, static_cast<int>(srows));
-  else
-    gn_quant_kernel<false><<<NB * cpi, kFqThreads, smem, st>>>(
-        reinterpret_cast<const __half*>(x), ldx, NB, HW, C, G, reinterpret_cast<const __half*>(gamma),
-        reinterpret_cast<const __half*>(beta), eps, q, reinterpret_cast<__half*>(y_out),
-        static_cast<DynWs*>(ws), scale_out, zp_out, cpi, rpc, static_cast<int>(srows));
-  MIXDQ_CHECK_LAUNCH();
+  auto gk = silu ? gn_quant_kernel<true> : gn_quant_kernel<false>;
+  if (launch_pdl(gk, NB * cpi, kFqThreads, smem, st, reinterpret_cast<const __half*>(x), ldx, NB, HW,
+                 C, G, reinterpret_cast<const __half*>(gamma), reinterpret_cast<const __half*>(beta),
+                 eps, q, reinterpret_cast<__half*>(y_out), static_cast<DynWs*>(ws), scale_out,
+                 zp_out, cpi, rpc, static_cast<int>(srows)) != cudaSuccess)
+    return MIXDQ_ERR_CUDA;
   return MIXDQ_OK;
 }

@@ -18,6 +18,7 @@ enum QuantMode { kStaticFma = 0, kDynamicDiv = 1 };
 struct QParams {
   float a;  // static: 1/delta      dynamic: delta
   float b;  // static: zp (-128 shifted)   dynamic: z (unshifted, in [0,255])
+  float inv;  // dynamic: 1/delta (set by quant_vec8 / the callers of quant_one)
 };
 
 template <int MODE>
@@ -26,9 +27,7 @@ __device__ __forceinline__ int quant_one(float x, QParams p) {
     int v = __float2int_rn(__fmaf_rn(x, p.a, p.b));
     return min(max(v, -128), 127);
   } else {
-    float r = __fadd_rn(rintf(__fdiv_rn(x, p.a)), p.b);
-    r = fminf(fmaxf(r, 0.0f), 255.0f);
-    return static_cast<int>(r) - 128;
+    return qdiff_code(x, p.a, p.inv, p.b);
   }
 }
 
@@ -37,13 +36,18 @@ __device__ __forceinline__ QParams load_qparams(const float* a, const float* b) 
   QParams p;
   p.a = __ldg(a);
   p.b = __ldg(b);
-  if (MODE == kDynamicDiv) p.b = p.b + 128.0f;  // stored zero point is z-128; exact in fp32
+  p.inv = 0.0f;
+  if (MODE == kDynamicDiv) {
+    p.b = p.b + 128.0f;  // stored zero point is z-128; exact in fp32
+    p.inv = __frcp_rn(p.a);
+  }
   return p;
 }
 
 template <int MODE>
 __device__ __forceinline__ uint2 quant_vec8(const int4& raw, QParams p) {
   const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+  if (MODE == kDynamicDiv) p.inv = __frcp_rn(p.a);
   int q[8];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -192,11 +196,18 @@ quant_nchw2nhwc_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int
 // batch-1 SDXL step) are read from memory exactly once; larger tensors are re-read (L2 hits).
 constexpr int kDynCache = 8;
 
-__global__ void __launch_bounds__(kQuantThreads)
+// CLUSTER: the launch is one thread-block cluster (<= 16 CTAs of NT threads) and carries a
+// programmatic dependency: min/max go through DSMEM + the cluster barrier, and the kernel's launch
+// latency hides behind the tail of the producer (griddepcontrol.wait before the first read).
+template <int NT, bool CLUSTER>
+__global__ void __launch_bounds__(NT)
 quant_dynamic_fused_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int64_t numel,
                            DynWs* __restrict__ ws, float* __restrict__ scale_out,
                            float* __restrict__ zp_out) {
+  constexpr int kQuantThreads = NT;   // shadows the file-level constant inside this kernel
   pdl_launch_dependents();
+  if (CLUSTER) cluster_enter();
+  pdl_wait();
   float mn = 0.0f, mx = 0.0f;  // qdiff clamps x_min <= 0 <= x_max (base_quantizer.py:155-158)
   const int64_t nvec = numel >> 3;
   const int4* xv = reinterpret_cast<const int4*>(x);
@@ -221,7 +232,9 @@ quant_dynamic_fused_kernel(const __half* __restrict__ x, int8_t* __restrict__ q,
     mx = fmaxf(mx, tailv);
   }
   QParams p;
-  grid_minmax_params<kQuantThreads>(ws, mn, mx, scale_out, zp_out, p.a, p.b);
+  if (CLUSTER) cluster_minmax_params<NT>(mn, mx, scale_out, zp_out, p.a, p.b);
+  else grid_minmax_params<NT>(ws, mn, mx, scale_out, zp_out, p.a, p.b);
+  p.inv = __frcp_rn(p.a);
 #pragma unroll
   for (int u = 0; u < kDynCache; ++u) {
     const int64_t i = i0 + u * stride;
@@ -230,6 +243,42 @@ quant_dynamic_fused_kernel(const __half* __restrict__ x, int8_t* __restrict__ q,
   for (int64_t i = i0 + kDynCache * stride; i < nvec; i += stride)
     qv[i] = quant_vec8<kDynamicDiv>(__ldg(xv + i), p);
   if (t < numel) q[t] = static_cast<int8_t>(quant_one<kDynamicDiv>(tailv, p));
+}
+
+// A10 when the tensor's min / max were already folded into ws->mm by the kernel that produced x
+// (tc_i8_kernel<KIND_GEGLU>): one pass, no barrier. Programmatic dependency on the producer.
+__global__ void __launch_bounds__(kQuantThreads)
+quant_premm_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int64_t nvec,
+                   DynWs* __restrict__ ws, float* __restrict__ scale_out,
+                   float* __restrict__ zp_out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const float mn = 0.0f - __int_as_float(static_cast<int>(__ldcg(&ws->mm[0])));
+  const float mx = __int_as_float(static_cast<int>(__ldcg(&ws->mm[1])));
+  QParams p;
+  qdiff_params(mn, mx, p.a, p.b);
+  p.inv = __frcp_rn(p.a);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *scale_out = p.a; *zp_out = p.b - 128.0f; }
+  const int4* xv = reinterpret_cast<const int4*>(x);
+  uint2* qv = reinterpret_cast<uint2*>(q);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kQuantThreads;
+  for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * kQuantThreads + threadIdx.x; i0 < nvec;
+       i0 += kQuantUnroll * stride) {
+    int4 v[kQuantUnroll];
+#pragma unroll
+    for (int u = 0; u < kQuantUnroll; ++u)
+      if (i0 + u * stride < nvec) v[u] = ld_stream16(xv + i0 + u * stride);
+#pragma unroll
+    for (int u = 0; u < kQuantUnroll; ++u)
+      if (i0 + u * stride < nvec) qv[i0 + u * stride] = quant_vec8<kDynamicDiv>(v[u], p);
+  }
+  __syncthreads();   // every thread of this CTA has read mm
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&ws->mm_done, 1u) == gridDim.x - 1) {
+      ws->mm[0] = 0u; ws->mm[1] = 0u; ws->mm_done = 0u;
+    }
+  }
 }
 
 static inline int grid_for(int64_t items, int per_block, int max_blocks) {
@@ -242,6 +291,8 @@ static inline int grid_for(int64_t items, int per_block, int max_blocks) {
 }  // namespace mixdq
 
 using namespace mixdq;
+
+extern "C" void mixdq_debug_set_cluster(int on) { cluster_mode_flag() = on ? 1 : 0; }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
@@ -332,10 +383,46 @@ extern "C" int mixdq_quant_i8_dynamic(const mixdq_half_t* x, int64_t numel, floa
   if (!aligned16(x) || !aligned8(q)) return MIXDQ_ERR_ALIGNMENT;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __half* xh = reinterpret_cast<const __half*>(x);
+  // tiny tensors (embeddings, pooled vectors): one cluster, DSMEM + hardware barrier. Anything
+  // larger needs the arithmetic throughput of the whole chip (measured: 0.33 M elements on one
+  // 16-CTA cluster took 7.5 us, issue-bound) and takes the counter barrier below.
+  constexpr int kClThreads = 512;
+  static int ncl = -1;
+  if (ncl < 0) ncl = max_cluster_ctas(quant_dynamic_fused_kernel<kClThreads, true>, kClThreads, 0);
+  const int ncl_now = cluster_enabled() ? ncl : 0;
+  if (ncl_now > 0 && numel <= kClusterMaxElems) {
+    int grid = grid_for(numel >> 3, kClThreads, ncl_now);
+    if (launch_cluster_pdl(quant_dynamic_fused_kernel<kClThreads, true>, grid, kClThreads, 0, st,
+                           xh, q, numel, static_cast<DynWs*>(ws), scale_out, zp_out) != cudaSuccess)
+      return MIXDQ_ERR_CUDA;
+    return MIXDQ_OK;
+  }
   // co-resident grid: at most 2 CTAs per SM (see quant_dynamic_fused_kernel)
   int grid = grid_for(numel >> 3, kQuantThreads * 2, 148 * 2);
-  quant_dynamic_fused_kernel<<<grid, kQuantThreads, 0, st>>>(xh, q, numel, static_cast<DynWs*>(ws),
-                                                            scale_out, zp_out);
-  MIXDQ_CHECK_LAUNCH();
+  if (launch_pdl(quant_dynamic_fused_kernel<kQuantThreads, false>, grid, kQuantThreads, 0, st, xh,
+                 q, numel, static_cast<DynWs*>(ws), scale_out, zp_out) != cudaSuccess)
+    return MIXDQ_ERR_CUDA;
+  return MIXDQ_OK;
+}
+
+extern "C" int mixdq_quant_i8_premm(const mixdq_half_t* x, int64_t numel, int8_t* q,
+                                    float* scale_out, float* zp_out, void* ws,
+                                    mixdq_stream_t stream) {
+  if (numel <= 0 || !x || !q || !scale_out || !zp_out || !ws) return MIXDQ_ERR_INVALID_ARG;
+  if ((numel & 7) || !aligned16(x) || !aligned8(q)) return MIXDQ_ERR_ALIGNMENT;
+  const int64_t nvec = numel >> 3;
+  const int grid = grid_for(nvec, kQuantThreads * kQuantUnroll, 148 * 4);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kQuantThreads);
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, quant_premm_kernel, reinterpret_cast<const __half*>(x), q, nvec,
+                         static_cast<DynWs*>(ws), scale_out, zp_out) != cudaSuccess)
+    return MIXDQ_ERR_CUDA;
   return MIXDQ_OK;
 }

@@ -14,6 +14,11 @@
 //               16-class x BN table built in shared memory by the epilogue warps
 //   KIND_SPLIT: two K-phases (two A/W operand pairs) into two TMEM accumulators, combined in the
 //               epilogue exactly like the reference's two fp16 convs + fp16 add (A6)
+//   KIND_GEGLU: KIND_GEMM whose weight rows are interleaved 16 value / 16 gate columns
+//               (ff.net.0.proj): the epilogue rounds the linear output to fp16, evaluates
+//               half(h * half(gelu(gate))) like the stock GEGLU module, stores [M][N/2] fp16 and
+//               folds the tensor's min / max into two device words (atomicMax on the bit patterns
+//               of -min >= 0 and max >= 0), so the quantiser that follows is a single pass
 //
 // Split-K over a thread-block cluster (p.splits > 1, cluster dims (1,1,splits)).
 //   Measured on B200 (tools/phase_timing.py): with both operands in shared memory one
@@ -42,7 +47,7 @@
 
 namespace mixdq {
 
-enum { KIND_GEMM = 0, KIND_CONV = 1, KIND_SPLIT = 2 };
+enum { KIND_GEMM = 0, KIND_CONV = 1, KIND_SPLIT = 2, KIND_GEGLU = 3 };
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 128;  // int8 elements = bytes = one 128B swizzle row
@@ -83,6 +88,7 @@ struct TcParams {
   __half* D;
   int64_t ldd;
   int32_t* acc_out;       // optional raw accumulator dump [rows][N]
+  unsigned int* mm;       // KIND_GEGLU: {bits(-min), bits(max)} of the fp16 output, atomicMax'ed
   int32_t* ws;            // split-K exchange workspace: [CTA][BN/4][128][4] int32 (splits > 1)
   unsigned long long* dbg; // optional phase timestamps (globaltimer ns), 8 slots per CTA
   int dbg_mode;            // profiling only: bit0 = skip MMA issue, bit1 = skip TMA loads
@@ -119,7 +125,7 @@ struct TcSmem {
   // fp16 output staging tile: 128 rows x (BN halves + 16 B pad), aliased onto the drained ring
   static constexpr int OUT_PITCH = BN * 2 + 16;
   static constexpr int OUT_BYTES = BLOCK_M * OUT_PITCH;
-  static_assert(OUT_BYTES <= OFF_PARAM, "staging tile must fit in the stage ring");
+  static_assert(OUT_BYTES + 80 <= OFF_PARAM, "staging tile (+ min/max scratch) must fit in the stage ring");
 };
 
 // Per-row geometry of the output tile (which output row / border class a tile row maps to).
@@ -213,7 +219,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   pdl_launch_dependents();
 
   // K range of this CTA (split-K rank == blockIdx.z == rank in the (1,1,splits) cluster)
-  const int splits = (KIND == KIND_SPLIT) ? 1 : p.splits;
+  const int splits = (KIND == KIND_SPLIT || KIND == KIND_GEGLU) ? 1 : p.splits;
   const int krank = (splits > 1) ? static_cast<int>(blockIdx.z) : 0;
   const int total_kb = p.num_kb + (KIND == KIND_SPLIT ? p.num_kb1 : 0);
   const int kb_begin = (splits > 1) ? (krank * total_kb) / splits : 0;
@@ -462,7 +468,76 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   int rows_here = BLOCK_M;               // tile rows whose results this CTA stages and stores
   int row_base = 0;
-  if (splits == 1) {
+  if (KIND == KIND_GEGLU) {
+    if constexpr (BN >= 32) {
+    if (warp >= 2) {
+      // ---- 32 accumulator columns = 16 value + 16 gate columns of the same 16 outputs ----
+      const int row = quarter * 32 + lane;
+      const RowInfo ri = row_info<KIND>(p, row, m0, tn0, tp0, tq0);
+      constexpr int NCH = BN / 32;
+      const int c_lo = (NCH >= 2) ? ehalf * (NCH / 2) : 0;
+      const int c_hi = (NCH >= 2) ? c_lo + NCH / 2 : (ehalf == 0 ? 1 : 0);
+      RowInfo ro[2];                               // rows this lane copies out (2 lanes per row)
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        ro[i] = row_info<KIND>(p, quarter * 32 + i * 16 + (lane >> 1), m0, tn0, tp0, tq0);
+      float mn = 0.f, mx = 0.f;
+#pragma unroll 1
+      for (int c = c_lo; c < c_hi; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32;
+        tmem_ld_32x32(taddr, reinterpret_cast<uint32_t(&)[32]>(v));
+        tmem_ld_wait();
+        const bool cols_ok = n_tile0 + c * 32 + 32 <= p.N;
+        if (ri.ok && cols_ok) {
+          __align__(16) __half h[32];
+#pragma unroll
+          for (int j8 = 0; j8 < 32; j8 += 8)
+            dequant_pack(0, c * 32 + j8, reinterpret_cast<const int32_t*>(v) + j8,
+                         reinterpret_cast<const int32_t*>(v) + j8, h + j8, 8);
+          __align__(16) __half y[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            y[j] = geglu_half(h[j], h[16 + j]);
+            const float f = __half2float(y[j]);
+            mn = fminf(mn, f);
+            mx = fmaxf(mx, f);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(stage_out + row * L::OUT_PITCH + c * 32);
+          dst[0] = reinterpret_cast<const uint4*>(y)[0];
+          dst[1] = reinterpret_cast<const uint4*>(y)[1];
+        }
+        __syncwarp();
+        if (cols_ok) {
+          const int64_t ocol = ((n_tile0 + c * 32) >> 1) + (lane & 1) * 8;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (!ro[i].ok) continue;
+            const int r = quarter * 32 + i * 16 + (lane >> 1);
+            *reinterpret_cast<uint4*>(p.D + ro[i].out_row * p.ldd + ocol) =
+                *reinterpret_cast<const uint4*>(stage_out + r * L::OUT_PITCH + c * 32 + (lane & 1) * 16);
+          }
+        }
+      }
+      tc_fence_before();
+      // tensor-wide min / max: warp -> CTA (shared memory past the staging tile) -> one atomic pair
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      float* s_mm = reinterpret_cast<float*>(smem + ((L::OUT_BYTES + 15) & ~15));
+      if (lane == 0) { s_mm[(warp - 2) * 2] = mn; s_mm[(warp - 2) * 2 + 1] = mx; }
+      epi_bar_sync();
+      if (threadIdx.x == 64) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { mn = fminf(mn, s_mm[2 * w]); mx = fmaxf(mx, s_mm[2 * w + 1]); }
+        atomicMax(reinterpret_cast<int*>(p.mm), __float_as_int(0.0f - mn));
+        atomicMax(reinterpret_cast<int*>(p.mm) + 1, __float_as_int(mx));
+      }
+    }
+    }
+  } else if (splits == 1) {
     if (warp >= 2) {
       // ---- TMEM (lane == row) -> dequant -> fp16 -> staging tile -> global, chunk by chunk.
       //      Each warp owns 32 rows x its column half and copies a chunk out (4 lanes x 16 B per

@@ -102,6 +102,24 @@ class CatLinear:
                                          self.wsum, self.bias)
 
 
+class GegluLinear:
+    """ff.net.0.proj with the GEGLU in its epilogue: an interleaved copy of the projection's
+    int8 rows / scales / sums / bias (16 value rows, then their 16 gate rows), so one accumulator
+    chunk holds both operands of 16 outputs. The module's own buffers stay untouched."""
+
+    def __init__(self, mod: QuantizedLinear):
+        inner = mod.out_features // 2
+        idx = ops.geglu_interleave_index(inner, mod.weight_int.device)
+        self.weight_int = mod.weight_int.index_select(0, idx).contiguous()
+        self.weight_scales = mod.weight_scales.index_select(0, idx).contiguous()
+        self.wsum = mod.weight_sum_by_input_channels.index_select(0, idx).contiguous()
+        self.bias = None if mod.bias is None else mod.bias.index_select(0, idx).contiguous()
+
+    def run(self, q8, scale, zp):
+        return ops.qlinear_geglu_quantize_dynamic(q8, self.weight_int, self.weight_scales, scale,
+                                                  zp, self.wsum, self.bias)
+
+
 class SharedInputGroup:
     """Layers of the whole UNet that consume one tensor (all attn2.to_k/to_v <- encoder hidden
     states; all resnet time_emb_proj <- silu(temb)): quantise once, one GEMM, hand out column
@@ -202,8 +220,11 @@ def fused_transformer_block_forward(self, hidden_states, *args, **kwargs):
     x = _run_linear(self.attn2.to_out[0], o8, s, z, residual=x)
     # --- feed-forward ---
     q8, s, z = ops.layernorm_quantize_dynamic(x, self.norm3.weight, self.norm3.bias, self.norm3.eps)
-    hg = _run_linear(self.ff.net[0].proj, q8, s, z)
-    g8, s, z = ops.geglu_quantize_dynamic(hg)
+    if f.get("ffproj") is not None:
+        g8, s, z = f["ffproj"].run(q8, s, z)
+    else:
+        hg = _run_linear(self.ff.net[0].proj, q8, s, z)
+        g8, s, z = ops.geglu_quantize_dynamic(hg)
     return _run_linear(self.ff.net[2], g8, s, z, residual=x)
 
 
@@ -307,8 +328,10 @@ def fuse_unet(unet: nn.Module, verbose: bool = False) -> dict:
     kv_objs = {k: SharedInputGroup(v, bos=k[1]) for k, v in kv_groups.items()}
     for blk in blocks:
         key = (blk.attn2.to_k.in_features, bool(getattr(blk.attn2.to_k, "bos", False)))
+        proj = blk.ff.net[0].proj
         blk._mixdq_fused = {"qkv": CatLinear([blk.attn1.to_q, blk.attn1.to_k, blk.attn1.to_v]),
-                            "kv": kv_objs[key]}
+                            "kv": kv_objs[key],
+                            "ffproj": GegluLinear(proj) if proj.out_features % 32 == 0 else None}
         blk.forward = types.MethodType(fused_transformer_block_forward, blk)
         summary["kv_layers"] += 2
     for m in t2ds:

@@ -700,6 +700,46 @@ def geglu_quantize_dynamic(hg: torch.Tensor, return_y: bool = False):
     return (q, sc, zp, y) if return_y else (q, sc, zp)
 
 
+def geglu_interleave_index(inner: int, device=None) -> torch.Tensor:
+    """Row order of the GEGLU projection for mixdq_gemm_w8a8_geglu_f16_dyn: groups of 16 value
+    rows followed by their 16 gate rows. Returns the gather index [2*inner] into the stock
+    [value rows | gate rows] order."""
+    _check(inner % 16 == 0, "GEGLU epilogue fusion needs inner_dim % 16 == 0")
+    g = torch.arange(inner // 16, device=device).view(-1, 1, 1) * 16
+    j = torch.arange(16, device=device).view(1, 1, -1)
+    half = torch.tensor([0, inner], device=device).view(1, 2, 1)
+    return (g + half + j).reshape(-1)
+
+
+def qlinear_geglu_quantize_dynamic(input_int8, weight_il, weight_scale_il, input_scale,
+                                   input_zero_point, weight_sum_il, bias_il=None,
+                                   return_y: bool = False):
+    """ff.net.0.proj (dynamic W8A8, rows interleaved by `geglu_interleave_index`) with the GEGLU in
+    the GEMM epilogue, then the single-pass quantiser fed by the epilogue's min/max:
+    2 kernels for Linear -> GEGLU -> quantise. Returns (q int8 [..., inner], scale, zp[, y])."""
+    N2, K = weight_il.shape
+    I = N2 // 2
+    a = input_int8 if input_int8.is_contiguous() else input_int8.contiguous()
+    M = a.numel() // K
+    y = torch.empty((*input_int8.shape[:-1], I), dtype=torch.float16, device=a.device)
+    q = torch.empty((*input_int8.shape[:-1], I), dtype=torch.int8, device=a.device)
+    qp, sc, zp = _qp_pair(a.device)
+    lib = _lib.load()
+    with _DeviceGuard(a):
+        ws = _dynamic_workspace(a.device)
+        _launch("gemm_geglu", lib.mixdq_gemm_w8a8_geglu_f16_dyn,
+                (a.data_ptr(), K, weight_il.data_ptr(), weight_scale_il.data_ptr(),
+                 weight_sum_il.data_ptr(), input_scale.data_ptr(), input_zero_point.data_ptr(),
+                 _ptr(bias_il), y.data_ptr(), I, M, N2, K, ws.data_ptr()), a,
+                keep=(a, weight_il, weight_scale_il, weight_sum_il, input_scale,
+                      input_zero_point, bias_il, y, ws),
+                algo_bytes=M * K + N2 * K + 2 * M * I + 10 * N2, algo_ops=2 * M * N2 * K)
+        _launch("quant_premm", lib.mixdq_quant_i8_premm,
+                (y.data_ptr(), y.numel(), q.data_ptr(), qp.data_ptr(), qp.data_ptr() + 4,
+                 ws.data_ptr()), y, keep=(y, q, qp, ws), algo_bytes=3 * y.numel())
+    return (q, sc, zp, y) if return_y else (q, sc, zp)
+
+
 def groupnorm_quantize_dynamic(x: torch.Tensor, num_groups: int, weight: torch.Tensor,
                                bias: torch.Tensor, eps: float, silu: bool, return_y: bool = False):
     """GroupNorm [+ SiLU] + dynamic quantisation in one kernel. x: fp16 logical [N,C,H,W] in

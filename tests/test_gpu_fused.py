@@ -92,6 +92,59 @@ def test_geglu_quant(ops, dev, M, I):
     check_quant(q, s, z, y, y_ref)
 
 
+@pytest.mark.parametrize("M,I,K", [(256, 5120, 1280), (1024, 2560, 640), (77, 64, 128),
+                                   (300, 80, 64), (4096, 1280, 320), (1, 16, 16)])
+def test_geglu_in_gemm_epilogue(ops, dev, M, I, K):
+    """ff.net.0.proj with the GEGLU in the tcgen05 epilogue + the single-pass quantiser fed by the
+    epilogue's min/max == the unfused linear -> GEGLU+quantise kernels, bit for bit; repeated
+    calls leave the min/max words of the workspace clean."""
+    g = torch.Generator().manual_seed(M + I + K)
+    x8 = torch.randint(-128, 128, (M, K), dtype=torch.int8, generator=g).to(dev)
+    w = torch.randint(-127, 128, (2 * I, K), dtype=torch.int8, generator=g).to(dev)
+    ws_ = (0.001 + 0.01 * torch.rand(2 * I, generator=g)).to(dev)
+    wsum = w.float().sum(1)
+    bias = torch.randn(2 * I, generator=g).half().to(dev)
+    a_s = torch.tensor(0.04, device=dev); a_z = torch.tensor(-7.0, device=dev)
+    hg = ops.qlinear_dynamic_fused(x8, w, ws_, a_s, a_z, wsum, bias)
+    q_ref, s_ref, z_ref, y_ref = ops.geglu_quantize_dynamic(hg, return_y=True)
+    idx = ops.geglu_interleave_index(I, dev)
+    args = (x8, w[idx].contiguous(), ws_[idx].contiguous(), a_s, a_z, wsum[idx].contiguous(),
+            bias[idx].contiguous())
+    for _ in range(3):
+        q, s, z, y = ops.qlinear_geglu_quantize_dynamic(*args, return_y=True)
+        assert torch.equal(bits(y), bits(y_ref)), "GEGLU epilogue differs from the stock sequence"
+        assert torch.equal(s, s_ref) and torch.equal(z, z_ref)
+        assert torch.equal(q, q_ref)
+
+
+def test_cluster_and_grid_quantisers_agree(ops, dev):
+    """Single-cluster (DSMEM + cluster barrier + PDL) and flag-barrier grid variants of the
+    dynamic quantisers return identical codes / scale / zero point."""
+    from mixdq_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(256, 1280, generator=g) * 2 + 0.3).half().to(dev)
+    w = (1 + 0.2 * torch.randn(1280, generator=g)).half().to(dev)
+    b = (0.1 * torch.randn(1280, generator=g)).half().to(dev)
+    wide = (torch.randn(1024, 1920, generator=g) * 3).half().to(dev)
+    outs = []
+    try:
+        for mode in (0, 1, 0, 1):
+            lib.mixdq_debug_set_cluster(mode)
+            ops.clear_dynamic_quant_cache()
+            o = []
+            for rows in (256, 48, 1):          # 48 x 1280 and below: the one-cluster variants
+                o += list(ops.layernorm_quantize_dynamic(x[:rows], w, b, 1e-5))
+                o += list(ops.quantize_per_tensor_dynamic(x[:rows].clone()))
+                o += list(ops.quantize_rows_dynamic(wide[:rows, 640:]))
+            outs.append([t.clone() for t in o])
+    finally:
+        lib.mixdq_debug_set_cluster(1)
+    for o in outs[1:]:
+        for a_, b_ in zip(o, outs[0]):
+            assert torch.equal(a_, b_)
+
+
 @pytest.mark.parametrize("N,C,H,W,G,silu", [
     (1, 320, 64, 64, 32, True), (1, 640, 32, 32, 32, True), (1, 1280, 16, 16, 32, True),
     (1, 2560, 16, 16, 32, True), (1, 960, 64, 64, 32, True), (1, 1920, 32, 32, 32, True),

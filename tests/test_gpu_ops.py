@@ -139,6 +139,21 @@ def test_quant_dynamic_one_sided_and_constant(ops, dev):
         assert torch.equal(q.cpu(), qr) and s.item() == sr.item() and z.item() == zr.item()
 
 
+@pytest.mark.parametrize("lim", [0.37, 1.0, 3.3, 17.0, 900.0])
+def test_quant_dynamic_every_fp16_value(ops, dev, lim):
+    """Every finite fp16 value of [-lim, 0.71*lim] (all rounding boundaries that exist for the
+    resulting delta): the kernels' reciprocal-multiply + exact fix-up equals the true division."""
+    allh = torch.arange(0, 65536, dtype=torch.int32).to(torch.int16).view(torch.float16)
+    x = allh[torch.isfinite(allh) & (allh >= -lim) & (allh <= 0.71 * lim)].contiguous()
+    x = torch.cat([x, x.flip(0)])[: (x.numel() * 2) // 8 * 8]
+    q, s, z = ops.quantize_per_tensor_dynamic(x.to(dev))
+    qr, sr, zr = O.quantize_dynamic_kernel(x)
+    assert s.item() == sr.item() and z.item() == zr.item()
+    assert torch.equal(q.cpu(), qr)
+    q2, s2, z2 = ops.quantize_rows_dynamic(x.to(dev).view(8, -1))
+    assert torch.equal(q2.cpu().view(-1), qr) and s2.item() == sr.item()
+
+
 def test_quant_cuda_graph_replay(ops, dev):
     """The (commented-out) graph test of op/quant.py:32-61: capture once, replay on new data."""
     x = torch.rand(4096, device=dev).half()
