@@ -65,6 +65,15 @@ void        mixdq_debug_set_mode(int mode);
    hardware cluster barrier + programmatic dependent launch); 0 = always the flag-barrier grid
    kernels. Results are identical either way; A/B timing and test aid (env MIXDQ_NO_CLUSTER=1). */
 void        mixdq_debug_set_cluster(int on);
+/* Enable (1, default) / disable (0) the two-kernel form of the dynamic quantisers (a min/max pass
+   and a quantise pass chained by programmatic dependent launch); 0 = one kernel with a grid
+   barrier. Identical results; A/B timing and test aid (env MIXDQ_SINGLE_KERNEL_QUANT=1). */
+void        mixdq_debug_set_two_pass(int on);
+/* Point the dynamic-quantisation workspace `ws` at a device buffer of
+   launches x 1024 CTAs x 8 uint64 (or NULL = off): every quantiser launch that uses `ws` then
+   stores, per CTA, %globaltimer (ns) at {entry, dependency wait passed, values loaded, barrier
+   passed, done} into the region of its launch sequence number. Stream-ordered. Profiling aid. */
+int         mixdq_debug_set_quant_timing_buffer(void* ws, void* dev_ptr, mixdq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * A1  static per-tensor activation quantisation, fp16 -> int8

@@ -18,7 +18,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libmixdq_b200.so"
 ABI_SYMBOLS = [
     "mixdq_abi_version", "mixdq_set_workspace", "mixdq_debug_set_pdl", "mixdq_strerror", "mixdq_last_path", "mixdq_force_simt",
     "mixdq_debug_force_bn", "mixdq_debug_force_splits", "mixdq_debug_set_timing_buffer",
-    "mixdq_debug_set_mode", "mixdq_debug_set_cluster",
+    "mixdq_debug_set_mode", "mixdq_debug_set_cluster", "mixdq_debug_set_two_pass", "mixdq_debug_set_quant_timing_buffer",
     "mixdq_quant_i8_static", "mixdq_quant_i8_static_strided", "mixdq_quant_i8_nchw2nhwc",
     "mixdq_quant_dynamic_ws_bytes", "mixdq_quant_i8_dynamic",
     "mixdq_gemm_w8a8_f16", "mixdq_gemm_w8a8_f16_dyn", "mixdq_gemm_w4a8_f16",
@@ -53,6 +53,10 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mixdq_debug_force_splits.argtypes = [c_int]
     lib.mixdq_debug_set_timing_buffer.restype = None
     lib.mixdq_debug_set_timing_buffer.argtypes = [P]
+    lib.mixdq_debug_set_quant_timing_buffer.restype = c_int
+    lib.mixdq_debug_set_quant_timing_buffer.argtypes = [P, P, P]
+    lib.mixdq_debug_set_two_pass.restype = None
+    lib.mixdq_debug_set_two_pass.argtypes = [c_int]
     lib.mixdq_debug_set_cluster.restype = None
     lib.mixdq_debug_set_cluster.argtypes = [c_int]
     lib.mixdq_debug_set_mode.restype = None

@@ -325,8 +325,10 @@ extern "C" int mixdq_gemm_w8a8_geglu_f16_dyn(const int8_t* A, int64_t lda, const
   p.scale = w_scale_il; p.bias0 = wsum_il; p.a_scale = a_scale; p.a_zp = a_zp;
   p.bias = reinterpret_cast<const __half*>(bias_il);
   p.D = reinterpret_cast<__half*>(Y); p.ldd = ldy;
-  p.mm = static_cast<DynWs*>(ws)->mm;     // address arithmetic only: ws is a device pointer
+  p.mm_partial = static_cast<DynWs*>(ws)->partial;   // address arithmetic only (device pointer)
   dim3 grid(m_tiles, (N2 + bn - 1) / bn, 1);
+  if (static_cast<int64_t>(grid.x) * grid.y > kMaxPartials) return MIXDQ_ERR_UNSUPPORTED;
+  partial_count_slot(ws) = static_cast<int>(grid.x * grid.y);
   g_last_path = "tcgen05-geglu";
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (bn) {

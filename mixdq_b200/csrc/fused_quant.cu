@@ -117,9 +117,12 @@ ln_quant_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
                 float* __restrict__ scale_out, float* __restrict__ zp_out, int rows_per_cta,
                 int stash_rows) {
   extern __shared__ int4 stash[];   // [stash_rows][C/8]
+  QDbg dbg;
+  dbg.begin(ws);
   pdl_launch_dependents();
   if (CLUSTER) cluster_enter();
   pdl_wait();
+  dbg.waited(ws);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = C >> 3;
   const int row0 = blockIdx.x * rows_per_cta;
@@ -140,8 +143,10 @@ ln_quant_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
     }
   }
   float delta, z;
+  dbg.stamp(2);
   if (CLUSTER) cluster_minmax_params<kFqThreads>(mn, mx, scale_out, zp_out, delta, z);
   else grid_minmax_params<kFqThreads>(ws, mn, mx, scale_out, zp_out, delta, z);
+  dbg.stamp(3);
   for (int r = row0 + warp; r < row1; r += kFqWarps) {
     const int lr = r - row0;
     uint2* qrow = reinterpret_cast<uint2*>(q + static_cast<int64_t>(r) * C);
@@ -157,6 +162,7 @@ ln_quant_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
       }
     }
   }
+  dbg.end(ws);
 }
 
 // =============================================================================================
@@ -288,7 +294,10 @@ __device__ __forceinline__ int4 gn_vec8(const int4& raw, int c8, int cpg,
   return pack8(o);
 }
 
-template <bool SILU>
+// MODE 0: everything in one kernel (two grid barriers).  MODE 1 / MODE 2: the same code cut at
+// the first barrier into a statistics kernel and an apply kernel (normalise -> fp16 y + min/max
+// published for quant2.cu's single-pass quantiser), chained by programmatic dependent launch.
+template <bool SILU, int MODE>
 __global__ void __launch_bounds__(kFqThreads, 1)
 gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C, int G,
                 const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps,
@@ -308,6 +317,7 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
   const int row1 = min(HW, row0 + rows_per_cta);
   const __half* ximg = x + static_cast<int64_t>(n) * HW * ldx;
 
+  if (MODE != 2) {
   // ---- phase 0: per-(n, group) sum / sum of squares ----
   float acc[kGnMaxChunks][4];   // per owned chunk: (sum, sq) of its low group, (sum, sq) of its high group
 #pragma unroll
@@ -363,6 +373,7 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
     const long long fixed = __double2ll_rn(static_cast<double>(t) * (k ? kFixSq : kFixSum));
     atomicAdd(&ws->gsum[(n * G) * 2 + threadIdx.x], static_cast<unsigned long long>(fixed));
   }
+  if (MODE == 1) return;     // statistics kernel: the kernel boundary is the barrier
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -374,6 +385,7 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
     }
   }
   __syncthreads();
+  }  // MODE != 2
   if (threadIdx.x < G) {
     const long long fs = static_cast<long long>(__ldcg(&ws->gsum[(n * G + threadIdx.x) * 2]));
     const long long fq = static_cast<long long>(__ldcg(&ws->gsum[(n * G + threadIdx.x) * 2 + 1]));
@@ -385,17 +397,19 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
     s_rstd[threadIdx.x] = rsqrtf(static_cast<float>(var) + eps);
   }
   __syncthreads();
-  // the last CTA to have read the statistics re-zeroes them for the next call
-  if (threadIdx.x == 0) s_last = (atomicAdd(&ws->done2, 1u) == gridDim.x - 1) ? 1 : 0;
+  // the last CTA to have read the statistics re-zeroes them for the next call (MODE 2: the
+  // quantise pass that follows clears them instead — nobody waits here)
+  if (MODE == 2) s_last = 0;
+  if (MODE != 2 && threadIdx.x == 0) s_last = (atomicAdd(&ws->done2, 1u) == gridDim.x - 1) ? 1 : 0;
   __syncthreads();
-  if (s_last) {
+  if (MODE != 2 && s_last) {
     for (int i = threadIdx.x; i < NB * G * 2; i += kFqThreads) ws->gsum[i] = 0ull;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
       ws->done2 = 0;
       __threadfence();
-      st_release_u32(&ws->counter2, 0u);
+      if (MODE == 0) st_release_u32(&ws->counter2, 0u);
     }
   }
 
@@ -407,10 +421,27 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
     for (int c = lane; c < nchunks; c += 32) {
       const int4 y = gn_vec8<SILU>(ldg16(xrow + 8 * c), 8 * c, cpg, s_mean, s_rstd, gamma, beta);
       minmax_vec8(y, mn, mx);
-      if (lr < stash_rows) stash[lr * nchunks + c] = y;
+      if (MODE == 0 && lr < stash_rows) stash[lr * nchunks + c] = y;
       if (y_out)
         reinterpret_cast<int4*>(y_out + (static_cast<int64_t>(n) * HW + r) * C)[c] = y;
     }
+  }
+  if (MODE == 2) {
+    // store this CTA's min / max partial (quant2.cu protocol) and stop: quantisation is the next
+    // kernel's job
+    __shared__ float s_mn[kFqWarps], s_mx[kFqWarps];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kFqWarps; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+      ws->partial[blockIdx.x] = make_float2(mn, mx);
+    }
+    return;
   }
   float delta, z;
   grid_minmax_params<kFqThreads>(ws, mn, mx, scale_out, zp_out, delta, z);
@@ -439,6 +470,17 @@ static int set_smem(K kern, int bytes) {
 }  // namespace mixdq
 
 using namespace mixdq;
+
+// quant2.cu / quant.cu
+int mixdq_q2_rows(const __half* x, int64_t ldx, int64_t M, int cols, int8_t* q, float* scale_out,
+                  float* zp_out, void* ws, cudaStream_t st);
+int mixdq_q2_premm(const __half* x, int64_t numel, int8_t* q, float* scale_out, float* zp_out,
+                   void* ws, int nparts, unsigned long long* zero_words, int zero_n,
+                   cudaStream_t st);
+int mixdq_q2_ln(const __half* x, int64_t ldx, int M, int C, const __half* gamma,
+                const __half* beta, float eps, int8_t* q, __half* y, float* scale_out,
+                float* zp_out, void* ws, cudaStream_t st);
+bool mixdq_two_pass_enabled();
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -517,6 +559,15 @@ extern "C" int mixdq_ln_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int
       return MIXDQ_ERR_CUDA;
     return MIXDQ_OK;
   }
+  // LayerNorm -> fp16 + min/max, then the single-pass quantiser: needs the caller's y buffer
+  if (y_out && mixdq_two_pass_enabled()) {
+    const int rc = mixdq_q2_ln(reinterpret_cast<const __half*>(x), ldx, M, C,
+                               reinterpret_cast<const __half*>(gamma),
+                               reinterpret_cast<const __half*>(beta), eps, q,
+                               reinterpret_cast<__half*>(y_out), scale_out, zp_out, ws,
+                               static_cast<cudaStream_t>(stream));
+    if (rc != MIXDQ_ERR_UNSUPPORTED) return rc;
+  }
   // one row per warp; >= 2 rows per CTA keeps the grid <= 128 CTAs for the batch-1 blocks
   plan_rows(M, static_cast<int64_t>(C) * 2, 2, &grid, &rpc, &srows, &smem);
   auto kern = (C <= 5 * 256) ? ln_quant_kernel<5, false> : ln_quant_kernel<8, false>;
@@ -570,6 +621,11 @@ extern "C" int mixdq_quant_i8_dynamic_rows(const mixdq_half_t* x, int64_t ldx, i
       return MIXDQ_ERR_CUDA;
     return MIXDQ_OK;
   }
+  if (mixdq_two_pass_enabled()) {
+    const int rc = mixdq_q2_rows(reinterpret_cast<const __half*>(x), ldx, M, cols, q, scale_out,
+                                 zp_out, ws, static_cast<cudaStream_t>(stream));
+    if (rc != MIXDQ_ERR_UNSUPPORTED) return rc;
+  }
   // >= 16 KB of fp16 (two 16-byte vectors per thread) per CTA
   int min_rows = static_cast<int>((8192 + cols - 1) / cols);
   if (min_rows < 1) min_rows = 1;
@@ -600,7 +656,9 @@ extern "C" int mixdq_gn_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int
     return MIXDQ_ERR_UNSUPPORTED;
   static bool attr = false;
   if (!attr) {
-    if (set_smem(gn_quant_kernel<true>, kFqMaxSmem) || set_smem(gn_quant_kernel<false>, kFqMaxSmem))
+    if (set_smem(gn_quant_kernel<true, 0>, kFqMaxSmem) || set_smem(gn_quant_kernel<false, 0>, kFqMaxSmem) ||
+        set_smem(gn_quant_kernel<true, 1>, kFqMaxSmem) || set_smem(gn_quant_kernel<false, 1>, kFqMaxSmem) ||
+        set_smem(gn_quant_kernel<true, 2>, kFqMaxSmem) || set_smem(gn_quant_kernel<false, 2>, kFqMaxSmem))
       return MIXDQ_ERR_CUDA;
     attr = true;
   }
@@ -616,7 +674,27 @@ extern "C" int mixdq_gn_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int
   const int scratch = kFqWarps * (C / 8) * 16;   // phase-0 partials [warps][chunks] float4
   if (smem < scratch) smem = scratch;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  auto gk = silu ? gn_quant_kernel<true> : gn_quant_kernel<false>;
+  if (y_out && mixdq_two_pass_enabled() && static_cast<int64_t>(NB) * HW * (C >> 3) < (1ll << 31)) {
+    // statistics kernel -> apply kernel (fp16 y + min/max) -> single-pass quantiser. No CTA waits
+    // for another one, so the grids need not be co-resident: the same row split is kept because
+    // the statistics kernel's deterministic in-CTA reduction is written for it.
+    auto k1 = silu ? gn_quant_kernel<true, 1> : gn_quant_kernel<false, 1>;
+    auto k2 = silu ? gn_quant_kernel<true, 2> : gn_quant_kernel<false, 2>;
+    const __half* xh = reinterpret_cast<const __half*>(x);
+    const __half* gh = reinterpret_cast<const __half*>(gamma);
+    const __half* bh = reinterpret_cast<const __half*>(beta);
+    __half* yh = reinterpret_cast<__half*>(y_out);
+    DynWs* w = static_cast<DynWs*>(ws);
+    if (launch_pdl(k1, NB * cpi, kFqThreads, scratch, st, xh, ldx, NB, HW, C, G, gh, bh, eps, q, yh,
+                   w, scale_out, zp_out, cpi, rpc, 0) != cudaSuccess)
+      return MIXDQ_ERR_CUDA;
+    if (launch_pdl(k2, NB * cpi, kFqThreads, 0, st, xh, ldx, NB, HW, C, G, gh, bh, eps, q, yh, w,
+                   scale_out, zp_out, cpi, rpc, 0) != cudaSuccess)
+      return MIXDQ_ERR_CUDA;
+    return mixdq_q2_premm(yh, static_cast<int64_t>(NB) * HW * C, q, scale_out, zp_out, ws,
+                          NB * cpi, w->gsum, NB * G * 2, st);
+  }
+  auto gk = silu ? gn_quant_kernel<true, 0> : gn_quant_kernel<false, 0>;
   if (launch_pdl(gk, NB * cpi, kFqThreads, smem, st, reinterpret_cast<const __half*>(x), ldx, NB, HW,
                  C, G, reinterpret_cast<const __half*>(gamma), reinterpret_cast<const __half*>(beta),
                  eps, q, reinterpret_cast<__half*>(y_out), static_cast<DynWs*>(ws), scale_out,

@@ -205,9 +205,12 @@ quant_dynamic_fused_kernel(const __half* __restrict__ x, int8_t* __restrict__ q,
                            DynWs* __restrict__ ws, float* __restrict__ scale_out,
                            float* __restrict__ zp_out) {
   constexpr int kQuantThreads = NT;   // shadows the file-level constant inside this kernel
+  QDbg dbg;
+  dbg.begin(ws);
   pdl_launch_dependents();
   if (CLUSTER) cluster_enter();
   pdl_wait();
+  dbg.waited(ws);
   float mn = 0.0f, mx = 0.0f;  // qdiff clamps x_min <= 0 <= x_max (base_quantizer.py:155-158)
   const int64_t nvec = numel >> 3;
   const int4* xv = reinterpret_cast<const int4*>(x);
@@ -232,9 +235,11 @@ quant_dynamic_fused_kernel(const __half* __restrict__ x, int8_t* __restrict__ q,
     mx = fmaxf(mx, tailv);
   }
   QParams p;
+  dbg.stamp(2);
   if (CLUSTER) cluster_minmax_params<NT>(mn, mx, scale_out, zp_out, p.a, p.b);
   else grid_minmax_params<NT>(ws, mn, mx, scale_out, zp_out, p.a, p.b);
   p.inv = __frcp_rn(p.a);
+  dbg.stamp(3);
 #pragma unroll
   for (int u = 0; u < kDynCache; ++u) {
     const int64_t i = i0 + u * stride;
@@ -243,42 +248,7 @@ quant_dynamic_fused_kernel(const __half* __restrict__ x, int8_t* __restrict__ q,
   for (int64_t i = i0 + kDynCache * stride; i < nvec; i += stride)
     qv[i] = quant_vec8<kDynamicDiv>(__ldg(xv + i), p);
   if (t < numel) q[t] = static_cast<int8_t>(quant_one<kDynamicDiv>(tailv, p));
-}
-
-// A10 when the tensor's min / max were already folded into ws->mm by the kernel that produced x
-// (tc_i8_kernel<KIND_GEGLU>): one pass, no barrier. Programmatic dependency on the producer.
-__global__ void __launch_bounds__(kQuantThreads)
-quant_premm_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int64_t nvec,
-                   DynWs* __restrict__ ws, float* __restrict__ scale_out,
-                   float* __restrict__ zp_out) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const float mn = 0.0f - __int_as_float(static_cast<int>(__ldcg(&ws->mm[0])));
-  const float mx = __int_as_float(static_cast<int>(__ldcg(&ws->mm[1])));
-  QParams p;
-  qdiff_params(mn, mx, p.a, p.b);
-  p.inv = __frcp_rn(p.a);
-  if (blockIdx.x == 0 && threadIdx.x == 0) { *scale_out = p.a; *zp_out = p.b - 128.0f; }
-  const int4* xv = reinterpret_cast<const int4*>(x);
-  uint2* qv = reinterpret_cast<uint2*>(q);
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * kQuantThreads;
-  for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * kQuantThreads + threadIdx.x; i0 < nvec;
-       i0 += kQuantUnroll * stride) {
-    int4 v[kQuantUnroll];
-#pragma unroll
-    for (int u = 0; u < kQuantUnroll; ++u)
-      if (i0 + u * stride < nvec) v[u] = ld_stream16(xv + i0 + u * stride);
-#pragma unroll
-    for (int u = 0; u < kQuantUnroll; ++u)
-      if (i0 + u * stride < nvec) qv[i0 + u * stride] = quant_vec8<kDynamicDiv>(v[u], p);
-  }
-  __syncthreads();   // every thread of this CTA has read mm
-  if (threadIdx.x == 0) {
-    __threadfence();
-    if (atomicAdd(&ws->mm_done, 1u) == gridDim.x - 1) {
-      ws->mm[0] = 0u; ws->mm[1] = 0u; ws->mm_done = 0u;
-    }
-  }
+  dbg.end(ws);
 }
 
 static inline int grid_for(int64_t items, int per_block, int max_blocks) {
@@ -292,7 +262,39 @@ static inline int grid_for(int64_t items, int per_block, int max_blocks) {
 
 using namespace mixdq;
 
+// quant2.cu: the two-kernel (min/max pass + quantise pass) implementations
+int mixdq_q2_rows(const __half* x, int64_t ldx, int64_t M, int cols, int8_t* q, float* scale_out,
+                  float* zp_out, void* ws, cudaStream_t st);
+int mixdq_q2_premm(const __half* x, int64_t numel, int8_t* q, float* scale_out, float* zp_out,
+                   void* ws, int nparts, unsigned long long* zero_words, int zero_n,
+                   cudaStream_t st);
+static int g_two_pass = -1;   // MIXDQ_SINGLE_KERNEL_QUANT=1 keeps the single-kernel quantisers
+bool mixdq_two_pass_enabled() {
+  if (g_two_pass < 0) {
+    const char* e = getenv("MIXDQ_SINGLE_KERNEL_QUANT");
+    g_two_pass = (e && e[0] == '1') ? 0 : 1;
+  }
+  return g_two_pass != 0;
+}
+extern "C" void mixdq_debug_set_two_pass(int on) { g_two_pass = on ? 1 : 0; }
+
 extern "C" void mixdq_debug_set_cluster(int on) { cluster_mode_flag() = on ? 1 : 0; }
+// profiling: point the workspace at a stamp buffer (or NULL) and restart the launch sequence;
+// stream-ordered device writes, no synchronisation
+extern "C" int mixdq_debug_set_quant_timing_buffer(void* ws, void* dev_ptr, mixdq_stream_t stream) {
+  if (!ws) return MIXDQ_ERR_INVALID_ARG;
+  DynWs* w = static_cast<DynWs*>(ws);
+  static unsigned long long* h_ptr[64];
+  static unsigned int h_zero = 0;
+  static int slot = 0;
+  unsigned long long** hp = &h_ptr[slot++ & 63];
+  *hp = static_cast<unsigned long long*>(dev_ptr);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cudaMemcpyAsync(&w->qdbg, hp, sizeof(*hp), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(&w->qdbg_seq, &h_zero, sizeof(h_zero), cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return MIXDQ_ERR_CUDA;
+  return MIXDQ_OK;
+}
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
@@ -397,6 +399,11 @@ extern "C" int mixdq_quant_i8_dynamic(const mixdq_half_t* x, int64_t numel, floa
       return MIXDQ_ERR_CUDA;
     return MIXDQ_OK;
   }
+  // two short kernels (min/max, then quantise) beat one kernel with a grid barrier (quant2.cu)
+  if (mixdq_two_pass_enabled() && (numel & 7) == 0 && numel < (1ll << 31)) {
+    const int rc = mixdq_q2_rows(xh, numel, 1, static_cast<int>(numel), q, scale_out, zp_out, ws, st);
+    if (rc != MIXDQ_ERR_UNSUPPORTED) return rc;
+  }
   // co-resident grid: at most 2 CTAs per SM (see quant_dynamic_fused_kernel)
   int grid = grid_for(numel >> 3, kQuantThreads * 2, 148 * 2);
   if (launch_pdl(quant_dynamic_fused_kernel<kQuantThreads, false>, grid, kQuantThreads, 0, st, xh,
@@ -410,19 +417,6 @@ extern "C" int mixdq_quant_i8_premm(const mixdq_half_t* x, int64_t numel, int8_t
                                     mixdq_stream_t stream) {
   if (numel <= 0 || !x || !q || !scale_out || !zp_out || !ws) return MIXDQ_ERR_INVALID_ARG;
   if ((numel & 7) || !aligned16(x) || !aligned8(q)) return MIXDQ_ERR_ALIGNMENT;
-  const int64_t nvec = numel >> 3;
-  const int grid = grid_for(nvec, kQuantThreads * kQuantUnroll, 148 * 4);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kQuantThreads);
-  cfg.stream = static_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, quant_premm_kernel, reinterpret_cast<const __half*>(x), q, nvec,
-                         static_cast<DynWs*>(ws), scale_out, zp_out) != cudaSuccess)
-    return MIXDQ_ERR_CUDA;
-  return MIXDQ_OK;
+  return mixdq_q2_premm(reinterpret_cast<const __half*>(x), numel, q, scale_out, zp_out, ws,
+                        partial_count_slot(ws), nullptr, 0, static_cast<cudaStream_t>(stream));
 }

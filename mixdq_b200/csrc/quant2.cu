@@ -1,0 +1,374 @@
+// quant2.cu — dynamic activation quantisation (A10) as SHORT kernels chained by programmatic
+// dependent launch, instead of one kernel with a grid barrier in the middle.
+//
+// Measured inside the batch-1 UNet graph on B200 (tools/quant_phase.py, %globaltimer stamps): the
+// single-kernel quantisers spent 2.6-3.6 us in the grid barrier alone (store + release fence +
+// acquire spin + reload, all dependent L2 round trips) and ~2 us in each fully unrolled 50-60 KB
+// code phase that a CTA executes exactly once (instruction fetch, not arithmetic), while a kernel
+// boundary under programmatic dependent launch costs ~1.0 us. Hence:
+//
+//   pass 1  (minmax_rows_kernel | ln_minmax_kernel | gn_apply in fused_quant.cu | the GEGLU
+//           epilogue of tc_i8_kernel) produce the fp16 values (if any op is fused); every CTA
+//           stores ITS min / max into DynWs::partial[cta] — plain stores, no atomics, nothing to
+//           reset;
+//   pass 2  quant_rows_premm_kernel: every CTA reduces the producer's partials (a few KB from
+//           L2, issued together with its first data load), quantises and writes int8.
+//
+// Every kernel here is a few KB of code: loops are not unrolled beyond what memory-level
+// parallelism needs, min/max runs on packed halves (HMNMX2, exact), and the one-in-500 exact
+// division of the rounding fix-up lives in a single out-of-line function.
+#include "common.cuh"
+#include "quant_ws.cuh"
+#include "../../include/mixdq_b200.h"
+
+namespace mixdq {
+
+constexpr int kQ2Threads = 256;
+
+// rare path of qdiff_round_quot, kept out of line so the hot loop stays small
+__device__ __noinline__ float exact_round_quot(float x, float delta) {
+  return rintf(__fdiv_rn(x, delta));
+}
+
+// 8 halves -> 8 codes, compact: fast reciprocal path for all, exact fix-up only when any element
+// of the vector sits within 1e-4 of a rounding boundary (see qdiff_round_quot in quant_ws.cuh;
+// 1e-4 > the 5e-5 error bound, and keeps the out-of-line path to ~5 % of the warps)
+__device__ __forceinline__ uint2 quant8_compact(const int4& raw, float delta, float inv, float z) {
+  const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+  float x[8], r[8];
+  bool near = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h2[i]);
+    x[2 * i] = f.x;
+    x[2 * i + 1] = f.y;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float t = __fmul_rn(x[i], inv);
+    r[i] = rintf(t);
+    near |= fabsf(__fsub_rn(t, r[i])) > 0.4999f;   // |t - x/delta| < 5e-5 (see quant_ws.cuh)
+  }
+  if (near) {
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+      // select element i without dynamic register indexing
+      float xi = x[0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) xi = (i == j) ? x[j] : xi;
+      const float e = exact_round_quot(xi, delta);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = (i == j) ? e : r[j];
+    }
+  }
+  uint32_t w[2] = {0u, 0u};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float c = __fadd_rn(r[i], z);
+    c = fminf(fmaxf(c, 0.0f), 255.0f);
+    const uint32_t b = static_cast<uint32_t>(static_cast<int>(c) - 128) & 0xffu;
+    w[i >> 2] |= b << (8 * (i & 3));
+  }
+  return make_uint2(w[0], w[1]);
+}
+
+// packed-half running min / max of one 16-byte vector (exact: no rounding in min/max)
+__device__ __forceinline__ void hminmax8(const int4& raw, __half2& mn, __half2& mx) {
+  const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    mn = __hmin2(mn, h2[i]);
+    mx = __hmax2(mx, h2[i]);
+  }
+}
+
+// CTA-wide reduction of the packed running min / max; thread 0 stores the CTA's partial.
+template <int NT>
+__device__ __forceinline__ void publish_partial(DynWs* __restrict__ ws, __half2 mn2, __half2 mx2) {
+  constexpr int NW = NT / 32;
+  __shared__ float s_mn[NW], s_mx[NW];
+  float mn = fminf(__low2float(mn2), __high2float(mn2));
+  float mx = fmaxf(__low2float(mx2), __high2float(mx2));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (NW > 1) {
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    if (warp == 0) {
+      mn = lane < NW ? s_mn[lane] : 0.0f;
+      mx = lane < NW ? s_mx[lane] : 0.0f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+    }
+  }
+  // qdiff clamps x_min <= 0 <= x_max (base_quantizer.py:155-158)
+  if (threadIdx.x == 0) ws->partial[blockIdx.x] = make_float2(fminf(mn, 0.0f), fmaxf(mx, 0.0f));
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1, plain tensor: min / max of a row-pitched fp16 view [M][8*nchunks] (pitch ldx halves)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kQ2Threads)
+minmax_rows_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int nchunks,
+                   unsigned int items, DynWs* __restrict__ ws) {
+  QDbg dbg;
+  dbg.begin(ws);
+  pdl_launch_dependents();
+  pdl_wait();
+  dbg.waited(ws);
+  __half2 mn = __float2half2_rn(0.0f), mx = mn;
+  const unsigned int stride = gridDim.x * kQ2Threads;
+#pragma unroll 2
+  for (unsigned int it = blockIdx.x * kQ2Threads + threadIdx.x; it < items; it += stride) {
+    const unsigned int r = it / nchunks;
+    const unsigned int c = it - r * nchunks;
+    hminmax8(__ldcg(reinterpret_cast<const int4*>(x + static_cast<int64_t>(r) * ldx) + c), mn, mx);
+  }
+  dbg.stamp(2);
+  publish_partial<kQ2Threads>(ws, mn, mx);
+  dbg.stamp(3);
+  dbg.end(ws);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2: quantise a row-pitched fp16 view with the min / max of the producer's `nparts` partials
+// -> dense int8. `zero_words` (optional): u64 words block 0 clears for the next producer
+// (GroupNorm statistics accumulators).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kQ2Threads)
+quant_rows_premm_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int nchunks,
+                        unsigned int items, int8_t* __restrict__ q, DynWs* __restrict__ ws,
+                        int nparts, float* __restrict__ scale_out, float* __restrict__ zp_out,
+                        unsigned long long* __restrict__ zero_words, int zero_n) {
+  __shared__ float s_mn[kQ2Threads / 32], s_mx[kQ2Threads / 32];
+  QDbg dbg;
+  dbg.begin(ws);
+  pdl_launch_dependents();
+  pdl_wait();
+  dbg.waited(ws);
+  const unsigned int stride = gridDim.x * kQ2Threads;
+  unsigned int it = blockIdx.x * kQ2Threads + threadIdx.x;
+  // first data vector and the partials travel together
+  int4 v = make_int4(0, 0, 0, 0);
+  if (it < items) {
+    const unsigned int r = it / nchunks;
+    v = __ldcg(reinterpret_cast<const int4*>(x + static_cast<int64_t>(r) * ldx) + (it - r * nchunks));
+  }
+  float mn = 0.0f, mx = 0.0f;
+  for (int i = threadIdx.x; i < nparts; i += kQ2Threads) {
+    const float2 p = __ldcg(&ws->partial[i]);
+    mn = fminf(mn, p.x);
+    mx = fmaxf(mx, p.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kQ2Threads / 32; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+  float delta, z;
+  qdiff_params(mn, mx, delta, z);
+  const float inv = __frcp_rn(delta);
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) { *scale_out = delta; *zp_out = z - 128.0f; }
+    for (int i = threadIdx.x; i < zero_n; i += kQ2Threads) zero_words[i] = 0ull;
+  }
+  dbg.stamp(2);
+  uint2* qv = reinterpret_cast<uint2*>(q);
+  if (it < items) qv[it] = quant8_compact(v, delta, inv, z);
+#pragma unroll 1
+  for (it += stride; it < items; it += stride) {
+    const unsigned int r = it / nchunks;
+    const unsigned int c = it - r * nchunks;
+    v = __ldcg(reinterpret_cast<const int4*>(x + static_cast<int64_t>(r) * ldx) + c);
+    qv[it] = quant8_compact(v, delta, inv, z);
+  }
+  dbg.stamp(3);
+  dbg.end(ws);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1, LayerNorm: y = half(gamma * (rstd * (x - mean)) + beta) -> fp16 [M][C] + min / max.
+// One row per warp at a time; 2 warps per CTA for the 256-token blocks of the batch-1 step (128
+// CTAs), 8 warps and a row loop (<= 512 CTAs = partials) for larger M.
+// PyTorch: statistics in fp32, biased variance (same restatement as fused_quant.cu::ln_row).
+// ---------------------------------------------------------------------------------------------
+template <int MAXCH, int NT>
+__global__ void __launch_bounds__(NT)
+ln_minmax_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
+                 const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps,
+                 __half* __restrict__ y, DynWs* __restrict__ ws) {
+  QDbg dbg;
+  dbg.begin(ws);
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = C >> 3;
+  // gamma / beta do not depend on the producer: fetch them before the dependency wait
+  int4 gr[MAXCH], br[MAXCH];
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) {
+      gr[i] = __ldg(reinterpret_cast<const int4*>(gamma) + c);
+      br[i] = __ldg(reinterpret_cast<const int4*>(beta) + c);
+    }
+  }
+  pdl_wait();
+  dbg.waited(ws);
+  __half2 mn = __float2half2_rn(0.0f), mx = mn;
+#pragma unroll 1
+  for (int r = blockIdx.x * (NT / 32) + warp; r < M; r += gridDim.x * (NT / 32)) {
+    const int4* xrow = reinterpret_cast<const int4*>(x + static_cast<int64_t>(r) * ldx);
+    int4 raw[MAXCH];
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) raw[i] = __ldcg(xrow + c);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) {
+      if (lane + 32 * i < nchunks) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h2[j]);
+          sum += f.x;
+          sum += f.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / static_cast<float>(C);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) {
+      if (lane + 32 * i < nchunks) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h2[j]);
+          const float d0 = f.x - mean, d1 = f.y - mean;
+          ss += d0 * d0;
+          ss += d1 * d1;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / static_cast<float>(C) + eps);
+    int4* yrow = reinterpret_cast<int4*>(y + static_cast<int64_t>(r) * C);
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[i]);
+        const __half2* g2 = reinterpret_cast<const __half2*>(&gr[i]);
+        const __half2* b2 = reinterpret_cast<const __half2*>(&br[i]);
+        int4 out;
+        __half2* o2 = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h2[j]);
+          const float2 g = __half22float2(g2[j]);
+          const float2 b = __half22float2(b2[j]);
+          o2[j] = __floats2half2_rn(fmaf(g.x, rstd * (f.x - mean), b.x),
+                                    fmaf(g.y, rstd * (f.y - mean), b.y));
+        }
+        hminmax8(out, mn, mx);
+        yrow[c] = out;
+      }
+    }
+  }
+  dbg.stamp(2);
+  publish_partial<NT>(ws, mn, mx);
+  dbg.stamp(3);
+  dbg.end(ws);
+}
+
+static inline int grid_for2(int64_t items, int per_block, int max_blocks) {
+  int64_t g = (items + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return static_cast<int>(g);
+}
+
+}  // namespace mixdq
+
+using namespace mixdq;
+
+// ---- internal entry points used by quant.cu / fused_quant.cu ---------------------------------
+// All return MIXDQ_ERR_UNSUPPORTED for tensors of >= 2^31 16-byte vectors (callers fall back to
+// the single-kernel path).
+static const int64_t kMaxItems = (1ll << 31) - 1;
+
+// A10 of a row-pitched view in two short kernels. cols % 8 == 0, 16-byte aligned rows.
+int mixdq_q2_rows(const __half* x, int64_t ldx, int64_t M, int cols, int8_t* q, float* scale_out,
+                  float* zp_out, void* ws, cudaStream_t st) {
+  const int64_t items = M * (cols >> 3);
+  if (items > kMaxItems) return MIXDQ_ERR_UNSUPPORTED;
+  // dense: one long row (no division result other than 0)
+  const unsigned int nchunks = (ldx == cols) ? static_cast<unsigned int>(items)
+                                             : static_cast<unsigned int>(cols >> 3);
+  const unsigned int n = static_cast<unsigned int>(items);
+  const int g1 = grid_for2(items, kQ2Threads * 2, 148 * 4);
+  if (launch_pdl(minmax_rows_kernel, g1, kQ2Threads, 0, st, x, ldx, nchunks, n,
+                 static_cast<DynWs*>(ws)) != cudaSuccess)
+    return MIXDQ_ERR_CUDA;
+  const int g2 = grid_for2(items, kQ2Threads, 148 * 8);
+  if (launch_pdl(quant_rows_premm_kernel, g2, kQ2Threads, 0, st, x, ldx, nchunks, n, q,
+                 static_cast<DynWs*>(ws), g1, scale_out, zp_out,
+                 static_cast<unsigned long long*>(nullptr), 0) != cudaSuccess)
+    return MIXDQ_ERR_CUDA;
+  return MIXDQ_OK;
+}
+
+// pass 2 alone on a dense tensor: the producer's CTAs stored `nparts` partials into ws->partial
+int mixdq_q2_premm(const __half* x, int64_t numel, int8_t* q, float* scale_out, float* zp_out,
+                   void* ws, int nparts, unsigned long long* zero_words, int zero_n,
+                   cudaStream_t st) {
+  const int64_t items = numel >> 3;
+  if (items > kMaxItems || nparts < 1 || nparts > kMaxPartials) return MIXDQ_ERR_UNSUPPORTED;
+  const unsigned int n = static_cast<unsigned int>(items);
+  const int g2 = grid_for2(items, kQ2Threads, 148 * 8);
+  if (launch_pdl(quant_rows_premm_kernel, g2, kQ2Threads, 0, st, x, static_cast<int64_t>(0), n, n,
+                 q, static_cast<DynWs*>(ws), nparts, scale_out, zp_out, zero_words, zero_n) !=
+      cudaSuccess)
+    return MIXDQ_ERR_CUDA;
+  return MIXDQ_OK;
+}
+
+// LayerNorm -> fp16 y (caller's buffer) + per-CTA min/max, then pass 2 on y
+int mixdq_q2_ln(const __half* x, int64_t ldx, int M, int C, const __half* gamma,
+                const __half* beta, float eps, int8_t* q, __half* y, float* scale_out,
+                float* zp_out, void* ws, cudaStream_t st) {
+  if (static_cast<int64_t>(M) * (C >> 3) > kMaxItems) return MIXDQ_ERR_UNSUPPORTED;
+  DynWs* w = static_cast<DynWs*>(ws);
+  cudaError_t e;
+  int g1;
+  if (M <= 512) {
+    g1 = (M + 1) / 2;
+    e = (C <= 5 * 256)
+            ? launch_pdl(ln_minmax_kernel<5, 64>, g1, 64, 0, st, x, ldx, M, C, gamma, beta, eps, y, w)
+            : launch_pdl(ln_minmax_kernel<8, 64>, g1, 64, 0, st, x, ldx, M, C, gamma, beta, eps, y, w);
+  } else {
+    g1 = (M + 7) / 8;
+    if (g1 > 512) g1 = 512;
+    e = (C <= 5 * 256)
+            ? launch_pdl(ln_minmax_kernel<5, 256>, g1, 256, 0, st, x, ldx, M, C, gamma, beta, eps, y, w)
+            : launch_pdl(ln_minmax_kernel<8, 256>, g1, 256, 0, st, x, ldx, M, C, gamma, beta, eps, y, w);
+  }
+  if (e != cudaSuccess) return MIXDQ_ERR_CUDA;
+  return mixdq_q2_premm(y, static_cast<int64_t>(M) * C, q, scale_out, zp_out, ws, g1, nullptr, 0, st);
+}

@@ -15,7 +15,7 @@
 
 namespace mixdq {
 
-constexpr int kMaxPartials = 1024;   // CTAs of one launch
+constexpr int kMaxPartials = 4096;   // CTAs of one producer launch
 constexpr int kMaxStatGroups = 4096; // (image, group) pairs of one GroupNorm launch
 
 struct DynWs {
@@ -33,9 +33,10 @@ struct DynWs {
   unsigned int mm[2];     // bit patterns of -min (>= +0) and max (>= +0), atomicMax'ed as ints
   unsigned int mm_done;   // consumer CTAs that have read mm (the last one zeroes all three)
   unsigned int pad2;
-  // ---- min/max of the flag barrier itself (same encoding as mm) ----
-  unsigned int gmm[2];
-  unsigned int pad3[2];
+  unsigned int gmm[2];    // unused (kept for layout stability)
+  unsigned int qdbg_seq;  // profiling: launches stamped so far (see QDbg)
+  unsigned int pad3;
+  unsigned long long* qdbg;   // profiling: stamp buffer or NULL
   float2 partial[kMaxPartials];
   // fixed-point (integer => order-independent, deterministic) sum / sum of squares per (n, group)
   unsigned long long gsum[2 * kMaxStatGroups];
@@ -57,6 +58,44 @@ __device__ __forceinline__ void spin_until_set(const unsigned int* flag) {
     if (++spins > (1u << 24)) __trap();   // protocol bug: fail instead of hanging the device
   }
 }
+
+// Profiling aid: per-CTA %globaltimer stamps of the quantiser kernels, kept in registers of
+// thread 0 and flushed at kernel end into ws->qdbg[(launch_seq * kQdbgMaxCtas + cta) * 8 + slot]
+// (slot 0 entry, 1 dependency wait passed, 2 values loaded / min-max taken, 3 barrier passed,
+// 4 done). launch_seq = ws->qdbg_seq, read after the dependency wait and bumped by CTA 0 at its
+// end, so back-to-back launches (PDL, CUDA graphs) land in consecutive regions without any host
+// involvement. ws->qdbg == NULL (the default) disables everything but one predicated load.
+constexpr int kQdbgMaxCtas = 1024;
+struct QDbg {
+  unsigned long long t[5];
+  unsigned long long* buf;
+  unsigned int seq;
+  __device__ __forceinline__ void begin(const DynWs* ws) {
+    buf = nullptr;
+    if (threadIdx.x == 0) {
+      buf = *reinterpret_cast<unsigned long long* const volatile*>(&ws->qdbg);
+      stamp(0);
+    }
+  }
+  __device__ __forceinline__ void stamp(int i) {
+    if (threadIdx.x == 0 && buf != nullptr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t[i]));
+  }
+  __device__ __forceinline__ void waited(const DynWs* ws) {   // call right after pdl_wait()
+    if (threadIdx.x == 0 && buf != nullptr) {
+      seq = *reinterpret_cast<const volatile unsigned int*>(&ws->qdbg_seq);
+      stamp(1);
+    }
+  }
+  __device__ __forceinline__ void end(DynWs* ws) {
+    if (threadIdx.x == 0 && buf != nullptr) {
+      stamp(4);
+      unsigned long long* dst = buf + (static_cast<size_t>(seq) * kQdbgMaxCtas + blockIdx.x) * 8;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) dst[i] = t[i];
+      if (blockIdx.x == 0) ws->qdbg_seq = seq + 1;
+    }
+  }
+};
 
 // qdiff asymmetric 8-bit min-max parameters (base_quantizer.py:155-190), fp32:
 //   delta = max((x_max - x_min) / 255, 1e-6),  z = rint(-x_min / delta)
@@ -204,13 +243,13 @@ __device__ __forceinline__ void cluster_minmax_params(float mn, float mx,
 
 // rint(RN(x / delta)) — the reference rounds the correctly rounded fp32 QUOTIENT
 // (torch.round(x / delta), base_quantizer.py:186) — without an IEEE division per element:
-// t = x * (1/delta) is within 2 ulp (< 1e-4 for |t| <= 256) of the quotient, so rint(t) is the
-// answer unless t sits within 1e-3 of a rounding boundary; only those elements (~0.2 %) take the
-// exact division. Bit-identical to the division everywhere (tests/test_gpu_ops.py).
+// t = x * (1/delta) is within 3 ulp (< 5e-5 for |t| <= 256: |x| <= 255 delta by construction) of
+// the quotient, so rint(t) is the answer unless t sits within 1e-4 of a rounding boundary; only
+// those elements (~0.02 %) take the exact division. Bit-identical to the division everywhere (tests/test_gpu_ops.py).
 __device__ __forceinline__ float qdiff_round_quot(float x, float delta, float inv_delta) {
   const float t = __fmul_rn(x, inv_delta);
   float r = rintf(t);
-  if (fabsf(__fsub_rn(t, r)) > 0.499f) r = rintf(__fdiv_rn(x, delta));
+  if (fabsf(__fsub_rn(t, r)) > 0.4999f) r = rintf(__fdiv_rn(x, delta));
   return r;
 }
 
@@ -286,11 +325,39 @@ inline int max_cluster_ctas(K kern, int threads, int smem) {
   return 0;
 }
 
+// Host-side note "the last min/max producer launched on workspace W wrote N partials", consumed
+// by the quantise pass that follows it on the same stream (separate C-ABI calls, e.g. the GEGLU
+// GEMM and mixdq_quant_i8_premm). One definition shared by all translation units.
+inline int& partial_count_slot(const void* ws) {
+  static const void* keys[32] = {nullptr};
+  static int vals[32] = {0};
+  for (int i = 0; i < 32; ++i) {
+    if (keys[i] == ws) return vals[i];
+    if (keys[i] == nullptr) { keys[i] = ws; return vals[i]; }
+  }
+  return vals[31];
+}
+
+// Experiment hook: MIXDQ_CARVEOUT=<percent> pins the shared-memory carve-out preference of the
+// quantiser kernels (so that the SM's L1/shared split need not change between them and the
+// tcgen05 kernels, which use ~200 KB of shared memory).
+template <typename K>
+inline void apply_carveout_pref(K kern) {
+  static int pct = -2;
+  if (pct == -2) {
+    const char* e = getenv("MIXDQ_CARVEOUT");
+    pct = e ? atoi(e) : -1;
+  }
+  if (pct >= 0) (void)cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 // plain grid launch with a programmatic dependency on the preceding kernel of the stream (the
 // kernel calls griddepcontrol.wait before its first global read)
 template <typename K, typename... Args>
 inline cudaError_t launch_pdl(K kern, int ctas, int threads, int smem, cudaStream_t st,
                               Args... args) {
+  static bool pref = false;          // one instance per kernel signature is enough for the hook
+  if (!pref) { apply_carveout_pref(kern); pref = true; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ctas);
   cfg.blockDim = dim3(threads);

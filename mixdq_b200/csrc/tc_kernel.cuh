@@ -17,8 +17,7 @@
 //   KIND_GEGLU: KIND_GEMM whose weight rows are interleaved 16 value / 16 gate columns
 //               (ff.net.0.proj): the epilogue rounds the linear output to fp16, evaluates
 //               half(h * half(gelu(gate))) like the stock GEGLU module, stores [M][N/2] fp16 and
-//               folds the tensor's min / max into two device words (atomicMax on the bit patterns
-//               of -min >= 0 and max >= 0), so the quantiser that follows is a single pass
+//               one min / max partial per CTA, so the quantiser that follows is a single pass
 //
 // Split-K over a thread-block cluster (p.splits > 1, cluster dims (1,1,splits)).
 //   Measured on B200 (tools/phase_timing.py): with both operands in shared memory one
@@ -88,7 +87,7 @@ struct TcParams {
   __half* D;
   int64_t ldd;
   int32_t* acc_out;       // optional raw accumulator dump [rows][N]
-  unsigned int* mm;       // KIND_GEGLU: {bits(-min), bits(max)} of the fp16 output, atomicMax'ed
+  float2* mm_partial;     // KIND_GEGLU: per-CTA {min(0, min), max(0, max)} of the fp16 output
   int32_t* ws;            // split-K exchange workspace: [CTA][BN/4][128][4] int32 (splits > 1)
   unsigned long long* dbg; // optional phase timestamps (globaltimer ns), 8 slots per CTA
   int dbg_mode;            // profiling only: bit0 = skip MMA issue, bit1 = skip TMA loads
@@ -415,10 +414,13 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
     epi_bar_sync();                        // named barrier among the 256 epilogue threads
+  }
+  // every epilogue path waits for the accumulators itself (after prefetching what it can)
+  auto wait_accumulators = [&]() {
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (threadIdx.x == 64) MIXDQ_DBG(6);  // accumulators ready
-  }
+  };
 
   __syncwarp();
   const bool has_bias = p.bias != nullptr;
@@ -482,6 +484,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int i = 0; i < 2; ++i)
         ro[i] = row_info<KIND>(p, quarter * 32 + i * 16 + (lane >> 1), m0, tn0, tp0, tq0);
       float mn = 0.f, mx = 0.f;
+      wait_accumulators();
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; ++c) {
         uint32_t v[32];
@@ -520,7 +523,8 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
       tc_fence_before();
-      // tensor-wide min / max: warp -> CTA (shared memory past the staging tile) -> one atomic pair
+      // min / max of this CTA's outputs: warp -> CTA (shared memory past the staging tile) -> one
+      // partial per CTA, reduced by the quantise pass that follows (quant2.cu)
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
@@ -532,8 +536,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (threadIdx.x == 64) {
 #pragma unroll
         for (int w = 0; w < 8; ++w) { mn = fminf(mn, s_mm[2 * w]); mx = fmaxf(mx, s_mm[2 * w + 1]); }
-        atomicMax(reinterpret_cast<int*>(p.mm), __float_as_int(0.0f - mn));
-        atomicMax(reinterpret_cast<int*>(p.mm) + 1, __float_as_int(mx));
+        p.mm_partial[blockIdx.y * gridDim.x + blockIdx.x] = make_float2(mn, mx);
       }
     }
     }
@@ -552,9 +555,32 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int c_lo = (NCH >= 2) ? ehalf * (NCH / 2) : 0;
       const int c_hi = (NCH >= 2) ? c_lo + NCH / 2 : (ehalf == 0 ? 1 : 0);
       RowInfo ro[LPR];                             // rows this lane copies out
+      int64_t ca_off[LPR];                         // chan_add row offset of those rows
 #pragma unroll
-      for (int i = 0; i < LPR; ++i)
+      for (int i = 0; i < LPR; ++i) {
         ro[i] = row_info<KIND>(p, quarter * 32 + i * RPI + lane / LPR, m0, tn0, tp0, tq0);
+        ca_off[i] = (p.chan_add != nullptr && ro[i].ok) ? (ro[i].out_row / p.rows_per_img) * p.ldca : 0;
+      }
+      // operands of the fused elementwise tail, fetched one chunk ahead: the first chunk's while
+      // the MMAs are still running, chunk c+1's while chunk c is dequantised (they come from L2,
+      // ~1 us away right after a kernel boundary)
+      const bool has_tail = (p.chan_add != nullptr) || (p.residual != nullptr);
+      uint4 t_ca[LPR], t_rs[LPR];
+      auto fetch_tail = [&](int c) {
+        const int ccol = n_tile0 + c * CH + (lane % LPR) * 8;
+        if (c < c_hi && ccol + 8 <= p.N) {
+#pragma unroll
+          for (int i = 0; i < LPR; ++i) {
+            if (!ro[i].ok) continue;
+            if (p.chan_add != nullptr)
+              t_ca[i] = __ldcg(reinterpret_cast<const uint4*>(p.chan_add + ca_off[i] + ccol));
+            if (p.residual != nullptr)
+              t_rs[i] = __ldcg(reinterpret_cast<const uint4*>(p.residual + ro[i].out_row * p.ldr + ccol));
+          }
+        }
+      };
+      if (has_tail) fetch_tail(c_lo);
+      wait_accumulators();
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; ++c) {
         uint32_t v[CH], v1[CH];
@@ -585,14 +611,24 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         __syncwarp();
         const int ccol = c * CH + (lane % LPR) * 8;
-        if (n_tile0 + ccol + 8 <= p.N) {
+        uint4 o[LPR];
+        const bool col_ok = n_tile0 + ccol + 8 <= p.N;
+        if (col_ok) {
 #pragma unroll
           for (int i = 0; i < LPR; ++i) {
             if (!ro[i].ok) continue;
             const int r = quarter * 32 + i * RPI + lane / LPR;
-            *reinterpret_cast<uint4*>(p.D + ro[i].out_row * p.ldd + n_tile0 + ccol) = epilogue_tail(
-                p, *reinterpret_cast<const uint4*>(stage_out + r * L::OUT_PITCH + ccol * 2),
-                ro[i].out_row, n_tile0 + ccol);
+            o[i] = *reinterpret_cast<const uint4*>(stage_out + r * L::OUT_PITCH + ccol * 2);
+            if (p.chan_add != nullptr) o[i] = add_half8(o[i], t_ca[i]);
+            if (p.residual != nullptr) o[i] = add_half8(o[i], t_rs[i]);
+          }
+        }
+        if (has_tail) fetch_tail(c + 1);           // next chunk's operands (registers are free now)
+        if (col_ok) {
+#pragma unroll
+          for (int i = 0; i < LPR; ++i) {
+            if (!ro[i].ok) continue;
+            *reinterpret_cast<uint4*>(p.D + ro[i].out_row * p.ldd + n_tile0 + ccol) = o[i];
           }
         }
       }
@@ -611,6 +647,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       constexpr int NCH = BN / CH;
       const int c_lo = (NCH >= 2) ? ehalf * (NCH / 2) : 0;
       const int c_hi = (NCH >= 2) ? c_lo + NCH / 2 : (ehalf == 0 ? 1 : 0);
+      wait_accumulators();
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; ++c) {
         uint32_t v[CH];

@@ -256,6 +256,12 @@ _dyn_cache = []          # [(tensor, version, (q, scale, zp))], most recent last
 _DYN_CACHE_SLOTS = 3
 
 
+def _dyn_kernels(numel: int) -> int:
+    """Kernels one dynamic quantisation launches: tiny tensors take the one-cluster kernel, the
+    rest a min/max pass + a quantise pass (csrc/quant2.cu)."""
+    return 1 if numel <= 65536 else 2
+
+
 def clear_dynamic_quant_cache() -> None:
     _dyn_cache.clear()
 
@@ -277,7 +283,8 @@ def quantize_per_tensor_dynamic(input: torch.Tensor) -> Tuple[torch.Tensor, torc
         ws = _dynamic_workspace(x.device)
         _launch("quant_dyn", lib.mixdq_quant_i8_dynamic,
                 (x.data_ptr(), x.numel(), qp.data_ptr(), qp.data_ptr() + 4, out.data_ptr(),
-                 ws.data_ptr()), x, kernels=1, keep=(x, qp, out, ws), algo_bytes=3 * x.numel())
+                 ws.data_ptr()), x, kernels=_dyn_kernels(x.numel()), keep=(x, qp, out, ws),
+                algo_bytes=3 * x.numel())
     res = (out, qp[0], qp[1])
     if DYNAMIC_QUANT_CACHE:
         _dyn_cache.append((input, input._version, res))
@@ -655,8 +662,9 @@ def qconv1x1_split_dynamic_fused(xa_int8, wa_int8, w_scale_a, wsum_a, a_scale_a,
 
 def layernorm_quantize_dynamic(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
                                eps: float, return_y: bool = False):
-    """LayerNorm over the last dim + qdiff dynamic quantisation in one kernel.
-    Returns (q int8 [..., C], scale, zero_point[, y fp16])."""
+    """LayerNorm over the last dim + qdiff dynamic quantisation: a LayerNorm kernel that also
+    publishes min/max, then the single-pass quantiser (the fp16 LayerNorm output lives in a
+    scratch tensor that stays in L2). Returns (q int8 [..., C], scale, zero_point[, y fp16])."""
     _check(x.dtype == torch.float16 and weight.dtype == torch.float16
            and bias.dtype == torch.float16, "layernorm_quantize_dynamic expects fp16 tensors")
     C = x.shape[-1]
@@ -665,7 +673,7 @@ def layernorm_quantize_dynamic(x: torch.Tensor, weight: torch.Tensor, bias: torc
         x2 = x2.contiguous()
     M = x2.shape[0]
     q = torch.empty(x.shape, dtype=torch.int8, device=x.device)
-    y = torch.empty(x.shape, dtype=torch.float16, device=x.device) if return_y else None
+    y = torch.empty(x.shape, dtype=torch.float16, device=x.device)   # scratch of the two-pass form
     qp, sc, zp = _qp_pair(x.device)
     lib = _lib.load()
     with _DeviceGuard(x2):
@@ -674,7 +682,7 @@ def layernorm_quantize_dynamic(x: torch.Tensor, weight: torch.Tensor, bias: torc
                 (x2.data_ptr(), x2.stride(0) if M > 1 else C, M, C, weight.data_ptr(),
                  bias.data_ptr(), float(eps), q.data_ptr(), _ptr(y), qp.data_ptr(),
                  qp.data_ptr() + 4, ws.data_ptr()), x2, keep=(x2, weight, bias, q, y, qp, ws),
-                algo_bytes=3 * M * C)
+                kernels=_dyn_kernels(M * C), algo_bytes=3 * M * C)
     return (q, sc, zp, y) if return_y else (q, sc, zp)
 
 
@@ -751,8 +759,9 @@ def groupnorm_quantize_dynamic(x: torch.Tensor, num_groups: int, weight: torch.T
         x = x.contiguous(memory_format=torch.channels_last)
     q = torch.empty((n, c, h, w), dtype=torch.int8, device=x.device,
                     memory_format=torch.channels_last)
+    # scratch of the three-kernel form (statistics, apply + min/max, quantise); stays in L2
     y = torch.empty((n, c, h, w), dtype=torch.float16, device=x.device,
-                    memory_format=torch.channels_last) if return_y else None
+                    memory_format=torch.channels_last)
     qp, sc, zp = _qp_pair(x.device)
     lib = _lib.load()
     with _DeviceGuard(x):
@@ -761,7 +770,7 @@ def groupnorm_quantize_dynamic(x: torch.Tensor, num_groups: int, weight: torch.T
                 (x.data_ptr(), c, n, h * w, c, num_groups, weight.data_ptr(), bias.data_ptr(),
                  float(eps), 1 if silu else 0, q.data_ptr(), _ptr(y), qp.data_ptr(),
                  qp.data_ptr() + 4, ws.data_ptr()), x, keep=(x, weight, bias, q, y, qp, ws),
-                algo_bytes=3 * x.numel())
+                kernels=3, algo_bytes=3 * x.numel())
     return (q, sc, zp, y) if return_y else (q, sc, zp)
 
 
@@ -778,7 +787,7 @@ def quantize_rows_dynamic(x2: torch.Tensor):
         _launch("quant_dyn", lib.mixdq_quant_i8_dynamic_rows,
                 (x2.data_ptr(), x2.stride(0) if M > 1 else cols, M, cols, q.data_ptr(),
                  qp.data_ptr(), qp.data_ptr() + 4, ws.data_ptr()), x2, keep=(x2, q, qp, ws),
-                algo_bytes=3 * M * cols)
+                kernels=_dyn_kernels(M * cols), algo_bytes=3 * M * cols)
     return q, sc, zp
 
 

@@ -145,6 +145,36 @@ def test_cluster_and_grid_quantisers_agree(ops, dev):
             assert torch.equal(a_, b_)
 
 
+def test_two_pass_and_single_kernel_quantisers_agree(ops, dev):
+    """min/max pass + quantise pass (csrc/quant2.cu) == the single-kernel quantisers with a grid
+    barrier, bit for bit, for plain / row-pitched / LayerNorm / GroupNorm inputs."""
+    from mixdq_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(1024, 640, generator=g) * 2 + 0.3).half().to(dev)
+    w = (1 + 0.2 * torch.randn(640, generator=g)).half().to(dev)
+    b = (0.1 * torch.randn(640, generator=g)).half().to(dev)
+    wide = (torch.randn(1024, 1920, generator=g) * 3).half().to(dev)
+    img = (torch.randn(2, 640, 32, 32, generator=g) * 1.5).half().to(dev).contiguous(
+        memory_format=torch.channels_last)
+    outs = []
+    try:
+        for mode in (0, 1, 0, 1):
+            lib.mixdq_debug_set_two_pass(mode)
+            ops.clear_dynamic_quant_cache()
+            o = list(ops.layernorm_quantize_dynamic(x, w, b, 1e-5, return_y=True))
+            o += list(ops.quantize_per_tensor_dynamic(x.clone()))
+            o += list(ops.quantize_rows_dynamic(wide[:, 640:]))
+            o += list(ops.groupnorm_quantize_dynamic(img, 32, w, b, 1e-5, True, return_y=True))
+            o += list(ops.groupnorm_quantize_dynamic(img, 32, w, b, 1e-6, False))
+            outs.append([t.clone() for t in o])
+    finally:
+        lib.mixdq_debug_set_two_pass(1)
+    for o in outs[1:]:
+        for a_, b_ in zip(o, outs[0]):
+            assert torch.equal(a_, b_)
+
+
 @pytest.mark.parametrize("N,C,H,W,G,silu", [
     (1, 320, 64, 64, 32, True), (1, 640, 32, 32, 32, True), (1, 1280, 16, 16, 32, True),
     (1, 2560, 16, 16, 32, True), (1, 960, 64, 64, 32, True), (1, 1920, 32, 32, 32, True),

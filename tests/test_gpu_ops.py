@@ -145,7 +145,7 @@ def test_quant_dynamic_every_fp16_value(ops, dev, lim):
     resulting delta): the kernels' reciprocal-multiply + exact fix-up equals the true division."""
     allh = torch.arange(0, 65536, dtype=torch.int32).to(torch.int16).view(torch.float16)
     x = allh[torch.isfinite(allh) & (allh >= -lim) & (allh <= 0.71 * lim)].contiguous()
-    x = torch.cat([x, x.flip(0)])[: (x.numel() * 2) // 8 * 8]
+    x = torch.cat([x, x.flip(0)])[: (x.numel() * 2) // 64 * 64]
     q, s, z = ops.quantize_per_tensor_dynamic(x.to(dev))
     qr, sr, zr = O.quantize_dynamic_kernel(x)
     assert s.item() == sr.item() and z.item() == zr.item()
