@@ -124,9 +124,10 @@ static int launch_tc(dim3 grid, const CUtensorMap& a, const CUtensorMap& w, cons
 // Tile-shape heuristic: a cost model fitted to in-kernel %globaltimer stamps on B200
 // (tools/phase_timing.py, tools/sweep_shapes.py; numbers in ns):
 //   * ~1400 from the end of the preceding kernel to the first stage landing (PDL wait + TMA);
-//   * 340 per 128-byte k-block for BN <= 128 (4 tcgen05.mma at ~97 cycles issue floor + barrier
-//     round trip), 440 for BN = 256 (160 cycles per MMA) — independent of the tile width, so a
-//     CTA's mainloop is proportional to its K range only;
+//   * per 128-byte k-block: 165 for BN <= 64, 195 for BN = 128 (two k-blocks = 8 tcgen05.mma per
+//     barrier round: ~52 cycles per MMA — the issuing thread is blocked for each MMA's duration —
+//     plus ~230 cycles of wait/fence/commit per stage), 420 for BN = 256 (one k-block per stage,
+//     ~130-160 cycles per MMA); it was 340 with one k-block per stage;
 //   * epilogue, no split: ~300 + 6.5 per tile column (dequant and ~26 B/clk/SM of stores overlap);
 //   * epilogue, split-K: 8.6 per column to write the INT32 partial tile, ~900 for the cluster
 //     barrier, 350 + 0.4 per owned element to sum the partials, 300 to store;
@@ -195,7 +196,7 @@ static void pick_tile(int m_tiles, int N, int total_kb, bool allow_split, int* b
       const int cap = (s <= 2) ? kNumSm : (s == 4 ? 132 : 120);
       const long waves = (ctas + cap - 1) / cap;
       const int kb_per = (total_kb + s - 1) / s;
-      const double main = kb_per * (bn == 256 ? 440.0 : 340.0);
+      const double main = kb_per * (bn == 256 ? 420.0 : bn == 128 ? 195.0 : 165.0);
       const double epi = (s == 1) ? 300.0 + 6.5 * bn
                                   : 8.6 * bn + 900.0 + 350.0 + 0.4 * (128.0 / s) * bn + 300.0;
       const double t = waves * (1400.0 + main + epi);
@@ -216,10 +217,10 @@ static int dispatch_tc(int bn, dim3 grid, const CUtensorMap& a, const CUtensorMa
                        cudaStream_t st) {
   switch (bn) {
     case 256: return launch_tc<256, 4, KIND>(grid, a, w, a1, w1, p, st);
-    case 128: return launch_tc<128, 6, KIND>(grid, a, w, a1, w1, p, st);
-    case 64: return launch_tc<64, 8, KIND>(grid, a, w, a1, w1, p, st);
-    case 32: return launch_tc<32, 8, KIND>(grid, a, w, a1, w1, p, st);
-    case 16: return launch_tc<16, 8, KIND>(grid, a, w, a1, w1, p, st);
+    case 128: return launch_tc<128, 3, KIND>(grid, a, w, a1, w1, p, st);   // 2 k-blocks per stage
+    case 64: return launch_tc<64, 4, KIND>(grid, a, w, a1, w1, p, st);
+    case 32: return launch_tc<32, 4, KIND>(grid, a, w, a1, w1, p, st);
+    case 16: return launch_tc<16, 4, KIND>(grid, a, w, a1, w1, p, st);
     default: return MIXDQ_ERR_UNSUPPORTED;
   }
 }
@@ -311,9 +312,25 @@ extern "C" int mixdq_gemm_w8a8_geglu_f16_dyn(const int8_t* A, int64_t lda, const
   if (g_force_simt) return MIXDQ_ERR_UNSUPPORTED;
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
-  int bn, splits;
-  pick_tile(m_tiles, N2, num_kb, false, &bn, &splits);
-  if (bn < 32) bn = 32;
+  // tile width: same wave / mainloop model as pick_tile, with the GEGLU epilogue's ALU cost
+  // (~14 ns per tile column: dequant + erff on 8 warps) and a 160-wide tile that puts the
+  // batch-1 projection (2 x 64 tiles) on one wave of 128 CTAs
+  int bn = 32;
+  {
+    if (g_force_bn < 0) { int d0, d1; pick_tile(1, 32, 1, false, &d0, &d1); }   // reads the env
+    const int cands[5] = {256, 160, 128, 64, 32};
+    const double main_ns[5] = {440.0, 280.0, 195.0, 165.0, 165.0};
+    double best = 1e30;
+    for (int i = 0; i < 5; ++i) {
+      const int c = cands[i];
+      if ((valid_bn(g_force_bn) || g_force_bn == 160) && c != g_force_bn) continue;
+      if (c > 32 && c / 2 >= N2) continue;
+      const long tiles = static_cast<long>(m_tiles) * ((N2 + c - 1) / c);
+      const long waves = (tiles + 147) / 148;
+      const double t = waves * (1400.0 + num_kb * main_ns[i] + 300.0 + 14.0 * c);
+      if (t < best) { best = t; bn = c; }
+    }
+  }
   CUtensorMap tmA, tmW;
   if (!make_tmap_2d(&tmA, A, K, M, lda, BLOCK_M)) return MIXDQ_ERR_CUDA;
   if (!make_tmap_2d(&tmW, W_il, K, N2, K, bn)) return MIXDQ_ERR_CUDA;
@@ -333,9 +350,10 @@ extern "C" int mixdq_gemm_w8a8_geglu_f16_dyn(const int8_t* A, int64_t lda, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (bn) {
     case 256: return launch_tc<256, 4, KIND_GEGLU>(grid, tmA, tmW, tmA, tmW, p, st);
-    case 128: return launch_tc<128, 6, KIND_GEGLU>(grid, tmA, tmW, tmA, tmW, p, st);
-    case 64: return launch_tc<64, 8, KIND_GEGLU>(grid, tmA, tmW, tmA, tmW, p, st);
-    default: return launch_tc<32, 8, KIND_GEGLU>(grid, tmA, tmW, tmA, tmW, p, st);
+    case 160: return launch_tc<160, 5, KIND_GEGLU>(grid, tmA, tmW, tmA, tmW, p, st);
+    case 128: return launch_tc<128, 3, KIND_GEGLU>(grid, tmA, tmW, tmA, tmW, p, st);
+    case 64: return launch_tc<64, 4, KIND_GEGLU>(grid, tmA, tmW, tmA, tmW, p, st);
+    default: return launch_tc<32, 4, KIND_GEGLU>(grid, tmA, tmW, tmA, tmW, p, st);
   }
 }
 

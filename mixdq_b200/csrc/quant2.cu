@@ -50,15 +50,16 @@ __device__ __forceinline__ uint2 quant8_compact(const int4& raw, float delta, fl
     near |= fabsf(__fsub_rn(t, r[i])) > 0.4999f;   // |t - x/delta| < 5e-5 (see quant_ws.cuh)
   }
   if (near) {
+    // redo all 8 exactly; the arrays are ROTATED so that the loop body only touches element 0
+    // (static register indexing, one call site)
 #pragma unroll 1
     for (int i = 0; i < 8; ++i) {
-      // select element i without dynamic register indexing
-      float xi = x[0];
+      const float e = exact_round_quot(x[0], delta);
+      const float x0 = x[0];
 #pragma unroll
-      for (int j = 1; j < 8; ++j) xi = (i == j) ? x[j] : xi;
-      const float e = exact_round_quot(xi, delta);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = (i == j) ? e : r[j];
+      for (int j = 0; j < 7; ++j) { x[j] = x[j + 1]; r[j] = r[j + 1]; }
+      x[7] = x0;
+      r[7] = e;
     }
   }
   uint32_t w[2] = {0u, 0u};
@@ -162,6 +163,7 @@ quant_rows_premm_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int 
     v = __ldcg(reinterpret_cast<const int4*>(x + static_cast<int64_t>(r) * ldx) + (it - r * nchunks));
   }
   float mn = 0.0f, mx = 0.0f;
+#pragma unroll 1
   for (int i = threadIdx.x; i < nparts; i += kQ2Threads) {
     const float2 p = __ldcg(&ws->partial[i]);
     mn = fminf(mn, p.x);
@@ -181,17 +183,21 @@ quant_rows_premm_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int 
   const float inv = __frcp_rn(delta);
   if (blockIdx.x == 0) {
     if (threadIdx.x == 0) { *scale_out = delta; *zp_out = z - 128.0f; }
+#pragma unroll 1
     for (int i = threadIdx.x; i < zero_n; i += kQ2Threads) zero_words[i] = 0ull;
   }
   dbg.stamp(2);
   uint2* qv = reinterpret_cast<uint2*>(q);
-  if (it < items) qv[it] = quant8_compact(v, delta, inv, z);
 #pragma unroll 1
-  for (it += stride; it < items; it += stride) {
-    const unsigned int r = it / nchunks;
-    const unsigned int c = it - r * nchunks;
-    v = __ldcg(reinterpret_cast<const int4*>(x + static_cast<int64_t>(r) * ldx) + c);
-    qv[it] = quant8_compact(v, delta, inv, z);
+  while (it < items) {                     // one inlined copy of the quantiser
+    const uint2 codes = quant8_compact(v, delta, inv, z);
+    const unsigned int nxt = it + stride;
+    if (nxt < items) {
+      const unsigned int r = nxt / nchunks;
+      v = __ldcg(reinterpret_cast<const int4*>(x + static_cast<int64_t>(r) * ldx) + (nxt - r * nchunks));
+    }
+    qv[it] = codes;
+    it = nxt;
   }
   dbg.stamp(3);
   dbg.end(ws);

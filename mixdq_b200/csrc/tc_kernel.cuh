@@ -51,7 +51,8 @@ enum { KIND_GEMM = 0, KIND_CONV = 1, KIND_SPLIT = 2, KIND_GEGLU = 3 };
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 128;  // int8 elements = bytes = one 128B swizzle row
 constexpr int UMMA_K = 32;
-constexpr int TC_THREADS = 320;      // warp 0 TMA, warp 1 MMA/TMEM, warps 2..9 epilogue
+constexpr int TC_THREADS = 352;      // warp 0 TMA, warp 1 MMA/TMEM, warps 2..9 epilogue,
+                                     // warp 10 second MMA issuer (TcDual kernels only)
 constexpr int EPI_THREADS = 256;
 
 struct TcParams {
@@ -106,10 +107,28 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
           gtime_ns();                                                                     \
   } while (0)
 
+// k-blocks (128 bytes of K) per ring stage. The thread that issues tcgen05.mma is blocked for the
+// duration of each MMA (measured: issue rate == completion rate), so the per-stage bookkeeping
+// (mbarrier try_wait, fence, elect, commit: ~230 cycles) is NOT overlapped with the tensor pipe;
+// two k-blocks = 8 MMAs per barrier round halve that overhead (442 -> ~325 cycles per k-block for
+// BN <= 128). BN = 256 keeps one k-block per stage: its stages are 48 KB already.
+template <int BN>
+struct TcKsub { static constexpr int value = (BN <= 128) ? 2 : 1; };
+
+// Two MMA-issuing warps, alternating ring stages, each with its OWN TMEM accumulator (summed
+// exactly in the epilogue: int32 addition is associative). The issuing thread is blocked while its
+// MMA executes, so one warp's barrier bookkeeping overlaps the other warp's MMAs and the tensor
+// pipe stays busy. Narrow tiles only (2 x BN TMEM columns; the wide tiles are pipe-bound anyway).
+template <int BN, int KIND>
+struct TcDual { static constexpr bool value = (BN <= 64) && (KIND != 2 /*KIND_SPLIT*/); };
+
 template <int BN, int STAGES, int KIND>
 struct TcSmem {
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K;
-  static constexpr int W_BYTES = BN * BLOCK_K;
+  static constexpr int KSUB = TcKsub<BN>::value;
+  static constexpr int A_SUB = BLOCK_M * BLOCK_K;
+  static constexpr int W_SUB = BN * BLOCK_K;
+  static constexpr int A_BYTES = KSUB * A_SUB;
+  static constexpr int W_BYTES = KSUB * W_SUB;
   static constexpr int TAB_PITCH = BN + 4;   // float4-aligned rows, classes land in different banks
   static constexpr int TAB_FLOATS = (KIND == KIND_CONV) ? 16 * TAB_PITCH : 0;
   static constexpr int PARAM_FLOATS = (KIND == KIND_SPLIT ? 5 : 3) * BN + TAB_FLOATS;
@@ -191,7 +210,9 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
              const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
              const TcParams p) {
   using L = TcSmem<BN, STAGES, KIND>;
-  constexpr int TMEM_COLS_USED = (KIND == KIND_SPLIT ? 2 : 1) * BN;
+  constexpr bool DUAL = TcDual<BN, KIND>::value;
+  static_assert(!DUAL || (STAGES % 2 == 0), "dual issue alternates stages: even ring depth");
+  constexpr int TMEM_COLS_USED = ((KIND == KIND_SPLIT || DUAL) ? 2 : 1) * BN;
   constexpr uint32_t TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64
                                : TMEM_COLS_USED <= 128 ? 128 : TMEM_COLS_USED <= 256 ? 256 : 512;
   constexpr uint32_t IDESC = umma_idesc_i8(BLOCK_M, BN);
@@ -240,7 +261,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmW);
     if (KIND == KIND_SPLIT) { tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmW1); }
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(tmem_full_bar, 1);
+    mbar_init(tmem_full_bar, DUAL ? 2 : 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -259,9 +280,9 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // (elect.sync): inside `if (lane == 0)` the compiler cannot prove uniformity and wraps every
     // uniform-datapath instruction in a waterfall loop.
     {
-      const uint32_t a_bytes = (KIND == KIND_CONV) ? p.a_tx_bytes : static_cast<uint32_t>(L::A_BYTES);
-      auto load_w = [&](int kb, int stage) {
-        uint8_t* w_dst = sW + stage * L::W_BYTES;
+      const uint32_t a_bytes = (KIND == KIND_CONV) ? p.a_tx_bytes : static_cast<uint32_t>(L::A_SUB);
+      auto load_w = [&](int kb, int stage, int u) {
+        uint8_t* w_dst = sW + stage * L::W_BYTES + u * L::W_SUB;
         if (KIND == KIND_CONV) {
           const int tap = kb / p.kb_per_tap;
           const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
@@ -272,8 +293,8 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tma_load_2d(w_dst, &tmW, &full_bar[stage], kb * BLOCK_K, n_tile0);
         }
       };
-      auto load_a = [&](int kb, int stage) {
-        uint8_t* a_dst = sA + stage * L::A_BYTES;
+      auto load_a = [&](int kb, int stage, int u) {
+        uint8_t* a_dst = sA + stage * L::A_BYTES + u * L::A_SUB;
         if (KIND == KIND_CONV) {
           const int tap = kb / p.kb_per_tap;
           const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
@@ -287,13 +308,18 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       };
       const bool skip = (p.dbg_mode & 2) != 0;
-      // prologue: weights of the first ring-full of k-blocks do not depend on the preceding
+      // ring stage si holds k-blocks kb_begin + si*KSUB .. (+KSUB-1); the last one may be short
+      const int nkb = kb_end - kb_begin;
+      const int nst = (nkb + L::KSUB - 1) / L::KSUB;
+      auto nsub_of = [&](int si) { const int rem = nkb - si * L::KSUB; return rem < L::KSUB ? rem : L::KSUB; };
+      // prologue: weights of the first ring-full of stages do not depend on the preceding
       // kernel -> issue them before the programmatic-dependency wait
-      const int npre = (kb_end - kb_begin) < STAGES ? (kb_end - kb_begin) : STAGES;
+      const int npre = nst < STAGES ? nst : STAGES;
       if (!skip && elect_one()) {
         for (int i = 0; i < npre; ++i) {
-          mbar_expect_tx(&full_bar[i], a_bytes + L::W_BYTES);
-          load_w(kb_begin + i, i);
+          const int ns = nsub_of(i);
+          mbar_expect_tx(&full_bar[i], ns * (a_bytes + L::W_SUB));
+          for (int u = 0; u < ns; ++u) load_w(kb_begin + i * L::KSUB + u, i, u);
         }
       }
       __syncwarp();
@@ -301,22 +327,26 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       pdl_wait();                          // activations / quantisation scalars are ready
       if (elect_one()) {
         for (int i = 0; i < npre; ++i) {
-          if (skip) mbar_arrive(&full_bar[i]);
-          else load_a(kb_begin + i, i);
+          if (skip) { mbar_arrive(&full_bar[i]); continue; }
+          const int ns = nsub_of(i);
+          for (int u = 0; u < ns; ++u) load_a(kb_begin + i * L::KSUB + u, i, u);
         }
       }
       __syncwarp();
       int stage = (npre == STAGES) ? 0 : npre;
       uint32_t phase = (npre == STAGES) ? 1 : 0;
-      for (int kb = kb_begin + npre; kb < kb_end; ++kb) {
+      for (int si = npre; si < nst; ++si) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           if (skip) {
             mbar_arrive(&full_bar[stage]);
           } else {
-            mbar_expect_tx(&full_bar[stage], a_bytes + L::W_BYTES);
-            load_w(kb, stage);
-            load_a(kb, stage);
+            const int ns = nsub_of(si);
+            mbar_expect_tx(&full_bar[stage], ns * (a_bytes + L::W_SUB));
+            for (int u = 0; u < ns; ++u) {
+              load_w(kb_begin + si * L::KSUB + u, stage, u);
+              load_a(kb_begin + si * L::KSUB + u, stage, u);
+            }
           }
         }
         __syncwarp();
@@ -324,42 +354,57 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       if (lane == 0) MIXDQ_DBG(3);         // last TMA issued
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp loops, one elected lane issues) ===========
-    {
-      int stage = 0; uint32_t phase = 0;
+  } else if (warp == 1 || warp == 10) {
+    // ===================== MMA issuer(s) (whole warp loops, one elected lane issues) =========
+    // warp 1 alone, or (DUAL) warp 1 on even ring stages + warp 10 on odd ones, each into its own
+    // accumulator
+    const int which = (warp == 10) ? 1 : 0;
+    if (which == 0 || DUAL) {
       // descriptor of stage 0 / k-slice 0; stages and k-slices advance the 16-byte-unit start
       // address field (the low word) by constants
       const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
       const uint64_t w_desc0 = umma_desc_sw128(smem_u32(sW));
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
+      const int nkb = kb_end - kb_begin;
+      const int nst = (nkb + L::KSUB - 1) / L::KSUB;
+      constexpr int STEP = DUAL ? 2 : 1;
+      bool first = true;
+      for (int si = which; si < nst; si += STEP) {
+        const int stage = si % STAGES;
+        const uint32_t phase = static_cast<uint32_t>(si / STAGES) & 1u;
         mbar_wait(&full_bar[stage], phase);
-        if (kb == kb_begin && lane == 0) MIXDQ_DBG(4);  // first stage landed
+        if (si == 0 && lane == 0) MIXDQ_DBG(4);  // first stage landed
         tc_fence_after();
-        uint32_t d_tmem = tmem_base;
-        int kb_in_phase = kb - kb_begin;
-        if (KIND == KIND_SPLIT && kb >= p.num_kb) { d_tmem += BN; kb_in_phase = kb - p.num_kb; }
         if (elect_one()) {
           if (p.dbg_mode & 1) {
             mbar_arrive(&empty_bar[stage]);
           } else {
-            const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(stage * (L::A_BYTES >> 4));
-            const uint64_t w_desc = w_desc0 + static_cast<uint64_t>(stage * (L::W_BYTES >> 4));
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              umma_i8(d_tmem, a_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)),
-                      w_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)), IDESC,
-                      (kb_in_phase | k) != 0 ? 1u : 0u);
+            for (int u = 0; u < L::KSUB; ++u) {
+              const int kb = kb_begin + si * L::KSUB + u;
+              if (kb < kb_end) {
+                uint32_t d_tmem = tmem_base + (DUAL ? which * BN : 0);
+                int kb_in_phase = kb - kb_begin;
+                if (KIND == KIND_SPLIT && kb >= p.num_kb) { d_tmem += BN; kb_in_phase = kb - p.num_kb; }
+                const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(stage * (L::A_BYTES >> 4) + u * (L::A_SUB >> 4));
+                const uint64_t w_desc = w_desc0 + static_cast<uint64_t>(stage * (L::W_BYTES >> 4) + u * (L::W_SUB >> 4));
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                  const bool overwrite = DUAL ? (first && u == 0 && k == 0) : ((kb_in_phase | k) == 0);
+                  umma_i8(d_tmem, a_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)),
+                          w_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)), IDESC,
+                          overwrite ? 0u : 1u);
+                }
+              }
             }
             umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           }
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        first = false;
       }
-      if (elect_one()) umma_commit(tmem_full_bar);   // accumulators complete
+      if (elect_one()) umma_commit(tmem_full_bar);   // this issuer's accumulator is complete
       __syncwarp();
-      if (lane == 0) MIXDQ_DBG(5);         // last MMA issued
+      if (which == 0 && lane == 0) MIXDQ_DBG(5);     // last MMA issued
     }
   } else {
     // ============ epilogue warps 2..9: stage the per-column operands, wait for the MMAs ========
@@ -423,6 +468,9 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   };
 
   __syncwarp();
+  const bool is_epi = warp >= 2 && warp < 10;
+  // second accumulator in use? (DUAL kernels whose K range spans more than one ring stage)
+  const bool dual_used = DUAL && ((kb_end - kb_begin + L::KSUB - 1) / L::KSUB) > 1;
   const bool has_bias = p.bias != nullptr;
   const int quarter = warp & 3;          // TMEM lane quarter this warp may access
   const int ehalf = (warp - 2) >> 2;     // which half of the tile's columns this epilogue warp takes
@@ -472,13 +520,13 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   int row_base = 0;
   if (KIND == KIND_GEGLU) {
     if constexpr (BN >= 32) {
-    if (warp >= 2) {
+    if (is_epi) {
       // ---- 32 accumulator columns = 16 value + 16 gate columns of the same 16 outputs ----
       const int row = quarter * 32 + lane;
       const RowInfo ri = row_info<KIND>(p, row, m0, tn0, tp0, tq0);
-      constexpr int NCH = BN / 32;
-      const int c_lo = (NCH >= 2) ? ehalf * (NCH / 2) : 0;
-      const int c_hi = (NCH >= 2) ? c_lo + NCH / 2 : (ehalf == 0 ? 1 : 0);
+      constexpr int NCH = BN / 32;                 // may be odd (BN = 160): 3 + 2 chunks
+      const int c_lo = ehalf ? (NCH + 1) / 2 : 0;
+      const int c_hi = ehalf ? NCH : (NCH + 1) / 2;
       RowInfo ro[2];                               // rows this lane copies out (2 lanes per row)
 #pragma unroll
       for (int i = 0; i < 2; ++i)
@@ -490,7 +538,15 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t v[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32;
         tmem_ld_32x32(taddr, reinterpret_cast<uint32_t(&)[32]>(v));
-        tmem_ld_wait();
+        if (DUAL && dual_used) {
+          uint32_t v2[32];
+          tmem_ld_32x32(taddr + BN, reinterpret_cast<uint32_t(&)[32]>(v2));
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += v2[j];
+        } else {
+          tmem_ld_wait();
+        }
         const bool cols_ok = n_tile0 + c * 32 + 32 <= p.N;
         if (ri.ok && cols_ok) {
           __align__(16) __half h[32];
@@ -541,7 +597,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     }
   } else if (splits == 1) {
-    if (warp >= 2) {
+    if (is_epi) {
       // ---- TMEM (lane == row) -> dequant -> fp16 -> staging tile -> global, chunk by chunk.
       //      Each warp owns 32 rows x its column half and copies a chunk out (4 lanes x 16 B per
       //      row, 8 rows per instruction) right after staging it, so the stores of chunk c drain
@@ -585,14 +641,19 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int c = c_lo; c < c_hi; ++c) {
         uint32_t v[CH], v1[CH];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * CH;
+        const bool second = (KIND == KIND_SPLIT) || (DUAL && dual_used);
         if (CH == 32) {
           tmem_ld_32x32(taddr, reinterpret_cast<uint32_t(&)[32]>(v));
-          if (KIND == KIND_SPLIT) tmem_ld_32x32(taddr + BN, reinterpret_cast<uint32_t(&)[32]>(v1));
+          if (second) tmem_ld_32x32(taddr + BN, reinterpret_cast<uint32_t(&)[32]>(v1));
         } else {
           tmem_ld_32x16(taddr, reinterpret_cast<uint32_t(&)[16]>(v));
-          if (KIND == KIND_SPLIT) tmem_ld_32x16(taddr + BN, reinterpret_cast<uint32_t(&)[16]>(v1));
+          if (second) tmem_ld_32x16(taddr + BN, reinterpret_cast<uint32_t(&)[16]>(v1));
         }
         tmem_ld_wait();
+        if (DUAL && dual_used) {       // the two issuers' accumulators: exact int32 sum
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] += v1[j];
+        }
         if (ri.ok) {
 #pragma unroll
           for (int j8 = 0; j8 < CH; j8 += 8) {
@@ -640,7 +701,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // workspace slab of one CTA: [BN/4][128 rows][4] int32 -> lanes (rows) write adjacent 16 B
     const int64_t tile_lin = static_cast<int64_t>(blockIdx.y) * gridDim.x + blockIdx.x;
     int32_t* ws_tile = p.ws + tile_lin * splits * (BLOCK_M * BN);
-    if (warp >= 2) {
+    if (is_epi) {
       const int row = quarter * 32 + lane;
       int32_t* my = ws_tile + static_cast<int64_t>(krank) * (BLOCK_M * BN);
       constexpr int CH = (BN >= 32) ? 32 : 16;
@@ -654,7 +715,16 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * CH;
         if (CH == 32) tmem_ld_32x32(taddr, reinterpret_cast<uint32_t(&)[32]>(v));
         else tmem_ld_32x16(taddr, reinterpret_cast<uint32_t(&)[16]>(v));
-        tmem_ld_wait();
+        if (DUAL && dual_used) {
+          uint32_t v2[CH];
+          if (CH == 32) tmem_ld_32x32(taddr + BN, reinterpret_cast<uint32_t(&)[32]>(v2));
+          else tmem_ld_32x16(taddr + BN, reinterpret_cast<uint32_t(&)[16]>(v2));
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] += v2[j];
+        } else {
+          tmem_ld_wait();
+        }
 #pragma unroll
         for (int j = 0; j < CH; j += 4) {
           const int c4 = (c * CH + j) >> 2;
@@ -671,7 +741,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (threadIdx.x == 64) MIXDQ_DBG(9);    // cluster barrier passed
     rows_here = BLOCK_M / splits;
     row_base = krank * rows_here;
-    if (warp >= 2) {
+    if (is_epi) {
       // ---- phase A': owner sums the partials of its rows (coalesced .cg loads, all `splits`
       //      loads of an item in flight together) ----
       const int et = threadIdx.x - 64;
@@ -721,7 +791,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   }
 
-  if (warp >= 2 && splits > 1) {
+  if (is_epi && splits > 1) {
     // ---- phase B: staging tile -> global, consecutive threads along a row (coalesced) ----
     epi_bar_sync();
     if (threadIdx.x == 64) MIXDQ_DBG(11);     // staging complete

@@ -187,8 +187,31 @@ def _heads(t: torch.Tensor, heads: int):
     return t.view(b, n, heads, c // heads).transpose(1, 2)
 
 
+_SDPA_BACKEND = None      # None = PyTorch's own choice; set by MIXDQ_SDPA_BACKEND (tuning aid)
+
+
+def _sdpa_ctx():
+    """Optional pin of the library attention backend (flash | efficient | cudnn | math) for A/B
+    timing; attention itself is stock PyTorch in the reference and stays a library call here."""
+    global _SDPA_BACKEND
+    if _SDPA_BACKEND is None:
+        import os
+        _SDPA_BACKEND = os.environ.get("MIXDQ_SDPA_BACKEND", "").lower() or "default"
+    if _SDPA_BACKEND == "default":
+        return None
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    table = {"flash": SDPBackend.FLASH_ATTENTION, "efficient": SDPBackend.EFFICIENT_ATTENTION,
+             "cudnn": SDPBackend.CUDNN_ATTENTION, "math": SDPBackend.MATH}
+    return sdpa_kernel(table[_SDPA_BACKEND])
+
+
 def _attention(q, k, v, heads):
-    o = F.scaled_dot_product_attention(_heads(q, heads), _heads(k, heads), _heads(v, heads))
+    ctx = _sdpa_ctx()
+    if ctx is None:
+        o = F.scaled_dot_product_attention(_heads(q, heads), _heads(k, heads), _heads(v, heads))
+    else:
+        with ctx:
+            o = F.scaled_dot_product_attention(_heads(q, heads), _heads(k, heads), _heads(v, heads))
     b, h, t, d = o.shape
     return o.transpose(1, 2).reshape(b, t, h * d)
 

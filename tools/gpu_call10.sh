@@ -1,0 +1,7 @@
+set -x
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/c10_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/c10_pytest.log
+tail -12 gpurun_out/c10_pytest.log
+timeout 600 python bench.py --no-cpu-baseline > gpurun_out/c10_bench.json 2> gpurun_out/c10_bench.err; tail -c 800 gpurun_out/c10_bench.err
+timeout 300 python tools/step_breakdown.py --out gpurun_out/c10_breakdown_w8a8.json > gpurun_out/c10_breakdown_w8a8.txt 2>&1
+python tools/crit_path.py gpurun_out/c10_breakdown_w8a8.json 24
+head -c 300 gpurun_out/c10_bench.json

@@ -6,3 +6,5 @@ timeout 600 python bench.py --no-cpu-baseline > gpurun_out/c9_bench.json 2> gpur
 timeout 300 python tools/step_breakdown.py --out gpurun_out/c9_breakdown_w8a8.json > gpurun_out/c9_breakdown_w8a8.txt 2>&1
 python tools/crit_path.py gpurun_out/c9_breakdown_w8a8.json 24
 head -c 300 gpurun_out/c9_bench.json
+timeout 300 python tools/phase_sweep.py > gpurun_out/c9_phase_sweep.txt 2>&1
+grep "mode=0" gpurun_out/c9_phase_sweep.txt | cut -c1-230
