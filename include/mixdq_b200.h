@@ -65,10 +65,12 @@ void        mixdq_debug_set_mode(int mode);
    hardware cluster barrier + programmatic dependent launch); 0 = always the flag-barrier grid
    kernels. Results are identical either way; A/B timing and test aid (env MIXDQ_NO_CLUSTER=1). */
 void        mixdq_debug_set_cluster(int on);
-/* Enable (1, default) / disable (0) the two-kernel form of the dynamic quantisers (a min/max pass
-   and a quantise pass chained by programmatic dependent launch); 0 = one kernel with a grid
-   barrier. Identical results; A/B timing and test aid (env MIXDQ_SINGLE_KERNEL_QUANT=1). */
-void        mixdq_debug_set_two_pass(int on);
+/* Form of the dynamic quantisers: 2 (default) = lean one-kernel form (values in registers, one
+   release-increment / acquire-spin grid barrier) where the tensor fits a co-resident grid, else a
+   min/max pass + a quantise pass chained by programmatic dependent launch; 1 = the two-pass form
+   only; 0 = first-generation single kernels with the counter barrier. Identical results in every
+   mode; A/B timing and test aid (env MIXDQ_QUANT_MODE). */
+void        mixdq_debug_set_two_pass(int mode);
 /* Point the dynamic-quantisation workspace `ws` at a device buffer of
    launches x 1024 CTAs x 8 uint64 (or NULL = off): every quantiser launch that uses `ws` then
    stores, per CTA, %globaltimer (ns) at {entry, dependency wait passed, values loaded, barrier

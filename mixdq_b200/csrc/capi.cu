@@ -124,10 +124,11 @@ static int launch_tc(dim3 grid, const CUtensorMap& a, const CUtensorMap& w, cons
 // Tile-shape heuristic: a cost model fitted to in-kernel %globaltimer stamps on B200
 // (tools/phase_timing.py, tools/sweep_shapes.py; numbers in ns):
 //   * ~1400 from the end of the preceding kernel to the first stage landing (PDL wait + TMA);
-//   * per 128-byte k-block: 165 for BN <= 64, 195 for BN = 128 (two k-blocks = 8 tcgen05.mma per
-//     barrier round: ~52 cycles per MMA — the issuing thread is blocked for each MMA's duration —
-//     plus ~230 cycles of wait/fence/commit per stage), 420 for BN = 256 (one k-block per stage,
-//     ~130-160 cycles per MMA); it was 340 with one k-block per stage;
+//   * per 128-byte k-block: 112 for BN <= 64 (two issuing warps: 54 cycles per MMA, the pipe's
+//     floor), 195 for BN = 128 (one issuer, two k-blocks = 8 tcgen05.mma per barrier round:
+//     ~52-64 cycles per MMA — the issuing thread is blocked for each MMA's duration — plus ~230
+//     cycles of wait/fence/commit per stage), 420 for BN = 256 (one k-block per stage, ~130-160
+//     cycles per MMA); it was 340 with one issuer and one k-block per stage;
 //   * epilogue, no split: ~300 + 6.5 per tile column (dequant and ~26 B/clk/SM of stores overlap);
 //   * epilogue, split-K: 8.6 per column to write the INT32 partial tile, ~900 for the cluster
 //     barrier, 350 + 0.4 per owned element to sum the partials, 300 to store;
@@ -158,6 +159,16 @@ static int64_t current_ws(int32_t** ptr) {
 }
 extern "C" void mixdq_debug_force_bn(int bn) { g_force_bn = bn; }
 extern "C" void mixdq_debug_force_splits(int s) { g_force_splits = s; }
+// MIXDQ_A_PREFETCH=1 enables an L2 prefetch of the first A tile before the dependency wait.
+// Measured neutral on B200 (7.878 vs 7.872 ms per batch-1 step), hence off by default.
+static int g_a_prefetch = -1;
+static int a_prefetch_flag() {
+  if (g_a_prefetch < 0) {
+    const char* e = getenv("MIXDQ_A_PREFETCH");
+    g_a_prefetch = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_a_prefetch;
+}
 static int g_dbg_mode = 0;
 extern "C" void mixdq_debug_set_mode(int mode) { g_dbg_mode = mode; }
 static unsigned long long* g_dbg = nullptr;
@@ -196,7 +207,7 @@ static void pick_tile(int m_tiles, int N, int total_kb, bool allow_split, int* b
       const int cap = (s <= 2) ? kNumSm : (s == 4 ? 132 : 120);
       const long waves = (ctas + cap - 1) / cap;
       const int kb_per = (total_kb + s - 1) / s;
-      const double main = kb_per * (bn == 256 ? 420.0 : bn == 128 ? 195.0 : 165.0);
+      const double main = kb_per * (bn == 256 ? 420.0 : bn == 128 ? 195.0 : 112.0);
       const double epi = (s == 1) ? 300.0 + 6.5 * bn
                                   : 8.6 * bn + 900.0 + 350.0 + 0.4 * (128.0 / s) * bn + 300.0;
       const double t = waves * (1400.0 + main + epi);
@@ -264,6 +275,7 @@ static int gemm_common(const int8_t* A, int64_t lda, const int8_t* W, const floa
   TcParams p{};
   p.dbg = g_dbg;
   p.dbg_mode = g_dbg_mode;
+  p.a_prefetch = a_prefetch_flag();
   p.splits = splits;
   current_ws(&p.ws);
   p.M = M; p.N = N; p.num_kb = num_kb;
@@ -319,7 +331,7 @@ extern "C" int mixdq_gemm_w8a8_geglu_f16_dyn(const int8_t* A, int64_t lda, const
   {
     if (g_force_bn < 0) { int d0, d1; pick_tile(1, 32, 1, false, &d0, &d1); }   // reads the env
     const int cands[5] = {256, 160, 128, 64, 32};
-    const double main_ns[5] = {440.0, 280.0, 195.0, 165.0, 165.0};
+    const double main_ns[5] = {440.0, 280.0, 195.0, 112.0, 112.0};
     double best = 1e30;
     for (int i = 0; i < 5; ++i) {
       const int c = cands[i];
@@ -337,6 +349,7 @@ extern "C" int mixdq_gemm_w8a8_geglu_f16_dyn(const int8_t* A, int64_t lda, const
   TcParams p{};
   p.dbg = g_dbg;
   p.dbg_mode = g_dbg_mode;
+  p.a_prefetch = a_prefetch_flag();
   p.splits = 1;
   p.M = M; p.N = N2; p.num_kb = num_kb;
   p.scale = w_scale_il; p.bias0 = wsum_il; p.a_scale = a_scale; p.a_zp = a_zp;
@@ -458,6 +471,7 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
   TcParams p{};
   p.dbg = g_dbg;
   p.dbg_mode = g_dbg_mode;
+  p.a_prefetch = a_prefetch_flag();
   p.splits = splits;
   current_ws(&p.ws);
   p.M = N * P * Q; p.N = K;
@@ -545,6 +559,7 @@ static int split_common(const int8_t* xa, int64_t lda, const int8_t* wa, int Ca,
   TcParams p{};
   p.dbg = g_dbg;
   p.dbg_mode = g_dbg_mode;
+  p.a_prefetch = a_prefetch_flag();
   p.splits = 1;
   p.M = M; p.N = K;
   p.num_kb = (Ca + BLOCK_K - 1) / BLOCK_K;

@@ -560,7 +560,7 @@ extern "C" int mixdq_ln_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int
     return MIXDQ_OK;
   }
   // LayerNorm -> fp16 + min/max, then the single-pass quantiser: needs the caller's y buffer
-  if (y_out && mixdq_two_pass_enabled()) {
+  if (mixdq_two_pass_enabled()) {
     const int rc = mixdq_q2_ln(reinterpret_cast<const __half*>(x), ldx, M, C,
                                reinterpret_cast<const __half*>(gamma),
                                reinterpret_cast<const __half*>(beta), eps, q,

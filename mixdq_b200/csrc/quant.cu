@@ -268,15 +268,19 @@ int mixdq_q2_rows(const __half* x, int64_t ldx, int64_t M, int cols, int8_t* q, 
 int mixdq_q2_premm(const __half* x, int64_t numel, int8_t* q, float* scale_out, float* zp_out,
                    void* ws, int nparts, unsigned long long* zero_words, int zero_n,
                    cudaStream_t st);
-static int g_two_pass = -1;   // MIXDQ_SINGLE_KERNEL_QUANT=1 keeps the single-kernel quantisers
-bool mixdq_two_pass_enabled() {
+// 0 = single-kernel quantisers with the counter barrier (first generation), 1 = min/max pass +
+// quantise pass only, 2 (default) = additionally the lean one-kernel form for tensors that fit the
+// registers of one co-resident grid. MIXDQ_QUANT_MODE / mixdq_debug_set_two_pass select it.
+static int g_two_pass = -1;
+int mixdq_quant_mode() {
   if (g_two_pass < 0) {
-    const char* e = getenv("MIXDQ_SINGLE_KERNEL_QUANT");
-    g_two_pass = (e && e[0] == '1') ? 0 : 1;
+    const char* e = getenv("MIXDQ_QUANT_MODE");
+    g_two_pass = (e && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : 2;
   }
-  return g_two_pass != 0;
+  return g_two_pass;
 }
-extern "C" void mixdq_debug_set_two_pass(int on) { g_two_pass = on ? 1 : 0; }
+bool mixdq_two_pass_enabled() { return mixdq_quant_mode() != 0; }
+extern "C" void mixdq_debug_set_two_pass(int mode) { g_two_pass = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 
 extern "C" void mixdq_debug_set_cluster(int on) { cluster_mode_flag() = on ? 1 : 0; }
 // profiling: point the workspace at a stamp buffer (or NULL) and restart the launch sequence;

@@ -36,7 +36,7 @@ __device__ __noinline__ float exact_round_quot(float x, float delta) {
 __device__ __forceinline__ uint2 quant8_compact(const int4& raw, float delta, float inv, float z) {
   const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
   float x[8], r[8];
-  bool near = false;
+  unsigned int near = 0u;                  // bit i: element i needs the exact quotient
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float2 f = __half22float2(h2[i]);
@@ -47,14 +47,16 @@ __device__ __forceinline__ uint2 quant8_compact(const int4& raw, float delta, fl
   for (int i = 0; i < 8; ++i) {
     const float t = __fmul_rn(x[i], inv);
     r[i] = rintf(t);
-    near |= fabsf(__fsub_rn(t, r[i])) > 0.4999f;   // |t - x/delta| < 5e-5 (see quant_ws.cuh)
+    near |= (fabsf(__fsub_rn(t, r[i])) > 0.4999f ? 1u : 0u) << i;   // |t - x/delta| < 5e-5
   }
-  if (near) {
-    // redo all 8 exactly; the arrays are ROTATED so that the loop body only touches element 0
-    // (static register indexing, one call site)
+  if (near != 0u) {
+    // the arrays are ROTATED so that the loop body only touches element 0 (static register
+    // indexing, one call site); only flagged elements pay for the division
 #pragma unroll 1
     for (int i = 0; i < 8; ++i) {
-      const float e = exact_round_quot(x[0], delta);
+      float e = r[0];
+      if (near & 1u) e = exact_round_quot(x[0], delta);
+      near >>= 1;
       const float x0 = x[0];
 #pragma unroll
       for (int j = 0; j < 7; ++j) { x[j] = x[j + 1]; r[j] = r[j + 1]; }
@@ -71,6 +73,13 @@ __device__ __forceinline__ uint2 quant8_compact(const int4& raw, float delta, fl
     w[i >> 2] |= b << (8 * (i & 3));
   }
   return make_uint2(w[0], w[1]);
+}
+
+// Touch an address BEFORE the programmatic-dependency wait: the line may still be stale (the
+// value is never used), but the translation and the L2 lookup are warm when the real ld.cg
+// follows the wait (measured: the first dependent load after a kernel boundary costs ~0.6 us).
+__device__ __forceinline__ void warm(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // packed-half running min / max of one 16-byte vector (exact: no rounding in min/max)
@@ -122,6 +131,13 @@ minmax_rows_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int nchun
   QDbg dbg;
   dbg.begin(ws);
   pdl_launch_dependents();
+  {
+    const unsigned int it0 = blockIdx.x * kQ2Threads + threadIdx.x;
+    if (it0 < items) {
+      const unsigned int r0 = it0 / nchunks;
+      warm(reinterpret_cast<const int4*>(x + static_cast<int64_t>(r0) * ldx) + (it0 - r0 * nchunks));
+    }
+  }
   pdl_wait();
   dbg.waited(ws);
   __half2 mn = __float2half2_rn(0.0f), mx = mn;
@@ -152,10 +168,15 @@ quant_rows_premm_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int 
   QDbg dbg;
   dbg.begin(ws);
   pdl_launch_dependents();
-  pdl_wait();
-  dbg.waited(ws);
   const unsigned int stride = gridDim.x * kQ2Threads;
   unsigned int it = blockIdx.x * kQ2Threads + threadIdx.x;
+  if (it < items) {
+    const unsigned int r0 = it / nchunks;
+    warm(reinterpret_cast<const int4*>(x + static_cast<int64_t>(r0) * ldx) + (it - r0 * nchunks));
+  }
+  if (static_cast<int>(threadIdx.x) < nparts) warm(&ws->partial[threadIdx.x]);
+  pdl_wait();
+  dbg.waited(ws);
   // first data vector and the partials travel together
   int4 v = make_int4(0, 0, 0, 0);
   if (it < items) {
@@ -227,6 +248,15 @@ ln_minmax_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
     if (c < nchunks) {
       gr[i] = __ldg(reinterpret_cast<const int4*>(gamma) + c);
       br[i] = __ldg(reinterpret_cast<const int4*>(beta) + c);
+    }
+  }
+  {
+    const int r0 = blockIdx.x * (NT / 32) + warp;
+    if (r0 < M) {
+#pragma unroll
+      for (int i = 0; i < MAXCH; ++i)
+        if (lane + 32 * i < nchunks)
+          warm(reinterpret_cast<const int4*>(x + static_cast<int64_t>(r0) * ldx) + lane + 32 * i);
     }
   }
   pdl_wait();
@@ -303,6 +333,203 @@ ln_minmax_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
   dbg.end(ws);
 }
 
+// ---------------------------------------------------------------------------------------------
+// One-kernel variants for tensors whose values fit the REGISTERS of one co-resident grid (every
+// transformer-block tensor of the batch-1 step): pass 1 and pass 2 above joined by a lean grid
+// barrier — store the partial, ONE release-increment, acquire-spin, read the partials. The counter
+// wraps to zero by itself (atomicInc with limit 2G-1: G arrivals, then G departures), so nothing
+// is reset and nothing returns a value on the critical path. ~1.8 us from "values ready" to "codes
+// stored" against ~2.5 us for the kernel boundary of the two-pass form, and no fp16 scratch.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_release_inc_u32(unsigned int* p, unsigned int limit) {
+  asm volatile("red.release.gpu.global.inc.u32 [%0], %1;" ::"l"(p), "r"(limit) : "memory");
+}
+__device__ __forceinline__ void red_relaxed_inc_u32(unsigned int* p, unsigned int limit) {
+  asm volatile("red.relaxed.gpu.global.inc.u32 [%0], %1;" ::"l"(p), "r"(limit) : "memory");
+}
+
+// All threads call it with the CTA's packed running min / max; returns (delta, z) of the tensor.
+template <int NT>
+__device__ __forceinline__ void lean_grid_params(DynWs* __restrict__ ws, __half2 mn2, __half2 mx2,
+                                                 float* __restrict__ scale_out,
+                                                 float* __restrict__ zp_out, float& delta,
+                                                 float& z) {
+  __shared__ float s_mn[NT / 32], s_mx[NT / 32];
+  publish_partial<NT>(ws, mn2, mx2);          // thread 0 stored ws->partial[blockIdx.x]
+  const unsigned int G = gridDim.x;
+  if (threadIdx.x == 0) {
+    red_release_inc_u32(&ws->counter, 2u * G - 1u);
+    unsigned int spins = 0;
+    while (ld_acquire_u32(&ws->counter) < G) {
+      if (++spins > (1u << 26)) __trap();     // protocol bug: fail instead of hanging the device
+    }
+  }
+  __syncthreads();
+  float mn = 0.0f, mx = 0.0f;
+#pragma unroll 1
+  for (unsigned int i = threadIdx.x; i < G; i += NT) {
+    const float2 p = __ldcg(&ws->partial[i]);
+    mn = fminf(mn, p.x);
+    mx = fmaxf(mx, p.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  // departure: every partial this CTA needs has been read
+  if (threadIdx.x == 0) red_relaxed_inc_u32(&ws->counter, 2u * G - 1u);
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+  qdiff_params(mn, mx, delta, z);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *scale_out = delta; *zp_out = z - 128.0f; }
+}
+
+// plain tensor, row-pitched view -> dense int8; each thread owns <= 2 vectors (registers)
+__global__ void __launch_bounds__(kQ2Threads)
+quant_lean_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int nchunks,
+                  unsigned int items, int8_t* __restrict__ q, DynWs* __restrict__ ws,
+                  float* __restrict__ scale_out, float* __restrict__ zp_out) {
+  QDbg dbg;
+  dbg.begin(ws);
+  pdl_launch_dependents();
+  pdl_wait();
+  dbg.waited(ws);
+  const unsigned int i0 = blockIdx.x * kQ2Threads + threadIdx.x;
+  const unsigned int i1 = i0 + gridDim.x * kQ2Threads;
+  int4 v0 = make_int4(0, 0, 0, 0), v1 = v0;
+  if (i0 < items) {
+    const unsigned int r = i0 / nchunks;
+    v0 = __ldcg(reinterpret_cast<const int4*>(x + static_cast<int64_t>(r) * ldx) + (i0 - r * nchunks));
+  }
+  if (i1 < items) {
+    const unsigned int r = i1 / nchunks;
+    v1 = __ldcg(reinterpret_cast<const int4*>(x + static_cast<int64_t>(r) * ldx) + (i1 - r * nchunks));
+  }
+  __half2 mn = __float2half2_rn(0.0f), mx = mn;
+  hminmax8(v0, mn, mx);     // zero-filled vectors do not move min <= 0 <= max
+  hminmax8(v1, mn, mx);
+  dbg.stamp(2);
+  float delta, z;
+  lean_grid_params<kQ2Threads>(ws, mn, mx, scale_out, zp_out, delta, z);
+  dbg.stamp(3);
+  const float inv = __frcp_rn(delta);
+  uint2* qv = reinterpret_cast<uint2*>(q);
+#pragma unroll 1
+  for (int u = 0; u < 2; ++u) {            // one inlined copy of the quantiser
+    const unsigned int it = u ? i1 : i0;
+    if (it < items) qv[it] = quant8_compact(u ? v1 : v0, delta, inv, z);
+  }
+  dbg.end(ws);
+}
+
+// LayerNorm -> int8, one row per warp, the row's fp16 output stays in registers
+template <int MAXCH, int NT>
+__global__ void __launch_bounds__(NT)
+ln_quant_lean_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
+                     const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps,
+                     int8_t* __restrict__ q, __half* __restrict__ y_out, DynWs* __restrict__ ws,
+                     float* __restrict__ scale_out, float* __restrict__ zp_out) {
+  QDbg dbg;
+  dbg.begin(ws);
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = C >> 3;
+  const int r = blockIdx.x * (NT / 32) + warp;
+  int4 gr[MAXCH], br[MAXCH];
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) {
+      gr[i] = __ldg(reinterpret_cast<const int4*>(gamma) + c);
+      br[i] = __ldg(reinterpret_cast<const int4*>(beta) + c);
+    }
+  }
+  pdl_wait();
+  dbg.waited(ws);
+  __half2 mn = __float2half2_rn(0.0f), mx = mn;
+  int4 out[MAXCH];
+  if (r < M) {
+    const int4* xrow = reinterpret_cast<const int4*>(x + static_cast<int64_t>(r) * ldx);
+    int4 raw[MAXCH];
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i)
+      if (lane + 32 * i < nchunks) raw[i] = __ldcg(xrow + lane + 32 * i);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) {
+      if (lane + 32 * i < nchunks) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h2[j]);
+          sum += f.x;
+          sum += f.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / static_cast<float>(C);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) {
+      if (lane + 32 * i < nchunks) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h2[j]);
+          const float d0 = f.x - mean, d1 = f.y - mean;
+          ss += d0 * d0;
+          ss += d1 * d1;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / static_cast<float>(C) + eps);
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[i]);
+        const __half2* g2 = reinterpret_cast<const __half2*>(&gr[i]);
+        const __half2* b2 = reinterpret_cast<const __half2*>(&br[i]);
+        __half2* o2 = reinterpret_cast<__half2*>(&out[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h2[j]);
+          const float2 g = __half22float2(g2[j]);
+          const float2 b = __half22float2(b2[j]);
+          o2[j] = __floats2half2_rn(fmaf(g.x, rstd * (f.x - mean), b.x),
+                                    fmaf(g.y, rstd * (f.y - mean), b.y));
+        }
+        hminmax8(out[i], mn, mx);
+        if (y_out) reinterpret_cast<int4*>(y_out + static_cast<int64_t>(r) * C)[c] = out[i];
+      }
+    }
+  }
+  dbg.stamp(2);
+  float delta, z;
+  lean_grid_params<NT>(ws, mn, mx, scale_out, zp_out, delta, z);
+  dbg.stamp(3);
+  if (r < M) {
+    const float inv = __frcp_rn(delta);
+    uint2* qrow = reinterpret_cast<uint2*>(q + static_cast<int64_t>(r) * C);
+#pragma unroll 1
+    for (int i = 0; i < MAXCH; ++i) {
+      // rotate so that the loop body only touches out[0] (one inlined copy of the quantiser)
+      const int c = lane + 32 * i;
+      if (c < nchunks) qrow[c] = quant8_compact(out[0], delta, inv, z);
+#pragma unroll
+      for (int j = 0; j + 1 < MAXCH; ++j) out[j] = out[j + 1];
+    }
+  }
+  dbg.end(ws);
+}
+
 static inline int grid_for2(int64_t items, int per_block, int max_blocks) {
   int64_t g = (items + per_block - 1) / per_block;
   if (g < 1) g = 1;
@@ -319,7 +546,9 @@ using namespace mixdq;
 // the single-kernel path).
 static const int64_t kMaxItems = (1ll << 31) - 1;
 
-// A10 of a row-pitched view in two short kernels. cols % 8 == 0, 16-byte aligned rows.
+int mixdq_quant_mode();   // quant.cu: 0 single-kernel (old), 1 two-pass only, 2 lean one-kernel too
+
+// A10 of a row-pitched view. cols % 8 == 0, 16-byte aligned rows.
 int mixdq_q2_rows(const __half* x, int64_t ldx, int64_t M, int cols, int8_t* q, float* scale_out,
                   float* zp_out, void* ws, cudaStream_t st) {
   const int64_t items = M * (cols >> 3);
@@ -328,6 +557,15 @@ int mixdq_q2_rows(const __half* x, int64_t ldx, int64_t M, int cols, int8_t* q, 
   const unsigned int nchunks = (ldx == cols) ? static_cast<unsigned int>(items)
                                              : static_cast<unsigned int>(cols >> 3);
   const unsigned int n = static_cast<unsigned int>(items);
+  // register-resident one-kernel form: <= 2 vectors per thread on a co-resident grid
+  // (256-thread CTAs without shared memory: 4 per SM is always resident)
+  if (mixdq_quant_mode() == 2 && items <= static_cast<int64_t>(148) * 4 * kQ2Threads * 2) {
+    const int g = grid_for2(items, kQ2Threads * 2, 148 * 4);
+    if (launch_pdl(quant_lean_kernel, g, kQ2Threads, 0, st, x, ldx, nchunks, n, q,
+                   static_cast<DynWs*>(ws), scale_out, zp_out) != cudaSuccess)
+      return MIXDQ_ERR_CUDA;
+    return MIXDQ_OK;
+  }
   const int g1 = grid_for2(items, kQ2Threads * 2, 148 * 4);
   if (launch_pdl(minmax_rows_kernel, g1, kQ2Threads, 0, st, x, ldx, nchunks, n,
                  static_cast<DynWs*>(ws)) != cudaSuccess)
@@ -363,6 +601,26 @@ int mixdq_q2_ln(const __half* x, int64_t ldx, int M, int C, const __half* gamma,
   DynWs* w = static_cast<DynWs*>(ws);
   cudaError_t e;
   int g1;
+  // one row per warp, the whole tensor in registers, lean barrier: M <= 148 CTAs x 8 warps
+  if (mixdq_quant_mode() == 2 && M <= 148 * 8) {
+    if (M <= 296) {
+      g1 = (M + 1) / 2;
+      e = (C <= 5 * 256)
+              ? launch_pdl(ln_quant_lean_kernel<5, 64>, g1, 64, 0, st, x, ldx, M, C, gamma, beta, eps,
+                           q, y, w, scale_out, zp_out)
+              : launch_pdl(ln_quant_lean_kernel<8, 64>, g1, 64, 0, st, x, ldx, M, C, gamma, beta, eps,
+                           q, y, w, scale_out, zp_out);
+    } else {
+      g1 = (M + 7) / 8;
+      e = (C <= 5 * 256)
+              ? launch_pdl(ln_quant_lean_kernel<5, 256>, g1, 256, 0, st, x, ldx, M, C, gamma, beta,
+                           eps, q, y, w, scale_out, zp_out)
+              : launch_pdl(ln_quant_lean_kernel<8, 256>, g1, 256, 0, st, x, ldx, M, C, gamma, beta,
+                           eps, q, y, w, scale_out, zp_out);
+    }
+    return e == cudaSuccess ? MIXDQ_OK : MIXDQ_ERR_CUDA;   // (y, if given, was written too)
+  }
+  if (y == nullptr) return MIXDQ_ERR_UNSUPPORTED;          // the two-pass form needs the scratch
   if (M <= 512) {
     g1 = (M + 1) / 2;
     e = (C <= 5 * 256)

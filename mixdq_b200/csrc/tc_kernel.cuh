@@ -92,6 +92,7 @@ struct TcParams {
   int32_t* ws;            // split-K exchange workspace: [CTA][BN/4][128][4] int32 (splits > 1)
   unsigned long long* dbg; // optional phase timestamps (globaltimer ns), 8 slots per CTA
   int dbg_mode;            // profiling only: bit0 = skip MMA issue, bit1 = skip TMA loads
+  int a_prefetch;          // 1: L2-prefetch the first A tile before the dependency wait
 };
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -320,6 +321,20 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int ns = nsub_of(i);
           mbar_expect_tx(&full_bar[i], ns * (a_bytes + L::W_SUB));
           for (int u = 0; u < ns; ++u) load_w(kb_begin + i * L::KSUB + u, i, u);
+        }
+        // warm the path of the first A tile (L2 prefetch: its contents are not consumed)
+        if (p.a_prefetch) {
+          const int kb = kb_begin;
+          if (KIND == KIND_CONV) {
+            const int tap = kb / p.kb_per_tap;
+            const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
+            const int r = tap / p.S, sx = tap - r * p.S;
+            tma_prefetch_4d(&tmA, c0, tq0 * p.stride - p.pad + sx, tp0 * p.stride - p.pad + r, tn0);
+          } else if (KIND == KIND_SPLIT && kb >= p.num_kb) {
+            tma_prefetch_2d(&tmA1, (kb - p.num_kb) * BLOCK_K, m0);
+          } else {
+            tma_prefetch_2d(&tmA, kb * BLOCK_K, m0);
+          }
         }
       }
       __syncwarp();

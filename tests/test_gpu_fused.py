@@ -146,8 +146,8 @@ def test_cluster_and_grid_quantisers_agree(ops, dev):
 
 
 def test_two_pass_and_single_kernel_quantisers_agree(ops, dev):
-    """min/max pass + quantise pass (csrc/quant2.cu) == the single-kernel quantisers with a grid
-    barrier, bit for bit, for plain / row-pitched / LayerNorm / GroupNorm inputs."""
+    """lean one-kernel form == min/max pass + quantise pass (csrc/quant2.cu) == the first-generation
+    single-kernel quantisers, bit for bit, for plain / row-pitched / LayerNorm / GroupNorm inputs."""
     from mixdq_b200 import _lib
     lib = _lib.load()
     g = torch.Generator().manual_seed(11)
@@ -159,7 +159,7 @@ def test_two_pass_and_single_kernel_quantisers_agree(ops, dev):
         memory_format=torch.channels_last)
     outs = []
     try:
-        for mode in (0, 1, 0, 1):
+        for mode in (0, 1, 2, 0, 2, 1):
             lib.mixdq_debug_set_two_pass(mode)
             ops.clear_dynamic_quant_cache()
             o = list(ops.layernorm_quantize_dynamic(x, w, b, 1e-5, return_y=True))
@@ -169,7 +169,7 @@ def test_two_pass_and_single_kernel_quantisers_agree(ops, dev):
             o += list(ops.groupnorm_quantize_dynamic(img, 32, w, b, 1e-6, False))
             outs.append([t.clone() for t in o])
     finally:
-        lib.mixdq_debug_set_two_pass(1)
+        lib.mixdq_debug_set_two_pass(2)
     for o in outs[1:]:
         for a_, b_ in zip(o, outs[0]):
             assert torch.equal(a_, b_)

@@ -81,15 +81,25 @@ def show(tag, stamps, ref, names):
           " ".join(f"{n}[{rel[:, j].mean():.0f}/{rel[:, j].max():.0f}]" for j, n in enumerate(names)))
 
 
-# launch order: ln(p1,p2) | per iteration: GEMM+res, ln(p1,p2), GEMM, quant(p1,p2)
+# launch order: ln | per iteration: GEMM+res, ln, GEMM, quant — each quantisation = PER kernels
+PER = int(sys.argv[3]) if len(sys.argv) > 3 else (2 if Q[1].shape[0] and Q[2 * L + 1].shape[0] else 1)
+print("kernels per quantisation:", PER)
 for i in range(1, L):
-    base = 2 + 4 * i
     g0_end = T[2 * i][:, 7].max()
-    show(f"[{i}] ln pass1 after GEMM end", Q[base][:, :5], g0_end, qn)
-    show(f"[{i}] ln pass2 after pass1 end", Q[base + 1][:, :5], Q[base][:, 4].max(), qn)
-    show(f"[{i}] GEMM after ln pass2 end", T[2 * i + 1][:, :8], Q[base + 1][:, 4].max(), tn)
     g1_end = T[2 * i + 1][:, 7].max()
-    show(f"[{i}] quant pass1 after GEMM end", Q[base + 2][:, :5], g1_end, qn)
-    show(f"[{i}] quant pass2 after pass1 end", Q[base + 3][:, :5], Q[base + 2][:, 4].max(), qn)
+    if PER == 2:
+        base = 2 + 4 * i
+        show(f"[{i}] ln pass1 after GEMM end", Q[base][:, :5], g0_end, qn)
+        show(f"[{i}] ln pass2 after pass1 end", Q[base + 1][:, :5], Q[base][:, 4].max(), qn)
+        show(f"[{i}] GEMM after ln pass2 end", T[2 * i + 1][:, :8], Q[base + 1][:, 4].max(), tn)
+        show(f"[{i}] quant pass1 after GEMM end", Q[base + 2][:, :5], g1_end, qn)
+        show(f"[{i}] quant pass2 after pass1 end", Q[base + 3][:, :5], Q[base + 2][:, 4].max(), qn)
+        last = Q[base + 3]
+    else:
+        base = 1 + 2 * i
+        show(f"[{i}] ln (one kernel) after GEMM end", Q[base][:, :5], g0_end, qn)
+        show(f"[{i}] GEMM after ln end", T[2 * i + 1][:, :8], Q[base][:, 4].max(), tn)
+        show(f"[{i}] quant (one kernel) after GEMM end", Q[base + 1][:, :5], g1_end, qn)
+        last = Q[base + 1]
     if i + 1 < L:
-        show(f"[{i}] next GEMM+res after quant pass2 end", T[2 * i + 2][:, :8], Q[base + 3][:, 4].max(), tn)
+        show(f"[{i}] next GEMM+res after quant end", T[2 * i + 2][:, :8], last[:, 4].max(), tn)
