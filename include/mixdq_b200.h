@@ -65,11 +65,11 @@ void        mixdq_debug_set_mode(int mode);
    hardware cluster barrier + programmatic dependent launch); 0 = always the flag-barrier grid
    kernels. Results are identical either way; A/B timing and test aid (env MIXDQ_NO_CLUSTER=1). */
 void        mixdq_debug_set_cluster(int on);
-/* Form of the dynamic quantisers: 2 (default) = lean one-kernel form (values in registers, one
-   release-increment / acquire-spin grid barrier) where the tensor fits a co-resident grid, else a
-   min/max pass + a quantise pass chained by programmatic dependent launch; 1 = the two-pass form
-   only; 0 = first-generation single kernels with the counter barrier. Identical results in every
-   mode; A/B timing and test aid (env MIXDQ_QUANT_MODE). */
+/* Form of the dynamic quantisers: 1 (default) = a min/max pass + a quantise pass chained by
+   programmatic dependent launch; 2 = lean one-kernel form (values in registers, tagged-partial
+   grid barrier) where the tensor fits a co-resident grid (faster in isolation, slower inside the
+   whole-UNet graph: see profiles/README.md); 0 = first-generation single kernels with the counter
+   barrier. Identical results in every mode; A/B timing and test aid (env MIXDQ_QUANT_MODE). */
 void        mixdq_debug_set_two_pass(int mode);
 /* Point the dynamic-quantisation workspace `ws` at a device buffer of
    launches x 1024 CTAs x 8 uint64 (or NULL = off): every quantiser launch that uses `ws` then

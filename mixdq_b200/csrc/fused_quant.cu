@@ -415,15 +415,32 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
 
   // ---- phase 1: normalise (+SiLU) -> fp16 -> stash, min/max ----
   float mn = 0.f, mx = 0.f;
-  for (int r = row0 + warp; r < row1; r += kFqWarps) {
-    const __half* xrow = ximg + static_cast<int64_t>(r) * ldx;
-    const int lr = r - row0;
-    for (int c = lane; c < nchunks; c += 32) {
-      const int4 y = gn_vec8<SILU>(ldg16(xrow + 8 * c), 8 * c, cpg, s_mean, s_rstd, gamma, beta);
-      minmax_vec8(y, mn, mx);
-      if (MODE == 0 && lr < stash_rows) stash[lr * nchunks + c] = y;
-      if (y_out)
-        reinterpret_cast<int4*>(y_out + (static_cast<int64_t>(n) * HW + r) * C)[c] = y;
+  {
+    // flat (row, chunk) items of this CTA, four 16-byte loads in flight per thread (a warp-per-row
+    // loop left each lane with one or two dependent load -> compute -> store chains per row)
+    const int items = (row1 - row0) * nchunks;
+    constexpr int U = 4;
+    for (int it0 = threadIdx.x; it0 < items; it0 += U * kFqThreads) {
+      int4 raw[U];
+      int lr[U], c[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int it = it0 + u * kFqThreads;
+        lr[u] = it / nchunks;
+        c[u] = it - lr[u] * nchunks;
+        if (it < items)
+          raw[u] = ldg16(ximg + static_cast<int64_t>(row0 + lr[u]) * ldx + 8 * c[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int it = it0 + u * kFqThreads;
+        if (it >= items) break;
+        const int4 y = gn_vec8<SILU>(raw[u], 8 * c[u], cpg, s_mean, s_rstd, gamma, beta);
+        minmax_vec8(y, mn, mx);
+        if (MODE == 0 && lr[u] < stash_rows) stash[it] = y;
+        if (y_out)
+          reinterpret_cast<int4*>(y_out + (static_cast<int64_t>(n) * HW + row0 + lr[u]) * C)[c[u]] = y;
+      }
     }
   }
   if (MODE == 2) {

@@ -268,14 +268,16 @@ int mixdq_q2_rows(const __half* x, int64_t ldx, int64_t M, int cols, int8_t* q, 
 int mixdq_q2_premm(const __half* x, int64_t numel, int8_t* q, float* scale_out, float* zp_out,
                    void* ws, int nparts, unsigned long long* zero_words, int zero_n,
                    cudaStream_t st);
-// 0 = single-kernel quantisers with the counter barrier (first generation), 1 = min/max pass +
-// quantise pass only, 2 (default) = additionally the lean one-kernel form for tensors that fit the
-// registers of one co-resident grid. MIXDQ_QUANT_MODE / mixdq_debug_set_two_pass select it.
+// 0 = single-kernel quantisers with the counter barrier (first generation), 1 (default) = min/max
+// pass + quantise pass, 2 = additionally the lean one-kernel form (tagged-partial barrier) for
+// tensors that fit the registers of one co-resident grid: 1.5 us of barrier in an isolated chain
+// (tools/quant_phase.py) but 8.8 us per kernel inside the whole-UNet graph (9.06 vs 7.87 ms per
+// step), so it is not the default. MIXDQ_QUANT_MODE / mixdq_debug_set_two_pass select the mode.
 static int g_two_pass = -1;
 int mixdq_quant_mode() {
   if (g_two_pass < 0) {
     const char* e = getenv("MIXDQ_QUANT_MODE");
-    g_two_pass = (e && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : 2;
+    g_two_pass = (e && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : 1;
   }
   return g_two_pass;
 }

@@ -335,56 +335,97 @@ ln_minmax_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
 
 // ---------------------------------------------------------------------------------------------
 // One-kernel variants for tensors whose values fit the REGISTERS of one co-resident grid (every
-// transformer-block tensor of the batch-1 step): pass 1 and pass 2 above joined by a lean grid
-// barrier — store the partial, ONE release-increment, acquire-spin, read the partials. The counter
-// wraps to zero by itself (atomicInc with limit 2G-1: G arrivals, then G departures), so nothing
-// is reset and nothing returns a value on the critical path. ~1.8 us from "values ready" to "codes
-// stored" against ~2.5 us for the kernel boundary of the two-pass form, and no fp16 scratch.
+// transformer-block tensor of the batch-1 step): pass 1 and pass 2 above joined by a grid barrier
+// made of ONE 8-byte store per CTA and plain polling loads — no fence, no atomic, no counter:
+//   * min and max come from fp16 values, so their fp32 patterns have 13 zero low mantissa bits
+//     each: 26 bits of room for a TAG = the launch's epoch (1 .. 2^26-1, never 0, so untagged
+//     partials of the two-pass producers never match);
+//   * a CTA publishes {min|tag_lo, max|tag_hi} with a single 64-bit store (single-copy atomic: a
+//     reader that sees the tag sees the values), and thread i of every CTA polls slot i until it
+//     carries the tag;
+//   * the epoch is read after the dependency wait (the previous launch is complete) and bumped
+//     by CTA 0 after it has passed the barrier (every CTA has read it by then).
+// A release-increment / acquire-spin counter barrier measured 2.3-2.5 us here (the release fence
+// dominates); this one is bounded by one store-to-load L2 round trip.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void red_release_inc_u32(unsigned int* p, unsigned int limit) {
-  asm volatile("red.release.gpu.global.inc.u32 [%0], %1;" ::"l"(p), "r"(limit) : "memory");
+constexpr unsigned int kTagMask = (1u << 13) - 1u;
+
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void red_relaxed_inc_u32(unsigned int* p, unsigned int limit) {
-  asm volatile("red.relaxed.gpu.global.inc.u32 [%0], %1;" ::"l"(p), "r"(limit) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
 
-// All threads call it with the CTA's packed running min / max; returns (delta, z) of the tensor.
+// All threads call it with the CTA's packed running min / max and the launch's tag (read from
+// ws->epoch after the dependency wait); returns (delta, z) of the tensor.
 template <int NT>
-__device__ __forceinline__ void lean_grid_params(DynWs* __restrict__ ws, __half2 mn2, __half2 mx2,
+__device__ __forceinline__ void lean_grid_params(DynWs* __restrict__ ws, unsigned int epoch,
+                                                 __half2 mn2, __half2 mx2,
                                                  float* __restrict__ scale_out,
                                                  float* __restrict__ zp_out, float& delta,
                                                  float& z) {
-  __shared__ float s_mn[NT / 32], s_mx[NT / 32];
-  publish_partial<NT>(ws, mn2, mx2);          // thread 0 stored ws->partial[blockIdx.x]
-  const unsigned int G = gridDim.x;
-  if (threadIdx.x == 0) {
-    red_release_inc_u32(&ws->counter, 2u * G - 1u);
-    unsigned int spins = 0;
-    while (ld_acquire_u32(&ws->counter) < G) {
-      if (++spins > (1u << 26)) __trap();     // protocol bug: fail instead of hanging the device
-    }
+  constexpr int NW = NT / 32;
+  __shared__ float s_mn[NW], s_mx[NW];
+  const unsigned int tag = epoch % ((1u << 26) - 1u) + 1u;     // 1 .. 2^26-1
+  float mn = fminf(__low2float(mn2), __high2float(mn2));
+  float mx = fmaxf(__low2float(mx2), __high2float(mx2));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
   __syncthreads();
-  float mn = 0.0f, mx = 0.0f;
+  unsigned long long* slots = reinterpret_cast<unsigned long long*>(ws->partial);
+  const unsigned int tag_lo = tag & kTagMask, tag_hi = (tag >> 13) & kTagMask;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+    // qdiff clamps x_min <= 0 <= x_max (base_quantizer.py:155-158)
+    const unsigned int a = __float_as_uint(fminf(mn, 0.0f)) | tag_lo;
+    const unsigned int b = __float_as_uint(fmaxf(mx, 0.0f)) | tag_hi;
+    st_relaxed_u64(&slots[blockIdx.x], (static_cast<unsigned long long>(b) << 32) | a);
+  }
+  // thread i waits for CTA i's partial
+  const unsigned int G = gridDim.x;
+  mn = 0.0f; mx = 0.0f;
 #pragma unroll 1
   for (unsigned int i = threadIdx.x; i < G; i += NT) {
-    const float2 p = __ldcg(&ws->partial[i]);
-    mn = fminf(mn, p.x);
-    mx = fmaxf(mx, p.y);
+    unsigned long long v;
+    unsigned int spins = 0;
+    do {
+      v = ld_relaxed_u64(&slots[i]);
+      if (++spins > (1u << 26)) __trap();     // protocol bug: fail instead of hanging the device
+    } while ((static_cast<unsigned int>(v) & kTagMask) != tag_lo ||
+             (static_cast<unsigned int>(v >> 32) & kTagMask) != tag_hi);
+    mn = fminf(mn, __uint_as_float(static_cast<unsigned int>(v) & ~kTagMask));
+    mx = fmaxf(mx, __uint_as_float(static_cast<unsigned int>(v >> 32) & ~kTagMask));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   }
-  if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+  __syncthreads();                             // s_mn / s_mx are reused
+  if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
   __syncthreads();
-  // departure: every partial this CTA needs has been read
-  if (threadIdx.x == 0) red_relaxed_inc_u32(&ws->counter, 2u * G - 1u);
 #pragma unroll
-  for (int w = 0; w < NT / 32; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+  for (int w = 0; w < NW; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
   qdiff_params(mn, mx, delta, z);
-  if (blockIdx.x == 0 && threadIdx.x == 0) { *scale_out = delta; *zp_out = z - 128.0f; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *scale_out = delta;
+    *zp_out = z - 128.0f;
+    // next launch's epoch (this CTA is past the barrier, so every CTA has read the current one)
+    ws->epoch = epoch + 1u;
+  }
+}
+
+__device__ __forceinline__ unsigned int lean_epoch(const DynWs* ws) {
+  return *reinterpret_cast<const volatile unsigned int*>(&ws->epoch);
 }
 
 // plain tensor, row-pitched view -> dense int8; each thread owns <= 2 vectors (registers)
@@ -397,6 +438,7 @@ quant_lean_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int nchunk
   pdl_launch_dependents();
   pdl_wait();
   dbg.waited(ws);
+  const unsigned int epoch = lean_epoch(ws);
   const unsigned int i0 = blockIdx.x * kQ2Threads + threadIdx.x;
   const unsigned int i1 = i0 + gridDim.x * kQ2Threads;
   int4 v0 = make_int4(0, 0, 0, 0), v1 = v0;
@@ -413,7 +455,7 @@ quant_lean_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int nchunk
   hminmax8(v1, mn, mx);
   dbg.stamp(2);
   float delta, z;
-  lean_grid_params<kQ2Threads>(ws, mn, mx, scale_out, zp_out, delta, z);
+  lean_grid_params<kQ2Threads>(ws, epoch, mn, mx, scale_out, zp_out, delta, z);
   dbg.stamp(3);
   const float inv = __frcp_rn(delta);
   uint2* qv = reinterpret_cast<uint2*>(q);
@@ -449,6 +491,7 @@ ln_quant_lean_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
   }
   pdl_wait();
   dbg.waited(ws);
+  const unsigned int epoch = lean_epoch(ws);
   __half2 mn = __float2half2_rn(0.0f), mx = mn;
   int4 out[MAXCH];
   if (r < M) {
@@ -513,7 +556,7 @@ ln_quant_lean_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
   }
   dbg.stamp(2);
   float delta, z;
-  lean_grid_params<NT>(ws, mn, mx, scale_out, zp_out, delta, z);
+  lean_grid_params<NT>(ws, epoch, mn, mx, scale_out, zp_out, delta, z);
   dbg.stamp(3);
   if (r < M) {
     const float inv = __frcp_rn(delta);

@@ -33,7 +33,8 @@ struct DynWs {
   unsigned int mm[2];     // bit patterns of -min (>= +0) and max (>= +0), atomicMax'ed as ints
   unsigned int mm_done;   // consumer CTAs that have read mm (the last one zeroes all three)
   unsigned int pad2;
-  unsigned int gmm[2];    // unused (kept for layout stability)
+  unsigned int epoch;     // launches of the tagged-partial barrier so far (quant2.cu lean kernels)
+  unsigned int gmm1;      // unused
   unsigned int qdbg_seq;  // profiling: launches stamped so far (see QDbg)
   unsigned int pad3;
   unsigned long long* qdbg;   // profiling: stamp buffer or NULL

@@ -256,14 +256,10 @@ _dyn_cache = []          # [(tensor, version, (q, scale, zp))], most recent last
 _DYN_CACHE_SLOTS = 3
 
 
-_LN_ONE_KERNEL_ROWS = 148 * 8          # csrc/quant2.cu::mixdq_q2_ln
-_ONE_KERNEL_ELEMS = 148 * 4 * 256 * 2 * 8   # csrc/quant2.cu::mixdq_q2_rows
-
-
 def _dyn_kernels(numel: int) -> int:
-    """Kernels one dynamic quantisation launches: one while the tensor fits the registers of a
-    co-resident grid, else a min/max pass + a quantise pass (csrc/quant2.cu)."""
-    return 1 if numel <= _ONE_KERNEL_ELEMS else 2
+    """Kernels one dynamic quantisation launches: tiny tensors take the one-cluster kernel, the
+    rest a min/max pass + a quantise pass (csrc/quant2.cu)."""
+    return 1 if numel <= 65536 else 2
 
 
 def clear_dynamic_quant_cache() -> None:
@@ -677,10 +673,8 @@ def layernorm_quantize_dynamic(x: torch.Tensor, weight: torch.Tensor, bias: torc
         x2 = x2.contiguous()
     M = x2.shape[0]
     q = torch.empty(x.shape, dtype=torch.int8, device=x.device)
-    # <= 1184 rows run as ONE kernel with the row in registers (csrc/quant2.cu); larger inputs as a
-    # LayerNorm pass + a quantise pass that meet in an fp16 scratch tensor (stays in L2)
-    y = torch.empty(x.shape, dtype=torch.float16, device=x.device) \
-        if (return_y or M > _LN_ONE_KERNEL_ROWS) else None
+    # LayerNorm pass + quantise pass meet in an fp16 scratch tensor (stays in L2)
+    y = torch.empty(x.shape, dtype=torch.float16, device=x.device)
     qp, sc, zp = _qp_pair(x.device)
     lib = _lib.load()
     with _DeviceGuard(x2):
@@ -689,7 +683,7 @@ def layernorm_quantize_dynamic(x: torch.Tensor, weight: torch.Tensor, bias: torc
                 (x2.data_ptr(), x2.stride(0) if M > 1 else C, M, C, weight.data_ptr(),
                  bias.data_ptr(), float(eps), q.data_ptr(), _ptr(y), qp.data_ptr(),
                  qp.data_ptr() + 4, ws.data_ptr()), x2, keep=(x2, weight, bias, q, y, qp, ws),
-                kernels=1 if M <= _LN_ONE_KERNEL_ROWS else 2, algo_bytes=3 * M * C)
+                kernels=_dyn_kernels(M * C), algo_bytes=3 * M * C)
     return (q, sc, zp, y) if return_y else (q, sc, zp)
 
 

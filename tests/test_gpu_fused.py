@@ -169,7 +169,7 @@ def test_two_pass_and_single_kernel_quantisers_agree(ops, dev):
             o += list(ops.groupnorm_quantize_dynamic(img, 32, w, b, 1e-6, False))
             outs.append([t.clone() for t in o])
     finally:
-        lib.mixdq_debug_set_two_pass(2)
+        lib.mixdq_debug_set_two_pass(1)
     for o in outs[1:]:
         for a_, b_ in zip(o, outs[0]):
             assert torch.equal(a_, b_)
