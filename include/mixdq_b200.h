@@ -236,6 +236,20 @@ int mixdq_gemm_w8a8_geglu_f16_dyn(const int8_t* A, int64_t lda, const int8_t* W_
 int mixdq_quant_i8_premm(const mixdq_half_t* x, int64_t numel, int8_t* q, float* scale_out,
                          float* zp_out, void* ws, mixdq_stream_t stream);
 
+/* Cross-attention of the fused transformer block (stock PyTorch SDPA in the reference: diffusers
+   Attention between attn2.to_q/to_k/to_v and attn2.to_out, run on fp16): head dim 64, <= 96
+   context tokens, no mask. q / k / v are fp16 with the heads side by side in a row (row pitch ld*,
+   batch stride bs*, in elements; k / v may be column slices of a wider matrix); out = dense fp16
+   [B][T][H*64] = softmax(scale * q k^T) v per head, fp32 scores / softmax / accumulation, one
+   rounding. The min(0, min) / max(0, max) of `out` are left in `ws` as per-CTA partials for exactly
+   one mixdq_quant_i8_premm call on the same stream (as mixdq_gemm_w8a8_geglu_f16_dyn does).
+   MIXDQ_ERR_UNSUPPORTED for Lk > 96 or more than 4096 (query block, head, batch) CTAs. */
+int mixdq_cross_attn_d64_f16(const mixdq_half_t* q, int64_t ldq, int64_t bsq,
+                             const mixdq_half_t* k, int64_t ldk, int64_t bsk,
+                             const mixdq_half_t* v, int64_t ldv, int64_t bsv,
+                             mixdq_half_t* out, int B, int T, int Lk, int H, float scale,
+                             void* ws, mixdq_stream_t stream);
+
 /* wsum_krs fp32 [K][R][S] iff pad > 0; wsum_k fp32 [K] (sum over taps and channels) iff pad == 0 */
 int mixdq_conv_w8a8_f16_dyn(const int8_t* x_nhwc, int64_t x_cpitch, const int8_t* w_krsc,
                             const float* w_scale, const float* wsum_krs, const float* wsum_k,

@@ -749,6 +749,41 @@ def qlinear_geglu_quantize_dynamic(input_int8, weight_il, weight_scale_il, input
     return (q, sc, zp, y) if return_y else (q, sc, zp)
 
 
+def cross_attention_quantize_dynamic(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
+                                     heads: int, return_y: bool = False):
+    """softmax(q k^T / sqrt(64)) v per head (head dim 64, <= 96 context tokens) + dynamic
+    quantisation of the result for attn2.to_out: an attention kernel that also publishes min/max
+    partials, then the single-pass quantiser. q [B,T,C], k / v [B,Lk,C] fp16 with unit inner stride
+    (k / v may be column slices of a wider matrix). Returns (o int8 [B,T,C], scale, zp[, o fp16])."""
+    b, t, c = q.shape
+    lk = k.shape[1]
+    _check(q.dtype == torch.float16 and k.dtype == torch.float16 and v.dtype == torch.float16,
+           "cross_attention_quantize_dynamic expects fp16")
+    _check(c == heads * 64 and lk <= 96 and k.shape == v.shape and k.shape[0] == b and k.shape[2] == c,
+           "cross_attention_quantize_dynamic: head dim 64, <= 96 context tokens")
+    if q.stride(2) != 1:
+        q = q.contiguous()
+    if k.stride(2) != 1:
+        k = k.contiguous()
+    if v.stride(2) != 1:
+        v = v.contiguous()
+    o = torch.empty((b, t, c), dtype=torch.float16, device=q.device)
+    o8 = torch.empty((b, t, c), dtype=torch.int8, device=q.device)
+    qp, sc, zp = _qp_pair(q.device)
+    lib = _lib.load()
+    with _DeviceGuard(q):
+        ws = _dynamic_workspace(q.device)
+        _launch("attn_cross", lib.mixdq_cross_attn_d64_f16,
+                (q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
+                 v.data_ptr(), v.stride(1), v.stride(0), o.data_ptr(), b, t, lk, heads, 0.125,
+                 ws.data_ptr()), q, keep=(q, k, v, o, ws),
+                algo_bytes=2 * (2 * b * t * c + 2 * b * lk * c))
+        _launch("quant_premm", lib.mixdq_quant_i8_premm,
+                (o.data_ptr(), o.numel(), o8.data_ptr(), qp.data_ptr(), qp.data_ptr() + 4,
+                 ws.data_ptr()), o, keep=(o, o8, qp, ws), algo_bytes=3 * o.numel())
+    return (o8, sc, zp, o) if return_y else (o8, sc, zp)
+
+
 def groupnorm_quantize_dynamic(x: torch.Tensor, num_groups: int, weight: torch.Tensor,
                                bias: torch.Tensor, eps: float, silu: bool, return_y: bool = False):
     """GroupNorm [+ SiLU] + dynamic quantisation in one kernel. x: fp16 logical [N,C,H,W] in
