@@ -619,7 +619,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       //      while chunk c+1 is being dequantised. Only __syncwarp is needed.
       const int row = quarter * 32 + lane;
       const RowInfo ri = row_info<KIND>(p, row, m0, tn0, tp0, tq0);
-      constexpr int CH = (BN >= 32) ? 32 : 16;
+      constexpr int CH = (BN >= 128) ? 32 : 16;   // narrow tiles: 16-column chunks keep all 8 epilogue warps busy
       constexpr int NCH = BN / CH;
       constexpr int LPR = CH / 8;                  // lanes (16-byte chunks) per row of a chunk
       constexpr int RPI = 32 / LPR;                // rows per copy-out instruction
@@ -719,7 +719,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (is_epi) {
       const int row = quarter * 32 + lane;
       int32_t* my = ws_tile + static_cast<int64_t>(krank) * (BLOCK_M * BN);
-      constexpr int CH = (BN >= 32) ? 32 : 16;
+      constexpr int CH = (BN >= 128) ? 32 : 16;   // narrow tiles: 16-column chunks keep all 8 epilogue warps busy
       constexpr int NCH = BN / CH;
       const int c_lo = (NCH >= 2) ? ehalf * (NCH / 2) : 0;
       const int c_hi = (NCH >= 2) ? c_lo + NCH / 2 : (ehalf == 0 ? 1 : 0);
