@@ -119,7 +119,9 @@ struct TcKsub { static constexpr int value = (BN <= 128) ? 2 : 1; };
 // Two MMA-issuing warps, alternating ring stages, each with its OWN TMEM accumulator (summed
 // exactly in the epilogue: int32 addition is associative). The issuing thread is blocked while its
 // MMA executes, so one warp's barrier bookkeeping overlaps the other warp's MMAs and the tensor
-// pipe stays busy. Narrow tiles only (2 x BN TMEM columns; the wide tiles are pipe-bound anyway).
+// pipe stays busy. Narrow tiles only: the 160-wide GEGLU tile was tried (2 x 160 TMEM columns, 4
+// stages instead of 5) and gained nothing — its mainloop streams 13 MB of weights and is bound by
+// the loads, not by the issuer.
 template <int BN, int KIND>
 struct TcDual { static constexpr bool value = (BN <= 64) && (KIND != 2 /*KIND_SPLIT*/); };
 
