@@ -77,15 +77,80 @@ simt_gemm_kernel(SimtGemmArgs g) {
   g.D[static_cast<int64_t>(m) * g.ldd + n] = h;
 }
 
+// Few output channels (SDXL conv_out: K = 4, C = 320): one WARP per output pixel, the lanes split
+// the (tap, 16-channel chunk) items of the reduction and shuffle-add their INT32 partials (exact,
+// order-independent); lane k < K finishes channel k with the same epilogue as below. The
+// one-thread-per-(pixel, channel) kernel left 28 of 32 lanes idle there (35 us per launch).
+__global__ void __launch_bounds__(256)
+simt_conv_smallk_kernel(SimtConvArgs c) {
+  const int lane = threadIdx.x & 31;
+  const unsigned int pix = blockIdx.x * 8u + (threadIdx.x >> 5);
+  const unsigned int npix = static_cast<unsigned int>(c.N) * c.P * c.Q;
+  if (pix >= npix) return;
+  const int q = pix % c.Q;
+  const int p = (pix / c.Q) % c.P;
+  const int n = pix / (static_cast<unsigned int>(c.Q) * c.P);
+  const int h0 = p * c.stride - c.pad, w0 = q * c.stride - c.pad;
+  const int chunks = c.C >> 4;
+  const int items = c.R * c.S * chunks;
+  int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int it = lane; it < items; it += 32) {
+    const int tap = it / chunks, ch = it - tap * chunks;
+    const int r = tap / c.S, s = tap - r * c.S;
+    const int h = h0 + r, w = w0 + s;
+    if (h < 0 || h >= c.H || w < 0 || w >= c.W) continue;
+    const int4 x = __ldg(reinterpret_cast<const int4*>(
+                             c.x + ((static_cast<int64_t>(n) * c.H + h) * c.W + w) * c.x_cpitch) + ch);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < c.K) {
+        const int4 y = __ldg(reinterpret_cast<const int4*>(
+                                 c.w + ((static_cast<int64_t>(k) * c.R + r) * c.S + s) * c.C) + ch);
+        acc[k] = __dp4a(x.x, y.x, acc[k]);
+        acc[k] = __dp4a(x.y, y.y, acc[k]);
+        acc[k] = __dp4a(x.z, y.z, acc[k]);
+        acc[k] = __dp4a(x.w, y.w, acc[k]);
+      }
+    }
+  }
+  int mine = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == k) mine = v;
+  }
+  if (lane >= c.K) return;
+  const int k = lane;
+  float wacc = 0.f;
+  if (c.wsum_krs) {
+    for (int r = 0; r < c.R; ++r) {
+      const int h = h0 + r;
+      if (h < 0 || h >= c.H) continue;
+      for (int s = 0; s < c.S; ++s) {
+        const int w = w0 + s;
+        if (w < 0 || w >= c.W) continue;
+        wacc = __fadd_rn(wacc, __ldg(c.wsum_krs + (static_cast<int64_t>(k) * c.R + r) * c.S + s));
+      }
+    }
+  }
+  if (c.acc_out) c.acc_out[static_cast<int64_t>(pix) * c.K + k] = mine;
+  const float b0 = c.wsum_krs ? __fmul_rn(wacc, __ldg(c.zp)) : __ldg(c.bias0_k + k);
+  float f = dequant_f32(mine, b0, __ldg(c.scale + k));
+  if (c.bias) f = __fadd_rn(f, __half2float(c.bias[k]));
+  c.y[static_cast<int64_t>(pix) * c.K + k] = __float2half_rn(f);
+}
+
 __global__ void __launch_bounds__(256)
 simt_conv_kernel(SimtConvArgs c) {
   const int k = blockIdx.y * 32 + (threadIdx.x & 31);
-  const int64_t pix = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  const int64_t npix = static_cast<int64_t>(c.N) * c.P * c.Q;
+  const unsigned int pix = blockIdx.x * 8u + (threadIdx.x >> 5);     // launch checks npix < 2^31
+  const unsigned int npix = static_cast<unsigned int>(c.N) * c.P * c.Q;
   if (k >= c.K || pix >= npix) return;
-  const int q = static_cast<int>(pix % c.Q);
-  const int p = static_cast<int>((pix / c.Q) % c.P);
-  const int n = static_cast<int>(pix / (static_cast<int64_t>(c.Q) * c.P));
+  const int q = pix % c.Q;
+  const int p = (pix / c.Q) % c.P;
+  const int n = pix / (static_cast<unsigned int>(c.Q) * c.P);
   const int h0 = p * c.stride - c.pad, w0 = q * c.stride - c.pad;
   const bool v16 = (c.C % 16 == 0) && (c.x_cpitch % 16 == 0) &&
                    ((reinterpret_cast<uintptr_t>(c.x) | reinterpret_cast<uintptr_t>(c.w)) & 15) == 0;
@@ -103,12 +168,12 @@ simt_conv_kernel(SimtConvArgs c) {
       if (c.wsum_krs) wacc = __fadd_rn(wacc, __ldg(c.wsum_krs + (static_cast<int64_t>(k) * c.R + r) * c.S + s));
     }
   }
-  if (c.acc_out) c.acc_out[pix * c.K + k] = acc;
+  if (c.acc_out) c.acc_out[static_cast<int64_t>(pix) * c.K + k] = acc;
   // zero-point propagation: float(acc_w) * zp (conv_act_zero_point_propagate.cu:35-49)
   const float b0 = c.wsum_krs ? __fmul_rn(wacc, __ldg(c.zp)) : __ldg(c.bias0_k + k);
   float f = dequant_f32(acc, b0, __ldg(c.scale + k));
   if (c.bias) f = __fadd_rn(f, __half2float(c.bias[k]));
-  c.y[pix * c.K + k] = __float2half_rn(f);
+  c.y[static_cast<int64_t>(pix) * c.K + k] = __float2half_rn(f);
 }
 
 int simt_gemm_launch(const SimtGemmArgs& g, cudaStream_t st) {
@@ -121,8 +186,13 @@ int simt_gemm_launch(const SimtGemmArgs& g, cudaStream_t st) {
 int simt_conv_launch(const SimtConvArgs& c, cudaStream_t st) {
   const int64_t npix = static_cast<int64_t>(c.N) * c.P * c.Q;
   dim3 grid(static_cast<unsigned>((npix + 7) / 8), (c.K + 31) / 32);
-  if (grid.y > 65535 || (npix + 7) / 8 > 2147483647LL) return -1;
-  simt_conv_kernel<<<grid, 256, 0, st>>>(c);
+  if (grid.y > 65535 || npix > 2147483647LL) return -1;
+  const bool v16 = (c.C % 16 == 0) && (c.x_cpitch % 16 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(c.x) | reinterpret_cast<uintptr_t>(c.w)) & 15) == 0;
+  if (c.K <= 8 && v16)
+    simt_conv_smallk_kernel<<<dim3(grid.x), 256, 0, st>>>(c);
+  else
+    simt_conv_kernel<<<grid, 256, 0, st>>>(c);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
