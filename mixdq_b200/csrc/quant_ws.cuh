@@ -332,11 +332,17 @@ inline int max_cluster_ctas(K kern, int threads, int smem) {
 inline int& partial_count_slot(const void* ws) {
   static const void* keys[32] = {nullptr};
   static int vals[32] = {0};
+  static int next_victim = 0;
   for (int i = 0; i < 32; ++i) {
     if (keys[i] == ws) return vals[i];
     if (keys[i] == nullptr) { keys[i] = ws; return vals[i]; }
   }
-  return vals[31];
+  // more than 32 live workspaces (one per device x stream): recycle round-robin — a producer
+  // always writes its entry right before its consumer reads it
+  const int v = next_victim++ & 31;
+  keys[v] = ws;
+  vals[v] = 0;
+  return vals[v];
 }
 
 // Experiment hook: MIXDQ_CARVEOUT=<percent> pins the shared-memory carve-out preference of the
