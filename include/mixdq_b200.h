@@ -68,8 +68,10 @@ void        mixdq_debug_set_cluster(int on);
 /* Form of the dynamic quantisers: 1 (default) = a min/max pass + a quantise pass chained by
    programmatic dependent launch; 2 = lean one-kernel form (values in registers, tagged-partial
    grid barrier) where the tensor fits a co-resident grid (faster in isolation, slower inside the
-   whole-UNet graph: see profiles/README.md); 0 = first-generation single kernels with the counter
-   barrier. Identical results in every mode; A/B timing and test aid (env MIXDQ_QUANT_MODE). */
+   whole-UNet graph: see profiles/README.md); 3 = compact one-cluster kernels (DSMEM + hardware
+   cluster barrier) where the tensor fits 16 CTAs' registers (also slower inside the graph);
+   0 = first-generation single kernels with the counter barrier. Identical results in every mode;
+   A/B timing and test aid (env MIXDQ_QUANT_MODE). */
 void        mixdq_debug_set_two_pass(int mode);
 /* Point the dynamic-quantisation workspace `ws` at a device buffer of
    launches x 1024 CTAs x 8 uint64 (or NULL = off): every quantiser launch that uses `ws` then

@@ -272,17 +272,21 @@ int mixdq_q2_premm(const __half* x, int64_t numel, int8_t* q, float* scale_out, 
 // pass + quantise pass, 2 = additionally the lean one-kernel form (tagged-partial barrier) for
 // tensors that fit the registers of one co-resident grid: 1.5 us of barrier in an isolated chain
 // (tools/quant_phase.py) but 8.8 us per kernel inside the whole-UNet graph (9.06 vs 7.87 ms per
-// step), so it is not the default. MIXDQ_QUANT_MODE / mixdq_debug_set_two_pass select the mode.
+// step), so it is not the default; 3 = compact ONE-CLUSTER kernels (16 CTAs x 512 threads, values
+// in registers, DSMEM + hardware cluster barrier) where the tensor fits: 9.1 us (LayerNorm) / 6.4
+// us (plain) per kernel inside the graph (8.16 ms per step) — gang-scheduling 16 CTAs into one GPC
+// while early-launched GEMM CTAs hold most SMs costs more than a kernel boundary.
+// MIXDQ_QUANT_MODE / mixdq_debug_set_two_pass select the mode.
 static int g_two_pass = -1;
 int mixdq_quant_mode() {
   if (g_two_pass < 0) {
     const char* e = getenv("MIXDQ_QUANT_MODE");
-    g_two_pass = (e && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : 1;
+    g_two_pass = (e && e[0] >= '0' && e[0] <= '3') ? (e[0] - '0') : 1;
   }
   return g_two_pass;
 }
 bool mixdq_two_pass_enabled() { return mixdq_quant_mode() != 0; }
-extern "C" void mixdq_debug_set_two_pass(int mode) { g_two_pass = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
+extern "C" void mixdq_debug_set_two_pass(int mode) { g_two_pass = mode < 0 ? 0 : (mode > 3 ? 3 : mode); }
 
 extern "C" void mixdq_debug_set_cluster(int on) { cluster_mode_flag() = on ? 1 : 0; }
 // profiling: point the workspace at a stamp buffer (or NULL) and restart the launch sequence;

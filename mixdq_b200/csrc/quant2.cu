@@ -575,6 +575,151 @@ ln_quant_lean_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
   dbg.end(ws);
 }
 
+// ---------------------------------------------------------------------------------------------
+// ONE-CLUSTER variants (mode 3): the whole tensor in the registers of one thread-block cluster of
+// 16 (or 8) CTAs x 512 threads; min/max meet through distributed shared memory and the hardware
+// cluster barrier (~0.2 us), so a quantisation is a single short kernel with no global
+// synchronisation at all. The first attempt at this (quant.cu / fused_quant.cu, 50 KB kernels with
+// an IEEE division per element) was issue-bound on 16 SMs (7.5-10 us); with the compact quantiser
+// (~12 instructions per element) the same 0.33 M elements are ~1 us of issue time on 16 SMs.
+// ---------------------------------------------------------------------------------------------
+constexpr int kClThreads = 512;
+constexpr int kClVec = 6;            // 16-byte vectors per thread
+
+__global__ void __launch_bounds__(kClThreads)
+quant_cluster_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int nchunks,
+                     unsigned int items, int8_t* __restrict__ q, float* __restrict__ scale_out,
+                     float* __restrict__ zp_out) {
+  pdl_launch_dependents();
+  cluster_enter();
+  pdl_wait();
+  const unsigned int stride = gridDim.x * kClThreads;
+  const unsigned int i0 = blockIdx.x * kClThreads + threadIdx.x;
+  int4 v[kClVec];
+  float mn = 0.f, mx = 0.f;
+  {
+    __half2 mn2 = __float2half2_rn(0.0f), mx2 = mn2;
+#pragma unroll
+    for (int u = 0; u < kClVec; ++u) {
+      const unsigned int it = i0 + u * stride;
+      v[u] = make_int4(0, 0, 0, 0);
+      if (it < items) {
+        const unsigned int r = it / nchunks;
+        v[u] = __ldcg(reinterpret_cast<const int4*>(x + static_cast<int64_t>(r) * ldx) + (it - r * nchunks));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kClVec; ++u) hminmax8(v[u], mn2, mx2);   // zero vectors keep min <= 0 <= max
+    mn = fminf(__low2float(mn2), __high2float(mn2));
+    mx = fmaxf(__low2float(mx2), __high2float(mx2));
+  }
+  float delta, z;
+  cluster_minmax_params<kClThreads>(mn, mx, scale_out, zp_out, delta, z);
+  const float inv = __frcp_rn(delta);
+  uint2* qv = reinterpret_cast<uint2*>(q);
+#pragma unroll 1
+  for (int u = 0; u < kClVec; ++u) {       // rotate: one inlined copy of the quantiser
+    const unsigned int it = i0 + u * stride;
+    if (it < items) qv[it] = quant8_compact(v[0], delta, inv, z);
+#pragma unroll
+    for (int j = 0; j + 1 < kClVec; ++j) v[j] = v[j + 1];
+  }
+}
+
+// LayerNorm -> int8, one row per warp, 16 rows per CTA
+template <int MAXCH>
+__global__ void __launch_bounds__(kClThreads)
+ln_quant_cluster_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
+                        const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                        float eps, int8_t* __restrict__ q, __half* __restrict__ y_out,
+                        float* __restrict__ scale_out, float* __restrict__ zp_out) {
+  pdl_launch_dependents();
+  cluster_enter();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = C >> 3;
+  const int r = blockIdx.x * (kClThreads / 32) + warp;
+  pdl_wait();
+  __half2 mn2 = __float2half2_rn(0.0f), mx2 = mn2;
+  int4 out[MAXCH];
+  if (r < M) {
+    const int4* xrow = reinterpret_cast<const int4*>(x + static_cast<int64_t>(r) * ldx);
+    int4 raw[MAXCH];
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i)
+      if (lane + 32 * i < nchunks) raw[i] = __ldcg(xrow + lane + 32 * i);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) {
+      if (lane + 32 * i < nchunks) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h2[j]);
+          sum += f.x;
+          sum += f.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / static_cast<float>(C);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) {
+      if (lane + 32 * i < nchunks) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h2[j]);
+          const float d0 = f.x - mean, d1 = f.y - mean;
+          ss += d0 * d0;
+          ss += d1 * d1;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / static_cast<float>(C) + eps);
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) {
+        const int4 gr = __ldg(reinterpret_cast<const int4*>(gamma) + c);
+        const int4 br = __ldg(reinterpret_cast<const int4*>(beta) + c);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[i]);
+        const __half2* g2 = reinterpret_cast<const __half2*>(&gr);
+        const __half2* b2 = reinterpret_cast<const __half2*>(&br);
+        __half2* o2 = reinterpret_cast<__half2*>(&out[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h2[j]);
+          const float2 g = __half22float2(g2[j]);
+          const float2 b = __half22float2(b2[j]);
+          o2[j] = __floats2half2_rn(fmaf(g.x, rstd * (f.x - mean), b.x),
+                                    fmaf(g.y, rstd * (f.y - mean), b.y));
+        }
+        hminmax8(out[i], mn2, mx2);
+        if (y_out) reinterpret_cast<int4*>(y_out + static_cast<int64_t>(r) * C)[c] = out[i];
+      }
+    }
+  }
+  float delta, z;
+  cluster_minmax_params<kClThreads>(fminf(__low2float(mn2), __high2float(mn2)),
+                                    fmaxf(__low2float(mx2), __high2float(mx2)), scale_out, zp_out,
+                                    delta, z);
+  if (r < M) {
+    const float inv = __frcp_rn(delta);
+    uint2* qrow = reinterpret_cast<uint2*>(q + static_cast<int64_t>(r) * C);
+#pragma unroll 1
+    for (int i = 0; i < MAXCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) qrow[c] = quant8_compact(out[0], delta, inv, z);
+#pragma unroll
+      for (int j = 0; j + 1 < MAXCH; ++j) out[j] = out[j + 1];
+    }
+  }
+}
+
 static inline int grid_for2(int64_t items, int per_block, int max_blocks) {
   int64_t g = (items + per_block - 1) / per_block;
   if (g < 1) g = 1;
@@ -602,6 +747,20 @@ int mixdq_q2_rows(const __half* x, int64_t ldx, int64_t M, int cols, int8_t* q, 
   const unsigned int nchunks = (ldx == cols) ? static_cast<unsigned int>(items)
                                              : static_cast<unsigned int>(cols >> 3);
   const unsigned int n = static_cast<unsigned int>(items);
+  // one-cluster form: the tensor fits the registers of 16 (8) CTAs x 512 threads x 6 vectors
+  if (mixdq_quant_mode() == 3) {
+    static int ncl = -1;
+    if (ncl < 0) ncl = max_cluster_ctas(quant_cluster_kernel, kClThreads, 0);
+    if (ncl > 0 && items <= static_cast<int64_t>(ncl) * kClThreads * kClVec) {
+      int g = static_cast<int>((items + kClThreads * kClVec - 1) / (kClThreads * kClVec));
+      // use the whole cluster: more SMs, fewer vectors per thread
+      g = ncl;
+      if (launch_cluster_pdl(quant_cluster_kernel, g, kClThreads, 0, st, x, ldx, nchunks, n, q,
+                             scale_out, zp_out) != cudaSuccess)
+        return MIXDQ_ERR_CUDA;
+      return MIXDQ_OK;
+    }
+  }
   // register-resident one-kernel form: <= 2 vectors per thread on a co-resident grid
   // (256-thread CTAs without shared memory: 4 per SM is always resident)
   if (mixdq_quant_mode() == 2 && items <= static_cast<int64_t>(148) * 4 * kQ2Threads * 2) {
@@ -646,6 +805,24 @@ int mixdq_q2_ln(const __half* x, int64_t ldx, int M, int C, const __half* gamma,
   DynWs* w = static_cast<DynWs*>(ws);
   cudaError_t e;
   int g1;
+  // one-cluster form: one row per warp, 16 warps per CTA
+  if (mixdq_quant_mode() == 3) {
+    static int ncl = -1;
+    if (ncl < 0) {
+      const int a = max_cluster_ctas(ln_quant_cluster_kernel<5>, kClThreads, 0);
+      const int b = max_cluster_ctas(ln_quant_cluster_kernel<8>, kClThreads, 0);
+      ncl = a < b ? a : b;
+    }
+    if (ncl > 0 && M <= ncl * (kClThreads / 32)) {
+      const int g = (M + kClThreads / 32 - 1) / (kClThreads / 32);
+      e = (C <= 5 * 256)
+              ? launch_cluster_pdl(ln_quant_cluster_kernel<5>, g, kClThreads, 0, st, x, ldx, M, C,
+                                   gamma, beta, eps, q, y, scale_out, zp_out)
+              : launch_cluster_pdl(ln_quant_cluster_kernel<8>, g, kClThreads, 0, st, x, ldx, M, C,
+                                   gamma, beta, eps, q, y, scale_out, zp_out);
+      return e == cudaSuccess ? MIXDQ_OK : MIXDQ_ERR_CUDA;
+    }
+  }
   // one row per warp, the whole tensor in registers, lean barrier: M <= 148 CTAs x 8 warps
   if (mixdq_quant_mode() == 2 && M <= 148 * 8) {
     if (M <= 296) {

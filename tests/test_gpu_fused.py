@@ -159,10 +159,13 @@ def test_two_pass_and_single_kernel_quantisers_agree(ops, dev):
         memory_format=torch.channels_last)
     outs = []
     try:
-        for mode in (0, 1, 2, 0, 2, 1):
+        for mode in (0, 1, 2, 3, 0, 3, 2, 1):
             lib.mixdq_debug_set_two_pass(mode)
             ops.clear_dynamic_quant_cache()
             o = list(ops.layernorm_quantize_dynamic(x, w, b, 1e-5, return_y=True))
+            o += list(ops.layernorm_quantize_dynamic(x[:256], w, b, 1e-5, return_y=True))   # one cluster
+            o += list(ops.quantize_per_tensor_dynamic(x[:400].clone()))
+            o += list(ops.quantize_rows_dynamic(wide[:200, 640:]))
             o += list(ops.quantize_per_tensor_dynamic(x.clone()))
             o += list(ops.quantize_rows_dynamic(wide[:, 640:]))
             o += list(ops.groupnorm_quantize_dynamic(img, 32, w, b, 1e-5, True, return_y=True))
