@@ -169,6 +169,10 @@ quant_rows_premm_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int 
   __shared__ float s_mn[kQ2Threads / 32], s_mx[kQ2Threads / 32];
   QDbg dbg;
   dbg.begin(ws);
+  // dependents may launch right away. Triggering later was tried (after the dependency wait, after
+  // the first loads, after the parameters, after the quantise loop): same-box A/B runs gave
+  // 7.38-7.50 ms/step for this placement against 7.54 / 7.57 / 7.93 / 8.15.
+  pdl_launch_dependents();
   const unsigned int stride = gridDim.x * kQ2Threads;
   unsigned int it = blockIdx.x * kQ2Threads + threadIdx.x;
   if (it < items) {
@@ -184,13 +188,6 @@ quant_rows_premm_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int 
     const unsigned int r = it / nchunks;
     v = __ldcg(reinterpret_cast<const int4*>(x + static_cast<int64_t>(r) * ldx) + (it - r * nchunks));
   }
-  // Let the consumer GEMM launch only NOW (not at kernel entry): its CTAs — 352 threads, up to
-  // 200 KB of shared memory, ~45 K registers each — then arrive after this kernel's own CTAs have
-  // all started and passed their dependency wait, instead of competing with them for SMs, and
-  // still early enough for its weight prefetch to overlap the quantisation. Measured (ms/step):
-  // trigger at entry 7.47, here 7.32, after the quantise loop 8.15; the same move in the min/max
-  // and LayerNorm passes (whose dependent is this small kernel) loses: 7.55.
-  pdl_launch_dependents();
   float mn = 0.0f, mx = 0.0f;
 #pragma unroll 1
   for (int i = threadIdx.x; i < nparts; i += kQ2Threads) {
