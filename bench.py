@@ -293,7 +293,7 @@ def capture(unet, inputs):
     mixdq.cuda_graph_opt(unet)
     with torch.no_grad():
         unet(**inputs)
-    (static_in, graph, static_out) = next(iter(unet.forward._cached.values()))
+    (static_in, graph, static_out, _stream) = next(iter(unet.forward._cached.values()))
     return graph, static_out
 
 

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MIXDQ_ABI_VERSION 1
+#define MIXDQ_ABI_VERSION 2
 
 /* error codes */
 #define MIXDQ_OK                 0
@@ -36,11 +36,16 @@ typedef void* mixdq_stream_t;      /* a cudaStream_t */
 typedef uint16_t mixdq_half_t;     /* IEEE binary16 bit pattern (__half)  */
 
 int         mixdq_abi_version(void);
-/* Register a device scratch buffer (caller-owned, >= 16-byte aligned) for CUDA device `device`:
-   split-K launches exchange their partial INT32 tiles through it (it stays L2-resident). Without
-   a workspace the contraction kernels never split K. Launches on different streams of one device
-   must not run concurrently while sharing a workspace. NULL / 0 unregisters. */
-int         mixdq_set_workspace(int device, void* ptr, int64_t bytes);
+/* Register a device scratch buffer (caller-owned, >= 16-byte aligned) for launches on `stream` of
+   CUDA device `device`: split-K launches exchange their partial INT32 tiles through it (it stays
+   L2-resident). A launch only ever uses the workspace registered for ITS stream, so concurrent
+   streams cannot corrupt each other's partial tiles; without a workspace for the stream the
+   contraction kernels never split K. NULL / 0 unregisters. Thread-safe. */
+int         mixdq_set_workspace(int device, mixdq_stream_t stream, void* ptr, int64_t bytes);
+/* *id_out = 0 when `stream` is not being captured into a CUDA graph, else the unique id of the
+   capture sequence. Host-side caches of device results key on it: a value computed eagerly must
+   not be reused inside a capture (its producing kernels would be missing from the graph). */
+int         mixdq_stream_capture_id(mixdq_stream_t stream, unsigned long long* id_out);
 const char* mixdq_strerror(int code);
 /* Name of the kernel family the last call on this thread dispatched to ("tcgen05", "simt", ...).
    Test/diagnostic aid only. */

@@ -12,11 +12,12 @@ from ctypes import c_char_p, c_int, c_int32, c_int64, c_void_p, POINTER
 from pathlib import Path
 
 _LIB = None
+ABI_VERSION = 2
 LIB_PATH = Path(__file__).resolve().parent / "libmixdq_b200.so"
 
 # every symbol include/mixdq_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "mixdq_abi_version", "mixdq_set_workspace", "mixdq_debug_set_pdl", "mixdq_strerror", "mixdq_last_path", "mixdq_force_simt",
+    "mixdq_abi_version", "mixdq_set_workspace", "mixdq_stream_capture_id", "mixdq_debug_set_pdl", "mixdq_strerror", "mixdq_last_path", "mixdq_force_simt",
     "mixdq_debug_force_bn", "mixdq_debug_force_splits", "mixdq_debug_set_timing_buffer",
     "mixdq_debug_set_mode", "mixdq_debug_set_cluster", "mixdq_debug_set_two_pass", "mixdq_debug_set_quant_timing_buffer",
     "mixdq_quant_i8_static", "mixdq_quant_i8_static_strided", "mixdq_quant_i8_nchw2nhwc",
@@ -38,7 +39,9 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mixdq_abi_version.restype = c_int
     lib.mixdq_abi_version.argtypes = []
     lib.mixdq_set_workspace.restype = c_int
-    lib.mixdq_set_workspace.argtypes = [c_int, P, c_int64]
+    lib.mixdq_set_workspace.argtypes = [c_int, P, P, c_int64]
+    lib.mixdq_stream_capture_id.restype = c_int
+    lib.mixdq_stream_capture_id.argtypes = [P, POINTER(ctypes.c_uint64)]
     lib.mixdq_debug_set_pdl.restype = None
     lib.mixdq_debug_set_pdl.argtypes = [c_int]
     lib.mixdq_strerror.restype = c_char_p
@@ -144,7 +147,7 @@ def load() -> ctypes.CDLL:
         if not hasattr(lib, sym):
             raise MixdqLibraryError(f"{path} does not export {sym}")
     _declare(lib)
-    if lib.mixdq_abi_version() != 1:
+    if lib.mixdq_abi_version() != ABI_VERSION:
         raise MixdqLibraryError("ABI version mismatch")
     _LIB = lib
     return lib
@@ -155,6 +158,13 @@ def check(code: int) -> None:
     if code != 0:
         msg = load().mixdq_strerror(code).decode()
         raise RuntimeError(msg)
+
+
+def capture_id(stream: int) -> int:
+    """0 outside CUDA-graph capture, else the id of the capture sequence `stream` belongs to."""
+    out = ctypes.c_uint64(0)
+    check(load().mixdq_stream_capture_id(stream, ctypes.byref(out)))
+    return int(out.value)
 
 
 def last_path() -> str:

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 
 #include "../../include/mixdq_b200.h"
 #include "simt.h"
@@ -142,20 +143,53 @@ static int g_force_splits = 0;
 int g_use_pdl_fwd = 1;
 extern "C" void mixdq_debug_set_pdl(int on) { g_use_pdl_fwd = on; }
 
-// split-K exchange workspace (registered by the host side; one per device)
-static int32_t* g_ws[64] = {nullptr};
-static int64_t g_ws_bytes[64] = {0};
-extern "C" int mixdq_set_workspace(int device, void* ptr, int64_t bytes) {
-  if (device < 0 || device >= 64 || bytes < 0) return MIXDQ_ERR_INVALID_ARG;
-  g_ws[device] = static_cast<int32_t*>(ptr);
-  g_ws_bytes[device] = ptr ? bytes : 0;
+// split-K exchange workspaces, registered by the host side: one per (device, stream). A launch on
+// stream S only ever uses the workspace registered for S (no registration -> no split-K), so two
+// streams can never corrupt each other's partial tiles.
+struct WsEntry { int device; cudaStream_t stream; int32_t* ptr; int64_t bytes; };
+static WsEntry g_ws_tab[256];
+static int g_ws_n = 0;
+static std::mutex g_ws_mu;
+extern "C" int mixdq_set_workspace(int device, mixdq_stream_t stream, void* ptr, int64_t bytes) {
+  if (device < 0 || bytes < 0) return MIXDQ_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lock(g_ws_mu);
+  for (int i = 0; i < g_ws_n; ++i) {
+    if (g_ws_tab[i].device == device && g_ws_tab[i].stream == st) {
+      if (ptr) { g_ws_tab[i].ptr = static_cast<int32_t*>(ptr); g_ws_tab[i].bytes = bytes; }
+      else { g_ws_tab[i] = g_ws_tab[--g_ws_n]; }
+      return MIXDQ_OK;
+    }
+  }
+  if (!ptr) return MIXDQ_OK;
+  if (g_ws_n >= 256) return MIXDQ_ERR_WORKSPACE;
+  g_ws_tab[g_ws_n++] = WsEntry{device, st, static_cast<int32_t*>(ptr), bytes};
   return MIXDQ_OK;
 }
-static int64_t current_ws(int32_t** ptr) {
+static int64_t current_ws(cudaStream_t st, int32_t** ptr) {
+  *ptr = nullptr;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { *ptr = nullptr; return 0; }
-  *ptr = g_ws[dev];
-  return g_ws_bytes[dev];
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  std::lock_guard<std::mutex> lock(g_ws_mu);
+  for (int i = 0; i < g_ws_n; ++i)
+    if (g_ws_tab[i].device == dev && g_ws_tab[i].stream == st) {
+      *ptr = g_ws_tab[i].ptr;
+      return g_ws_tab[i].bytes;
+    }
+  return 0;
+}
+// 0 when `stream` is not being captured into a CUDA graph, else the capture sequence's unique id.
+extern "C" int mixdq_stream_capture_id(mixdq_stream_t stream, unsigned long long* id_out) {
+  if (!id_out) return MIXDQ_ERR_INVALID_ARG;
+  cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+  unsigned long long id = 0;
+  if (cudaStreamGetCaptureInfo(static_cast<cudaStream_t>(stream), &status, &id) != cudaSuccess) {
+    cudaGetLastError();   // e.g. the legacy default stream while another stream captures
+    *id_out = 0ull;
+    return MIXDQ_OK;
+  }
+  *id_out = (status == cudaStreamCaptureStatusActive) ? id : 0ull;
+  return MIXDQ_OK;
 }
 extern "C" void mixdq_debug_force_bn(int bn) { g_force_bn = bn; }
 extern "C" void mixdq_debug_force_splits(int s) { g_force_splits = s; }
@@ -180,10 +214,10 @@ static inline bool valid_bn(int bn) {
   return bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256;
 }
 
-static void pick_tile(int m_tiles, int N, int total_kb, bool allow_split, int* bn_out,
-                      int* splits_out) {
+static void pick_tile(int m_tiles, int N, int total_kb, bool allow_split, cudaStream_t st,
+                      int* bn_out, int* splits_out) {
   int32_t* ws_ptr = nullptr;
-  const int64_t ws_bytes = current_ws(&ws_ptr);
+  const int64_t ws_bytes = allow_split ? current_ws(st, &ws_ptr) : 0;
   if (g_force_bn < 0) {
     const char* e = getenv("MIXDQ_FORCE_BN");
     g_force_bn = e ? atoi(e) : 0;
@@ -268,7 +302,7 @@ static int gemm_common(const int8_t* A, int64_t lda, const int8_t* W, const floa
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
   int bn, splits;
-  pick_tile(m_tiles, N, num_kb, true, &bn, &splits);
+  pick_tile(m_tiles, N, num_kb, true, st, &bn, &splits);
   CUtensorMap tmA, tmW;
   if (!make_tmap_2d(&tmA, A, K, M, lda, BLOCK_M)) return MIXDQ_ERR_CUDA;
   if (!make_tmap_2d(&tmW, W, K, N, K, bn)) return MIXDQ_ERR_CUDA;
@@ -277,7 +311,7 @@ static int gemm_common(const int8_t* A, int64_t lda, const int8_t* W, const floa
   p.dbg_mode = g_dbg_mode;
   p.a_prefetch = a_prefetch_flag();
   p.splits = splits;
-  current_ws(&p.ws);
+  current_ws(st, &p.ws);
   p.M = M; p.N = N; p.num_kb = num_kb;
   p.scale = p_scale; p.bias0 = p_bias0; p.a_scale = a_scale; p.a_zp = a_zp;
   p.bias = reinterpret_cast<const __half*>(bias);
@@ -329,7 +363,7 @@ extern "C" int mixdq_gemm_w8a8_geglu_f16_dyn(const int8_t* A, int64_t lda, const
   // batch-1 projection (2 x 64 tiles) on one wave of 128 CTAs
   int bn = 32;
   {
-    if (g_force_bn < 0) { int d0, d1; pick_tile(1, 32, 1, false, &d0, &d1); }   // reads the env
+    if (g_force_bn < 0) { int d0, d1; pick_tile(1, 32, 1, false, nullptr, &d0, &d1); }   // reads the env
     const int cands[5] = {256, 160, 128, 64, 32};
     const double main_ns[5] = {440.0, 280.0, 195.0, 112.0, 112.0};
     double best = 1e30;
@@ -421,7 +455,7 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
   // stride 2 (the down-samplers): the A box is fetched with TMA element strides (traversal
   // stride 2 along W and H), so the tile rows are still consecutive OUTPUT pixels
   const bool geom_ok = (stride == 1 || stride == 2) &&
-                       (pad == 0 || (pad == 1 && R == 3 && S == 3)) && Q <= 128;
+                       (pad == 0 || (pad == 1 && R == 3 && S == 3));
   const bool tc_ok = !g_force_simt && geom_ok && (C % 16 == 0) && (x_cpitch % 16 == 0) &&
                      (K % 8 == 0) && al16(x) && al16(w) && al16(y) && (!acc_out || al16(acc_out)) &&
                      (!chan_add || (al16(chan_add) && ldca % 8 == 0 && ldca >= K)) &&
@@ -440,15 +474,19 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
   }
 
   // A box: boxN x boxH x boxW output pixels (<= 128 rows of the UMMA tile)
-  int boxW = Q, boxH = BLOCK_M / boxW;
+  // (output rows wider than one tile — latents beyond 1024 px — are tiled along q as well)
+  int boxW = Q < BLOCK_M ? Q : BLOCK_M, boxH = BLOCK_M / boxW;
   if (boxH > P) boxH = P;
   int boxN = 1;
-  if (boxH == P) { boxN = BLOCK_M / (boxW * boxH); if (boxN > N) boxN = N; if (boxN < 1) boxN = 1; }
-  const int tilesQ = 1, tilesP = (P + boxH - 1) / boxH, tilesN = (N + boxN - 1) / boxN;
+  if (boxH == P && boxW == Q) {
+    boxN = BLOCK_M / (boxW * boxH); if (boxN > N) boxN = N; if (boxN < 1) boxN = 1;
+  }
+  const int tilesQ = (Q + boxW - 1) / boxW, tilesP = (P + boxH - 1) / boxH,
+            tilesN = (N + boxN - 1) / boxN;
   const int m_tiles = tilesQ * tilesP * tilesN;
   const int kb_per_tap = (C + BLOCK_K - 1) / BLOCK_K;
   int bn, splits;
-  pick_tile(m_tiles, K, R * S * kb_per_tap, true, &bn, &splits);
+  pick_tile(m_tiles, K, R * S * kb_per_tap, true, st, &bn, &splits);
 
   CUtensorMap tmA, tmW;
   {
@@ -473,7 +511,7 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
   p.dbg_mode = g_dbg_mode;
   p.a_prefetch = a_prefetch_flag();
   p.splits = splits;
-  current_ws(&p.ws);
+  current_ws(st, &p.ws);
   p.M = N * P * Q; p.N = K;
   p.kb_per_tap = kb_per_tap;
   p.num_kb = R * S * p.kb_per_tap;
@@ -549,8 +587,8 @@ static int split_common(const int8_t* xa, int64_t lda, const int8_t* wa, int Ca,
   }
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   int bn, splits_unused;
-  pick_tile(m_tiles, K, (Ca + BLOCK_K - 1) / BLOCK_K + (Cb + BLOCK_K - 1) / BLOCK_K, false, &bn,
-            &splits_unused);
+  pick_tile(m_tiles, K, (Ca + BLOCK_K - 1) / BLOCK_K + (Cb + BLOCK_K - 1) / BLOCK_K, false, st,
+            &bn, &splits_unused);
   if (bn > 128) bn = 128;  // two accumulators: 2 x BN TMEM columns, keep smem params small
   CUtensorMap tmA, tmW, tmA1, tmW1;
   if (!make_tmap_2d(&tmA, xa, Ca, M, lda, BLOCK_M) || !make_tmap_2d(&tmW, wa, Ca, K, Ca, bn) ||

@@ -123,9 +123,14 @@ class GegluLinear:
 class SharedInputGroup:
     """Layers of the whole UNet that consume one tensor (all attn2.to_k/to_v <- encoder hidden
     states; all resnet time_emb_proj <- silu(temb)): quantise once, one GEMM, hand out column
-    slices. The result is cached on the identity + version of the input tensor (held strongly, so
-    the id cannot be recycled); under CUDA-graph capture the Python runs once and the captured
-    kernels replay."""
+    slices.
+
+    The result is cached for the duration of ONE UNet forward: `fuse_unet` registers a forward
+    pre-hook on the UNet that calls `reset()`, and the key also carries the tensor's identity
+    (held strongly, so the id cannot be recycled), its version counter (where the tensor tracks
+    one) and the CUDA-graph capture id of the current stream. A value computed eagerly (e.g. in
+    the warm-up passes of `cuda_graph_opt`) is therefore never reused inside a capture — its
+    kernels would be missing from the graph and every replay would see the first prompt's K/V."""
 
     def __init__(self, mods: List[QuantizedLinear], pre=None, bos: bool = False):
         self.cat = CatLinear(mods)
@@ -137,8 +142,13 @@ class SharedInputGroup:
         self._key = None
         self._out = None
 
+    def reset(self) -> None:
+        self._key = None
+        self._out = None
+
     def get(self, mod, x: torch.Tensor) -> torch.Tensor:
-        if self._key is None or self._key[0] is not x or self._key[1] != x._version:
+        key = (x, ops._version_of(x), ops._capture_id(x.device))
+        if self._key is None or self._key[0] is not x or self._key[1:] != key[1:]:
             xin = self.pre(x) if self.pre is not None else x
             if self.bos:
                 xin = xin[:, 1:, :]
@@ -147,7 +157,7 @@ class SharedInputGroup:
             out = self.cat.run(q8, s, z)
             if self.bos:
                 out = torch.cat([self.bos_rows.expand(out.shape[0], -1, -1), out], dim=1)
-            self._key = (x, x._version)
+            self._key = key
             self._out = out
         i = self.index[id(mod)]
         off = self.cat.offsets[i]
@@ -225,16 +235,46 @@ def _attention(q, k, v, heads):
     return o.transpose(1, 2).reshape(b, t, h * d)
 
 
-def _ctx_of(args, kwargs):
+def _is_native(m) -> bool:
+    """True for the in-repo skeleton classes (mixdq_b200.unet); anything else with a diffusers
+    class name is called / answered with the diffusers conventions (keyword context, tuple or
+    output-class returns)."""
+    return type(m).__module__.startswith("mixdq_b200.")
+
+
+# call-time arguments of the diffusers block forwards that the fused forwards do not implement:
+# when any of them carries a value the original forward runs instead
+_UNSUPPORTED_KW = ("attention_mask", "encoder_attention_mask", "timestep", "class_labels",
+                   "added_cond_kwargs")
+
+
+def _needs_stock_forward(args, kwargs, n_pos_ok: int) -> bool:
+    if len(args) > n_pos_ok:
+        return any(a is not None for a in args[n_pos_ok:])
+    for k in _UNSUPPORTED_KW:
+        if kwargs.get(k) is not None:
+            return True
+    cak = kwargs.get("cross_attention_kwargs")
+    return bool(cak)
+
+
+def _ctx_of(self, args, kwargs):
+    """encoder_hidden_states of a block call: keyword, or positional (index 0 for the in-repo
+    skeleton `blk(x, ctx)`, index 1 for diffusers `blk(x, attention_mask, ctx, ...)`)."""
     if "encoder_hidden_states" in kwargs:
         return kwargs["encoder_hidden_states"]
-    return args[0] if args else None
+    if _is_native(self):
+        return args[0] if args else None
+    return args[1] if len(args) > 1 else None
 
 
 def fused_transformer_block_forward(self, hidden_states, *args, **kwargs):
     """BasicTransformerBlock: 14 kernels instead of ~30 (see module docstring)."""
     f = self._mixdq_fused
-    ctx = _ctx_of(args, kwargs)
+    if not _is_native(self) and (_needs_stock_forward(args, kwargs, 2)
+                                 or (args and args[0] is not None)):
+        return f["orig_forward"](hidden_states, *args, **kwargs)
+    ctx = _ctx_of(self, args, kwargs)
     x = hidden_states
     c = x.shape[-1]
     # --- self-attention ---
@@ -268,8 +308,16 @@ def fused_transformer_block_forward(self, hidden_states, *args, **kwargs):
 
 
 def fused_transformer2d_forward(self, hidden_states, *args, **kwargs):
-    """Transformer2DModel: GroupNorm -> int8 feeds proj_in; proj_out adds the residual."""
-    ctx = _ctx_of(args, kwargs)
+    """Transformer2DModel: GroupNorm -> int8 feeds proj_in; proj_out adds the residual.
+    diffusers conventions are honoured for non-skeleton classes: `encoder_hidden_states` as the
+    first positional or a keyword, `return_dict` (default True) selects the module's output class
+    or a 1-tuple; calls carrying masks / class labels / cross_attention_kwargs run the original
+    forward."""
+    native = _is_native(self)
+    if not native and _needs_stock_forward(args, kwargs, 1):
+        return self._mixdq_fused["orig_forward"](hidden_states, *args, **kwargs)
+    ctx = kwargs["encoder_hidden_states"] if "encoder_hidden_states" in kwargs else \
+        (args[0] if args else None)
     x = hidden_states
     b, c, h, w = x.shape
     if not x.is_contiguous(memory_format=torch.channels_last):
@@ -278,11 +326,18 @@ def fused_transformer2d_forward(self, hidden_states, *args, **kwargs):
                                               self.norm.bias, self.norm.eps, silu=False)
     y = _run_linear(self.proj_in, q8.permute(0, 2, 3, 1).reshape(b, h * w, c), s, z)
     for blk in self.transformer_blocks:
-        y = blk(y, ctx)
+        y = blk(y, ctx) if native else blk(y, encoder_hidden_states=ctx)
     o8, s, z = _quant_tokens(y)
     res = x.permute(0, 2, 3, 1).reshape(b, h * w, c)
     out = _run_linear(self.proj_out, o8, s, z, residual=res)
-    return out.reshape(b, h, w, c).permute(0, 3, 1, 2)
+    out = out.reshape(b, h, w, c).permute(0, 3, 1, 2)
+    if native:
+        return out
+    if not kwargs.get("return_dict", True):
+        return (out,)
+    import sys
+    out_cls = getattr(sys.modules.get(type(self).__module__), "Transformer2DModelOutput", None)
+    return out_cls(sample=out) if out_cls is not None else (out,)
 
 
 def fused_resnet_forward(self, input_tensor, temb, *args, **kwargs):
@@ -321,7 +376,33 @@ def _is(m, name: str) -> bool:
     return type(m).__name__ == name
 
 
+def _plain(obj, **expected) -> bool:
+    """every attribute named in `expected` is absent or equal to the expected value"""
+    return all(getattr(obj, k, v) == v for k, v in expected.items())
+
+
+def _attn_plain(attn) -> bool:
+    """diffusers Attention features the fused forward ignores must be off."""
+    head = attn.to_q.out_features // attn.heads
+    scale = getattr(attn, "scale", head ** -0.5)
+    return (_plain(attn, group_norm=None, spatial_norm=None, norm_cross=None, norm_q=None,
+                   norm_k=None, residual_connection=False, rescale_output_factor=1.0,
+                   upcast_attention=False, upcast_softmax=False, added_kv_proj_dim=None,
+                   only_cross_attention=False)
+            and abs(float(scale) - head ** -0.5) < 1e-6)
+
+
 def _block_ok(blk) -> bool:
+    if not _is_native(blk):
+        if not _plain(blk, only_cross_attention=False, use_ada_layer_norm=False,
+                      use_ada_layer_norm_zero=False, use_ada_layer_norm_single=False,
+                      use_ada_layer_norm_continuous=False, use_layer_norm=True,
+                      pos_embed=None, _chunk_size=None, fuser=None):
+            return False
+        if getattr(blk, "norm_type", "layer_norm") != "layer_norm":
+            return False
+        if not (_attn_plain(blk.attn1) and _attn_plain(blk.attn2)):
+            return False
     try:
         lins = [blk.attn1.to_q, blk.attn1.to_k, blk.attn1.to_v, blk.attn1.to_out[0],
                 blk.attn2.to_q, blk.attn2.to_k, blk.attn2.to_v, blk.attn2.to_out[0],
@@ -336,6 +417,10 @@ def _block_ok(blk) -> bool:
 
 
 def _resnet_ok(res) -> bool:
+    if not _is_native(res) and not _plain(res, output_scale_factor=1.0, up=False, down=False,
+                                          time_embedding_norm="default", upsample=None,
+                                          downsample=None):
+        return False
     try:
         ok = (_conv_ok(res.conv1) and res.conv1.split == 0 and _conv_ok(res.conv2)
               and res.conv2.split == 0 and _lin_ok(res.time_emb_proj)
@@ -356,7 +441,9 @@ def fuse_unet(unet: nn.Module, verbose: bool = False) -> dict:
     resnets = [m for m in unet.modules() if _is(m, "ResnetBlock2D") and _resnet_ok(m)]
     t2ds = [m for m in unet.modules() if _is(m, "Transformer2DModel")
             and hasattr(m, "proj_in") and _lin_ok(m.proj_in) and _lin_ok(m.proj_out)
-            and isinstance(m.norm, nn.GroupNorm) and _gn_ok(m.norm)]
+            and isinstance(m.norm, nn.GroupNorm) and _gn_ok(m.norm)
+            and (_is_native(m) or _plain(m, is_input_continuous=True, use_linear_projection=True,
+                                         is_input_vectorized=False, is_input_patches=False))]
     summary = {"transformer_blocks": len(blocks), "transformer2d": len(t2ds),
                "resnets": len(resnets), "kv_layers": 0, "temb_layers": 0}
     # one K/V group per (context width, BOS mode)
@@ -368,12 +455,14 @@ def fuse_unet(unet: nn.Module, verbose: bool = False) -> dict:
     for blk in blocks:
         key = (blk.attn2.to_k.in_features, bool(getattr(blk.attn2.to_k, "bos", False)))
         proj = blk.ff.net[0].proj
-        blk._mixdq_fused = {"qkv": CatLinear([blk.attn1.to_q, blk.attn1.to_k, blk.attn1.to_v]),
+        blk._mixdq_fused = {"orig_forward": blk.forward,
+                            "qkv": CatLinear([blk.attn1.to_q, blk.attn1.to_k, blk.attn1.to_v]),
                             "kv": kv_objs[key],
                             "ffproj": GegluLinear(proj) if proj.out_features % 32 == 0 else None}
         blk.forward = types.MethodType(fused_transformer_block_forward, blk)
         summary["kv_layers"] += 2
     for m in t2ds:
+        m._mixdq_fused = {"orig_forward": m.forward}
         m.forward = types.MethodType(fused_transformer2d_forward, m)
     if resnets:
         temb_groups = {}
@@ -384,6 +473,14 @@ def fuse_unet(unet: nn.Module, verbose: bool = False) -> dict:
             r._mixdq_fused = {"temb": temb_objs[r.time_emb_proj.in_features]}
             r.forward = types.MethodType(fused_resnet_forward, r)
             summary["temb_layers"] += 1
+    # the shared-input results live for ONE UNet forward (see SharedInputGroup)
+    groups = list(kv_objs.values()) + (list(temb_objs.values()) if resnets else [])
+    unet._mixdq_shared_groups = groups
+
+    def _reset_shared(_module, _args, _kwargs=None):
+        for g in groups:
+            g.reset()
+    unet.register_forward_pre_hook(_reset_shared)
     unet._mixdq_fused_summary = summary
     if verbose:
         print(f"mixdq fuse_unet: {summary}")

@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 from torch.ao.quantization import PlaceholderObserver, QConfig
 
+from . import ops
 from .nn.conv2d import QuantizedConv2d
 from .nn.linear import QuantizedLinear
 from .quantize import convert, derive_up_block_splits
@@ -194,6 +195,25 @@ def _copy_into(dst, src):
             _copy_into(dst[k], v)
 
 
+def _first_cuda_device(obj) -> torch.device:
+    if isinstance(obj, torch.Tensor):
+        return obj.device if obj.device.type == "cuda" else None
+    if isinstance(obj, (tuple, list)):
+        for o in obj:
+            d = _first_cuda_device(o)
+            if d is not None:
+                return d
+    if isinstance(obj, dict):
+        return _first_cuda_device(list(obj.values()))
+    return None
+
+
+def _invalidate_host_caches(unet) -> None:
+    ops.clear_dynamic_quant_cache()
+    for g in getattr(unet, "_mixdq_shared_groups", ()):
+        g.reset()
+
+
 def cuda_graph_opt(unet, args=None, warmup: int = 3):
     """Replace `unet.forward` by a version that captures one CUDA graph per argument signature
     and replays it: inputs are copied into static buffers, the graph is replayed, the static
@@ -209,17 +229,27 @@ def cuda_graph_opt(unet, args=None, warmup: int = 3):
             with lock:
                 if key not in cache:
                     sa, skw = _clone((a, kw))
-                    side = torch.cuda.Stream()
-                    side.wait_stream(torch.cuda.current_stream())
+                    dev = _first_cuda_device((sa, skw))
+                    # warm-up AND capture run on a stream of this graph's own, whose scratch
+                    # buffers (split-K exchange, dynamic-quantisation workspace) are allocated
+                    # before the capture begins — outside the graph's private memory pool, and
+                    # not shared with any other graph or stream (replays may run concurrently)
+                    side = torch.cuda.Stream(device=dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
                     with torch.no_grad(), torch.cuda.stream(side):
+                        ops.prepare_stream(dev)
                         for _ in range(warmup):
                             wrapped(*sa, **skw)
-                    torch.cuda.current_stream().wait_stream(side)
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    # nothing computed eagerly may be reused inside the capture: its kernels
+                    # would be missing from the graph (the caches also key on the capture id)
+                    _invalidate_host_caches(unet)
                     graph = torch.cuda.CUDAGraph()
-                    with torch.no_grad(), torch.cuda.graph(graph):
+                    with torch.no_grad(), torch.cuda.graph(graph, stream=side):
                         static_out = wrapped(*sa, **skw)
-                    cache[key] = ((sa, skw), graph, static_out)
-        (sa, skw), graph, static_out = cache[key]
+                    _invalidate_host_caches(unet)
+                    cache[key] = ((sa, skw), graph, static_out, side)
+        (sa, skw), graph, static_out, _ = cache[key]
         _copy_into((sa, skw), (a, kw))
         graph.replay()
         return static_out

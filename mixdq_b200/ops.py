@@ -56,17 +56,40 @@ def stop_recording() -> list:
 
 
 _workspaces = {}
-WORKSPACE_BYTES = 64 << 20
+WORKSPACE_BYTES = 32 << 20
 
 
 def _ensure_workspace(device: torch.device) -> None:
-    """Split-K scratch (stays L2-resident); allocated once per device through torch and handed
-    to the library, which never allocates."""
+    """Split-K scratch (stays L2-resident) of the CURRENT stream of `device`: allocated once per
+    (device, stream) through torch and registered with the library, which never allocates and
+    only uses a stream's own workspace (two streams cannot corrupt each other's partial tiles)."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    if idx not in _workspaces:
+    stream = torch.cuda.current_stream(device).cuda_stream
+    if (idx, stream) not in _workspaces:
         ws = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=torch.device("cuda", idx))
-        _lib.check(_lib.load().mixdq_set_workspace(idx, ws.data_ptr(), ws.numel()))
-        _workspaces[idx] = ws
+        _lib.check(_lib.load().mixdq_set_workspace(idx, stream, ws.data_ptr(), ws.numel()))
+        _workspaces[(idx, stream)] = ws
+
+
+def prepare_stream(device: torch.device) -> None:
+    """Allocate the per-stream workspaces of the current stream of `device` now. Call it on a
+    capture stream BEFORE the capture begins, so the scratch buffers live outside the graph's
+    private memory pool (mixdq.cuda_graph_opt does)."""
+    _ensure_workspace(device)
+    _dynamic_workspace(device)
+
+
+def _capture_id(device: torch.device) -> int:
+    """0 outside CUDA-graph capture, else the id of the capture the current stream belongs to."""
+    return _lib.capture_id(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _version_of(t: torch.Tensor):
+    """In-place-write counter of `t`, or None for inference tensors (which do not track one)."""
+    try:
+        return t._version
+    except RuntimeError:
+        return None
 
 
 def _launch(family: str, fn, args: tuple, ref: torch.Tensor, kernels: int = 1, keep=(),
@@ -252,7 +275,7 @@ def _dynamic_workspace(device: torch.device) -> torch.Tensor:
 # Keys are the tensor OBJECT (held strongly, so its storage cannot be recycled) and its version
 # counter (bumped by any in-place write).
 DYNAMIC_QUANT_CACHE = True
-_dyn_cache = []          # [(tensor, version, (q, scale, zp))], most recent last
+_dyn_cache = []          # [(tensor, version, capture id, (q, scale, zp))], most recent last
 _DYN_CACHE_SLOTS = 3
 
 
@@ -268,12 +291,19 @@ def clear_dynamic_quant_cache() -> None:
 
 def quantize_per_tensor_dynamic(input: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """qdiff asymmetric 8-bit min-max quantisation of one tensor (base_quantizer.py:155-190).
-    Returns (q int8, scale fp32[], zero_point fp32[] (shifted by -128))."""
+    Returns (q int8, scale fp32[], zero_point fp32[] (shifted by -128)).
+
+    The identity cache is keyed on (tensor object, version counter, CUDA-graph capture id): a
+    result computed eagerly is never reused inside a capture (its kernels would be missing from
+    the graph and every replay would read the stale codes), nor across two captures. Inference
+    tensors carry no version counter and are not cached."""
     _check(input.device.type == "cuda", "input should be on CUDA")
     _check(input.dtype == torch.float16, "input should be fp16")
-    if DYNAMIC_QUANT_CACHE:
-        for ref, ver, res in _dyn_cache:
-            if ref is input and ver == input._version:
+    ver = _version_of(input) if DYNAMIC_QUANT_CACHE else None
+    cap = _capture_id(input.device) if ver is not None else 0
+    if ver is not None:
+        for ref, v, c, res in _dyn_cache:
+            if ref is input and v == ver and c == cap:
                 return res
     lib = _lib.load()
     x = input if _is_dense(input) else input.contiguous()
@@ -286,8 +316,8 @@ def quantize_per_tensor_dynamic(input: torch.Tensor) -> Tuple[torch.Tensor, torc
                  ws.data_ptr()), x, kernels=_dyn_kernels(x.numel()), keep=(x, qp, out, ws),
                 algo_bytes=3 * x.numel())
     res = (out, qp[0], qp[1])
-    if DYNAMIC_QUANT_CACHE:
-        _dyn_cache.append((input, input._version, res))
+    if ver is not None:
+        _dyn_cache.append((input, ver, cap, res))
         if len(_dyn_cache) > _DYN_CACHE_SLOTS:
             _dyn_cache.pop(0)
     return res

@@ -40,7 +40,7 @@ def test_no_torch_or_python_dependency():
 
 
 def test_version_and_strerror(lib):
-    assert lib.mixdq_abi_version() == 1
+    assert lib.mixdq_abi_version() == 2
     assert lib.mixdq_strerror(0) == b"success"
     # the reference's alignment message (qlinear.cc:130-133)
     assert lib.mixdq_strerror(-2) == \

@@ -441,6 +441,8 @@ SDXL_CONVS = [  # (n,h,w,c,k,r,s,pad,stride)
     (2, 64, 64, 320, 320, 3, 3, 1, 1), (1, 1, 1, 64, 64, 3, 3, 1, 1), (1, 2, 3, 32, 16, 3, 3, 1, 1),
     (1, 64, 64, 320, 320, 3, 3, 1, 2), (1, 32, 32, 640, 640, 3, 3, 1, 2),   # SDXL downsamplers
     (2, 14, 14, 512, 1024, 3, 3, 1, 2), (1, 15, 13, 64, 64, 3, 3, 1, 2), (3, 14, 14, 128, 64, 3, 3, 0, 2),
+    # output rows wider than one 128-pixel tile (latents beyond 1024 px): tiled along q as well
+    (1, 3, 160, 32, 32, 3, 3, 1, 1), (2, 2, 131, 64, 16, 1, 1, 0, 1), (1, 5, 300, 16, 32, 3, 3, 1, 2),
 ]
 
 
