@@ -154,13 +154,49 @@ int mixdq_gemm_w8a8_f16_dyn(const int8_t* A, int64_t lda, const int8_t* W,
                             mixdq_half_t* D, int64_t ldd, int M, int N, int K,
                             int32_t* acc_out, mixdq_stream_t stream);
 
-/* W4A8 (north star; no kernel in the reference): W_packed uint8 [N][K/2], two signed 4-bit
- * two's-complement codes per byte, EVEN k in the HIGH nibble (nibble order of
- * nn/utils.py:26-28). Same epilogue as A2. K % 32 == 0 required. */
+/* ------------------------------------------------------------------------------------------
+ * W4A8 (north star "W4A8 layers unpacked on the fly"; the reference has no 4-bit kernel: its
+ * 4-/2-bit layers fall back to fp16, nn/Linear.py:28-36, nn/Conv2d.py:37-61). Arithmetic = the
+ * qdiff 4-bit symmetric per-channel weight quantiser (base_quantizer.py:119-185) feeding the
+ * same integer identity and epilogue as A2 / A3.
+ * W_packed uint8 [N][K/2] (conv: KRSC [K][R][S][C/2]): two signed 4-bit two's-complement codes
+ * per byte, EVEN k (c) in the HIGH nibble — the nibble order of nn/utils.py:26-28. The packed
+ * tiles travel through TMA as they are (half the weight bytes of W8) and are expanded to int8
+ * inside the tcgen05 kernel. K % 32 == 0 (conv: C % 32 == 0) required.
+ * mixdq_gemm_w4a8_f16 falls back to a portable kernel when the tcgen05 alignment conditions do
+ * not hold; the other entry points return MIXDQ_ERR_ALIGNMENT (keep such layers as W8 codes).
+ * ---------------------------------------------------------------------------------------- */
 int mixdq_gemm_w4a8_f16(const int8_t* A, int64_t lda, const uint8_t* W_packed,
                         const float* bias0, const float* scale, const mixdq_half_t* bias,
                         mixdq_half_t* D, int64_t ldd, int M, int N, int K,
                         int32_t* acc_out, mixdq_stream_t stream);
+/* dynamic activation scalars + optional fused residual add (see mixdq_gemm_w8a8_f16_dyn_res) */
+int mixdq_gemm_w4a8_f16_dyn_res(const int8_t* A, int64_t lda, const uint8_t* W_packed,
+                                const float* w_scale, const float* wsum,
+                                const float* a_scale, const float* a_zp, const mixdq_half_t* bias,
+                                const mixdq_half_t* residual, int64_t ldr,
+                                mixdq_half_t* D, int64_t ldd, int M, int N, int K,
+                                int32_t* acc_out, mixdq_stream_t stream);
+/* GEGLU projection with packed 4-bit weights (see mixdq_gemm_w8a8_geglu_f16_dyn; rows interleaved
+   BEFORE packing) */
+int mixdq_gemm_w4a8_geglu_f16_dyn(const int8_t* A, int64_t lda, const uint8_t* W_il_packed,
+                                  const float* w_scale_il, const float* wsum_il,
+                                  const float* a_scale, const float* a_zp,
+                                  const mixdq_half_t* bias_il, mixdq_half_t* Y, int64_t ldy,
+                                  int M, int N2, int K, void* ws, mixdq_stream_t stream);
+/* convolutions, static / dynamic (see mixdq_conv_w8a8_f16 / mixdq_conv_w8a8_f16_dyn) */
+int mixdq_conv_w4a8_f16(const int8_t* x_nhwc, int64_t x_cpitch, const uint8_t* w_krsc_packed,
+                        const float* scale, const float* wsum_krs, const float* bias0_k,
+                        const float* zp, const mixdq_half_t* bias, mixdq_half_t* y_nhwc,
+                        int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
+                        int32_t* acc_out, mixdq_stream_t stream);
+int mixdq_conv_w4a8_f16_dyn(const int8_t* x_nhwc, int64_t x_cpitch, const uint8_t* w_krsc_packed,
+                            const float* w_scale, const float* wsum_krs, const float* wsum_k,
+                            const float* a_scale, const float* a_zp, const mixdq_half_t* bias,
+                            const mixdq_half_t* chan_add, int64_t ldca,
+                            const mixdq_half_t* residual, mixdq_half_t* y_nhwc, int N, int H,
+                            int W, int C, int K, int R, int S, int stride, int pad,
+                            int32_t* acc_out, mixdq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * A3 + A4  W8A8 conv2d fprop, NHWC, cross-correlation, dilation 1, square stride/padding,

@@ -27,6 +27,8 @@ ABI_SYMBOLS = [
     "mixdq_gemm_w8a8_f16_dyn_res", "mixdq_conv_w8a8_f16_dyn", "mixdq_conv1x1_split_w8a8_f16_dyn",
     "mixdq_quant_i8_dynamic_rows", "mixdq_ln_quant_i8_dynamic", "mixdq_geglu_quant_i8_dynamic", "mixdq_gn_quant_i8_dynamic",
     "mixdq_gemm_w8a8_geglu_f16_dyn", "mixdq_quant_i8_premm", "mixdq_cross_attn_d64_f16",
+    "mixdq_gemm_w4a8_f16_dyn_res", "mixdq_gemm_w4a8_geglu_f16_dyn", "mixdq_conv_w4a8_f16",
+    "mixdq_conv_w4a8_f16_dyn",
 ]
 
 
@@ -122,6 +124,12 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mixdq_cross_attn_d64_f16.restype = c_int
     lib.mixdq_cross_attn_d64_f16.argtypes = [P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64,
                                              c_int64, P, c_int, c_int, c_int, c_int, c_float, P, P]
+    for w8, w4 in (("mixdq_gemm_w8a8_f16_dyn_res", "mixdq_gemm_w4a8_f16_dyn_res"),
+                   ("mixdq_gemm_w8a8_geglu_f16_dyn", "mixdq_gemm_w4a8_geglu_f16_dyn"),
+                   ("mixdq_conv_w8a8_f16", "mixdq_conv_w4a8_f16"),
+                   ("mixdq_conv_w8a8_f16_dyn", "mixdq_conv_w4a8_f16_dyn")):
+        getattr(lib, w4).restype = c_int              # same signatures, packed weight pointer
+        getattr(lib, w4).argtypes = getattr(lib, w8).argtypes
     lib.mixdq_quant_i8_premm.restype = c_int
     lib.mixdq_quant_i8_premm.argtypes = [P, c_int64, P, P, P, P, P]
     lib.mixdq_gn_quant_i8_dynamic.restype = c_int

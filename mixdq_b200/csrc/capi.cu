@@ -63,7 +63,7 @@ static PFN_encodeTiled get_encode() {
 // rank-R uint8 tensor, dims/box innermost first, strides in bytes for dims 1..R-1.
 static bool make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides, const uint32_t* box,
-                      const uint32_t* elem_strides = nullptr) {
+                      const uint32_t* elem_strides = nullptr, bool swizzle = true) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return false;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -73,7 +73,8 @@ static bool make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t
                    const_cast<void*>(base), reinterpret_cast<const cuuint64_t*>(dims),
                    reinterpret_cast<const cuuint64_t*>(strides),
                    reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -85,17 +86,26 @@ static bool make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64
   uint32_t box[2] = {BLOCK_K, box_rows};
   return make_tmap(m, base, 2, dims, strides, box);
 }
+// packed 4-bit weights [rows][k/2 bytes]: 64-byte (one k-block) wide boxes, no swizzle — the
+// converter warps read the tile linearly and write the swizzled int8 layout themselves
+static bool make_tmap_2d_w4(CUtensorMap* m, const void* base, uint64_t k, uint64_t rows,
+                            uint32_t box_rows) {
+  uint64_t dims[2] = {k / 2, rows};
+  uint64_t strides[1] = {k / 2};
+  uint32_t box[2] = {BLOCK_K / 2, box_rows};
+  return make_tmap(m, base, 2, dims, strides, box, nullptr, false);
+}
 
 // ------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------
 extern int g_use_pdl_fwd;
-template <int BN, int STAGES, int KIND>
+template <int BN, int STAGES, int KIND, bool W4 = false>
 static int launch_tc(dim3 grid, const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a1,
                      const CUtensorMap& w1, const TcParams& p, cudaStream_t st) {
-  using L = TcSmem<BN, STAGES, KIND>;
+  using L = TcSmem<BN, STAGES, KIND, W4>;
   static bool attr_set = false;
-  auto kern = tc_i8_kernel<BN, STAGES, KIND>;
+  auto kern = tc_i8_kernel<BN, STAGES, KIND, W4>;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) !=
         cudaSuccess)
@@ -256,16 +266,16 @@ static void pick_tile(int m_tiles, int N, int total_kb, bool allow_split, cudaSt
   *splits_out = best_s;
 }
 
-template <int KIND>
+template <int KIND, bool W4 = false>
 static int dispatch_tc(int bn, dim3 grid, const CUtensorMap& a, const CUtensorMap& w,
                        const CUtensorMap& a1, const CUtensorMap& w1, const TcParams& p,
                        cudaStream_t st) {
   switch (bn) {
-    case 256: return launch_tc<256, 4, KIND>(grid, a, w, a1, w1, p, st);
-    case 128: return launch_tc<128, 3, KIND>(grid, a, w, a1, w1, p, st);   // 2 k-blocks per stage
-    case 64: return launch_tc<64, 4, KIND>(grid, a, w, a1, w1, p, st);
-    case 32: return launch_tc<32, 4, KIND>(grid, a, w, a1, w1, p, st);
-    case 16: return launch_tc<16, 4, KIND>(grid, a, w, a1, w1, p, st);
+    case 256: return launch_tc<256, 4, KIND, W4>(grid, a, w, a1, w1, p, st);
+    case 128: return launch_tc<128, 3, KIND, W4>(grid, a, w, a1, w1, p, st);   // 2 k-blocks per stage
+    case 64: return launch_tc<64, 4, KIND, W4>(grid, a, w, a1, w1, p, st);
+    case 32: return launch_tc<32, 4, KIND, W4>(grid, a, w, a1, w1, p, st);
+    case 16: return launch_tc<16, 4, KIND, W4>(grid, a, w, a1, w1, p, st);
     default: return MIXDQ_ERR_UNSUPPORTED;
   }
 }
@@ -279,11 +289,11 @@ static int gemm_common(const int8_t* A, int64_t lda, const int8_t* W, const floa
                        const float* p_bias0, const float* a_scale, const float* a_zp,
                        const mixdq_half_t* bias, const mixdq_half_t* residual, int64_t ldr,
                        mixdq_half_t* D, int64_t ldd, int M, int N, int K,
-                       int32_t* acc_out, cudaStream_t st) {
+                       int32_t* acc_out, cudaStream_t st, bool w4 = false) {
   if (M < 0 || N <= 0 || K <= 0 || !W || !p_scale || !p_bias0) return MIXDQ_ERR_INVALID_ARG;
   if (M == 0) return MIXDQ_OK;
   if (!A || !D || lda < K || ldd < N || (residual && ldr < N)) return MIXDQ_ERR_INVALID_ARG;
-  if ((K & 3) || (N & 3)) return MIXDQ_ERR_ALIGNMENT;
+  if ((K & (w4 ? 31 : 3)) || (N & 3)) return MIXDQ_ERR_ALIGNMENT;
 
   const bool tc_ok = !g_force_simt && (K % 16 == 0) && (N % 8 == 0) && (lda % 16 == 0) &&
                      (ldd % 8 == 0) && al16(A) && al16(W) && al16(D) &&
@@ -295,7 +305,8 @@ static int gemm_common(const int8_t* A, int64_t lda, const int8_t* W, const floa
     g.scale = p_scale; g.bias0 = p_bias0; g.a_scale = a_scale; g.a_zp = a_zp;
     g.bias = reinterpret_cast<const __half*>(bias);
     g.D = reinterpret_cast<__half*>(D); g.ldd = ldd; g.M = M; g.N = N; g.acc_out = acc_out;
-    g_last_path = "simt";
+    g.w4 = w4 ? 1 : 0;
+    g_last_path = w4 ? "simt-w4" : "simt";
     return simt_gemm_launch(g, st) == 0 ? MIXDQ_OK : MIXDQ_ERR_CUDA;
   }
 
@@ -305,7 +316,8 @@ static int gemm_common(const int8_t* A, int64_t lda, const int8_t* W, const floa
   pick_tile(m_tiles, N, num_kb, true, st, &bn, &splits);
   CUtensorMap tmA, tmW;
   if (!make_tmap_2d(&tmA, A, K, M, lda, BLOCK_M)) return MIXDQ_ERR_CUDA;
-  if (!make_tmap_2d(&tmW, W, K, N, K, bn)) return MIXDQ_ERR_CUDA;
+  if (w4 ? !make_tmap_2d_w4(&tmW, W, K, N, bn) : !make_tmap_2d(&tmW, W, K, N, K, bn))
+    return MIXDQ_ERR_CUDA;
   TcParams p{};
   p.dbg = g_dbg;
   p.dbg_mode = g_dbg_mode;
@@ -318,6 +330,10 @@ static int gemm_common(const int8_t* A, int64_t lda, const int8_t* W, const floa
   p.D = reinterpret_cast<__half*>(D); p.ldd = ldd; p.acc_out = acc_out;
   p.residual = reinterpret_cast<const __half*>(residual); p.ldr = ldr;
   dim3 grid(m_tiles, (N + bn - 1) / bn, splits);
+  if (w4) {
+    g_last_path = splits > 1 ? "tcgen05-w4-splitk" : "tcgen05-w4";
+    return dispatch_tc<KIND_GEMM, true>(bn, grid, tmA, tmW, tmA, tmW, p, st);
+  }
   g_last_path = splits > 1 ? "tcgen05-splitk" : "tcgen05";
   return dispatch_tc<KIND_GEMM>(bn, grid, tmA, tmW, tmA, tmW, p, st);
 }
@@ -343,17 +359,17 @@ extern "C" int mixdq_gemm_w8a8_f16_dyn(const int8_t* A, int64_t lda, const int8_
 
 // ff.net.0.proj + GEGLU (KIND_GEGLU): W / w_scale / wsum / bias rows interleaved in groups of
 // 16 value rows followed by their 16 gate rows; Y = [M][N2/2] fp16; min/max -> ws (DynWs::mm)
-extern "C" int mixdq_gemm_w8a8_geglu_f16_dyn(const int8_t* A, int64_t lda, const int8_t* W_il,
-                                             const float* w_scale_il, const float* wsum_il,
-                                             const float* a_scale, const float* a_zp,
-                                             const mixdq_half_t* bias_il, mixdq_half_t* Y,
-                                             int64_t ldy, int M, int N2, int K, void* ws,
-                                             mixdq_stream_t stream) {
+static int geglu_common(const int8_t* A, int64_t lda, const int8_t* W_il,
+                        const float* w_scale_il, const float* wsum_il, const float* a_scale,
+                        const float* a_zp, const mixdq_half_t* bias_il, mixdq_half_t* Y,
+                        int64_t ldy, int M, int N2, int K, void* ws, mixdq_stream_t stream,
+                        bool w4) {
   if (M < 0 || N2 <= 0 || K <= 0 || !W_il || !w_scale_il || !wsum_il || !a_scale || !a_zp || !ws)
     return MIXDQ_ERR_INVALID_ARG;
   if (M == 0) return MIXDQ_OK;
   if (!A || !Y || lda < K || ldy < N2 / 2) return MIXDQ_ERR_INVALID_ARG;
-  if ((K % 16) || (N2 % 32) || (lda % 16) || (ldy % 8) || !al16(A) || !al16(W_il) || !al16(Y))
+  if ((K % (w4 ? 32 : 16)) || (N2 % 32) || (lda % 16) || (ldy % 8) || !al16(A) || !al16(W_il) ||
+      !al16(Y))
     return MIXDQ_ERR_ALIGNMENT;
   if (g_force_simt) return MIXDQ_ERR_UNSUPPORTED;
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
@@ -379,7 +395,8 @@ extern "C" int mixdq_gemm_w8a8_geglu_f16_dyn(const int8_t* A, int64_t lda, const
   }
   CUtensorMap tmA, tmW;
   if (!make_tmap_2d(&tmA, A, K, M, lda, BLOCK_M)) return MIXDQ_ERR_CUDA;
-  if (!make_tmap_2d(&tmW, W_il, K, N2, K, bn)) return MIXDQ_ERR_CUDA;
+  if (w4 ? !make_tmap_2d_w4(&tmW, W_il, K, N2, bn) : !make_tmap_2d(&tmW, W_il, K, N2, K, bn))
+    return MIXDQ_ERR_CUDA;
   TcParams p{};
   p.dbg = g_dbg;
   p.dbg_mode = g_dbg_mode;
@@ -393,8 +410,18 @@ extern "C" int mixdq_gemm_w8a8_geglu_f16_dyn(const int8_t* A, int64_t lda, const
   dim3 grid(m_tiles, (N2 + bn - 1) / bn, 1);
   if (static_cast<int64_t>(grid.x) * grid.y > kMaxPartials) return MIXDQ_ERR_UNSUPPORTED;
   partial_count_slot(ws) = static_cast<int>(grid.x * grid.y);
-  g_last_path = "tcgen05-geglu";
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (w4) {
+    g_last_path = "tcgen05-w4-geglu";
+    switch (bn) {
+      case 256: return launch_tc<256, 4, KIND_GEGLU, true>(grid, tmA, tmW, tmA, tmW, p, st);
+      case 160: return launch_tc<160, 5, KIND_GEGLU, true>(grid, tmA, tmW, tmA, tmW, p, st);
+      case 128: return launch_tc<128, 3, KIND_GEGLU, true>(grid, tmA, tmW, tmA, tmW, p, st);
+      case 64: return launch_tc<64, 4, KIND_GEGLU, true>(grid, tmA, tmW, tmA, tmW, p, st);
+      default: return launch_tc<32, 4, KIND_GEGLU, true>(grid, tmA, tmW, tmA, tmW, p, st);
+    }
+  }
+  g_last_path = "tcgen05-geglu";
   switch (bn) {
     case 256: return launch_tc<256, 4, KIND_GEGLU>(grid, tmA, tmW, tmA, tmW, p, st);
     case 160: return launch_tc<160, 5, KIND_GEGLU>(grid, tmA, tmW, tmA, tmW, p, st);
@@ -402,6 +429,26 @@ extern "C" int mixdq_gemm_w8a8_geglu_f16_dyn(const int8_t* A, int64_t lda, const
     case 64: return launch_tc<64, 4, KIND_GEGLU>(grid, tmA, tmW, tmA, tmW, p, st);
     default: return launch_tc<32, 4, KIND_GEGLU>(grid, tmA, tmW, tmA, tmW, p, st);
   }
+}
+
+extern "C" int mixdq_gemm_w8a8_geglu_f16_dyn(const int8_t* A, int64_t lda, const int8_t* W_il,
+                                             const float* w_scale_il, const float* wsum_il,
+                                             const float* a_scale, const float* a_zp,
+                                             const mixdq_half_t* bias_il, mixdq_half_t* Y,
+                                             int64_t ldy, int M, int N2, int K, void* ws,
+                                             mixdq_stream_t stream) {
+  return geglu_common(A, lda, W_il, w_scale_il, wsum_il, a_scale, a_zp, bias_il, Y, ldy, M, N2, K,
+                      ws, stream, false);
+}
+
+extern "C" int mixdq_gemm_w4a8_geglu_f16_dyn(const int8_t* A, int64_t lda,
+                                             const uint8_t* W_il_packed, const float* w_scale_il,
+                                             const float* wsum_il, const float* a_scale,
+                                             const float* a_zp, const mixdq_half_t* bias_il,
+                                             mixdq_half_t* Y, int64_t ldy, int M, int N2, int K,
+                                             void* ws, mixdq_stream_t stream) {
+  return geglu_common(A, lda, reinterpret_cast<const int8_t*>(W_il_packed), w_scale_il, wsum_il,
+                      a_scale, a_zp, bias_il, Y, ldy, M, N2, K, ws, stream, true);
 }
 
 extern "C" int mixdq_gemm_w8a8_f16_dyn_res(const int8_t* A, int64_t lda, const int8_t* W,
@@ -415,20 +462,27 @@ extern "C" int mixdq_gemm_w8a8_f16_dyn_res(const int8_t* A, int64_t lda, const i
                      acc_out, static_cast<cudaStream_t>(stream));
 }
 
+// W4A8: packed signed 4-bit weights [N][K/2] (even k in the high nibble), unpacked on the fly by the
+// converter warps of tc_i8_kernel<..., W4 = true>
 extern "C" int mixdq_gemm_w4a8_f16(const int8_t* A, int64_t lda, const uint8_t* W_packed,
                                    const float* bias0, const float* scale,
                                    const mixdq_half_t* bias, mixdq_half_t* D, int64_t ldd, int M,
                                    int N, int K, int32_t* acc_out, mixdq_stream_t stream) {
-  if (M < 0 || N <= 0 || K <= 0 || !W_packed || !scale || !bias0) return MIXDQ_ERR_INVALID_ARG;
-  if (M == 0) return MIXDQ_OK;
-  if (!A || !D || lda < K || ldd < N) return MIXDQ_ERR_INVALID_ARG;
-  if ((K & 31) || (N & 3)) return MIXDQ_ERR_ALIGNMENT;
-  SimtGemmArgs g{};
-  g.A = A; g.lda = lda; g.W = reinterpret_cast<const int8_t*>(W_packed); g.K = K;
-  g.scale = scale; g.bias0 = bias0; g.bias = reinterpret_cast<const __half*>(bias);
-  g.D = reinterpret_cast<__half*>(D); g.ldd = ldd; g.M = M; g.N = N; g.acc_out = acc_out; g.w4 = 1;
-  g_last_path = "simt-w4";
-  return simt_gemm_launch(g, static_cast<cudaStream_t>(stream)) == 0 ? MIXDQ_OK : MIXDQ_ERR_CUDA;
+  return gemm_common(A, lda, reinterpret_cast<const int8_t*>(W_packed), scale, bias0, nullptr,
+                     nullptr, bias, nullptr, 0, D, ldd, M, N, K, acc_out,
+                     static_cast<cudaStream_t>(stream), true);
+}
+
+extern "C" int mixdq_gemm_w4a8_f16_dyn_res(const int8_t* A, int64_t lda, const uint8_t* W_packed,
+                                           const float* w_scale, const float* wsum,
+                                           const float* a_scale, const float* a_zp,
+                                           const mixdq_half_t* bias, const mixdq_half_t* residual,
+                                           int64_t ldr, mixdq_half_t* D, int64_t ldd, int M, int N,
+                                           int K, int32_t* acc_out, mixdq_stream_t stream) {
+  if (!a_scale || !a_zp) return MIXDQ_ERR_INVALID_ARG;
+  return gemm_common(A, lda, reinterpret_cast<const int8_t*>(W_packed), w_scale, wsum, a_scale,
+                     a_zp, bias, residual, ldr, D, ldd, M, N, K, acc_out,
+                     static_cast<cudaStream_t>(stream), true);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -439,7 +493,7 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
                        const float* a_scale, const mixdq_half_t* bias,
                        const mixdq_half_t* chan_add, int64_t ldca, const mixdq_half_t* residual,
                        mixdq_half_t* y, int N, int H, int W, int C, int K, int R, int S,
-                       int stride, int pad, int32_t* acc_out, cudaStream_t st) {
+                       int stride, int pad, int32_t* acc_out, cudaStream_t st, bool w4 = false) {
   if (N < 0 || H <= 0 || W <= 0 || C <= 0 || K <= 0 || R <= 0 || S <= 0 || stride <= 0 ||
       pad < 0 || !w || !scale)
     return MIXDQ_ERR_INVALID_ARG;
@@ -456,13 +510,13 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
   // stride 2 along W and H), so the tile rows are still consecutive OUTPUT pixels
   const bool geom_ok = (stride == 1 || stride == 2) &&
                        (pad == 0 || (pad == 1 && R == 3 && S == 3));
-  const bool tc_ok = !g_force_simt && geom_ok && (C % 16 == 0) && (x_cpitch % 16 == 0) &&
+  const bool tc_ok = !g_force_simt && geom_ok && (C % (w4 ? 32 : 16) == 0) && (x_cpitch % 16 == 0) &&
                      (K % 8 == 0) && al16(x) && al16(w) && al16(y) && (!acc_out || al16(acc_out)) &&
                      (!chan_add || (al16(chan_add) && ldca % 8 == 0 && ldca >= K)) &&
                      (!residual || al16(residual));
   if (!tc_ok) {
-    // dynamic scalars and the fused tails exist on the tcgen05 path only
-    if (a_scale || chan_add || residual) return MIXDQ_ERR_ALIGNMENT;
+    // dynamic scalars, the fused tails and packed 4-bit weights exist on the tcgen05 path only
+    if (a_scale || chan_add || residual || w4) return MIXDQ_ERR_ALIGNMENT;
     SimtConvArgs c{};
     c.x = x; c.x_cpitch = x_cpitch; c.w = w; c.scale = scale;
     c.wsum_krs = pad > 0 ? wsum_krs : nullptr; c.bias0_k = bias0_k; c.zp = zp;
@@ -500,11 +554,13 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
     if (!make_tmap(&tmA, x, 4, dims, strides, box, estr)) return MIXDQ_ERR_CUDA;
   }
   {
-    uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(R) * S,
-                        static_cast<uint64_t>(K)};
-    uint64_t strides[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(C) * R * S};
-    uint32_t box[3] = {BLOCK_K, 1, static_cast<uint32_t>(bn)};
-    if (!make_tmap(&tmW, w, 3, dims, strides, box)) return MIXDQ_ERR_CUDA;
+    // KRSC (W4: C/2 packed bytes per tap, 64-byte boxes, unswizzled)
+    const uint64_t cb = w4 ? C / 2 : C;
+    uint64_t dims[3] = {cb, static_cast<uint64_t>(R) * S, static_cast<uint64_t>(K)};
+    uint64_t strides[2] = {cb, cb * R * S};
+    uint32_t box[3] = {static_cast<uint32_t>(w4 ? BLOCK_K / 2 : BLOCK_K), 1,
+                       static_cast<uint32_t>(bn)};
+    if (!make_tmap(&tmW, w, 3, dims, strides, box, nullptr, !w4)) return MIXDQ_ERR_CUDA;
   }
   TcParams p{};
   p.dbg = g_dbg;
@@ -526,8 +582,40 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
   p.rows_per_img = static_cast<int64_t>(P) * Q;
   p.residual = reinterpret_cast<const __half*>(residual); p.ldr = K;
   dim3 grid(m_tiles, (K + bn - 1) / bn, splits);
+  if (w4) {
+    g_last_path = splits > 1 ? "tcgen05-w4-splitk" : "tcgen05-w4";
+    return dispatch_tc<KIND_CONV, true>(bn, grid, tmA, tmW, tmA, tmW, p, st);
+  }
   g_last_path = splits > 1 ? "tcgen05-splitk" : "tcgen05";
   return dispatch_tc<KIND_CONV>(bn, grid, tmA, tmW, tmA, tmW, p, st);
+}
+
+// W4A8 convolutions: w_krsc_packed = uint8 [K][R][S][C/2], two signed 4-bit codes per byte along
+// C, even c in the high nibble. tcgen05 path only (C % 32 == 0, K % 8 == 0, 1x1 or 3x3/pad 1,
+// stride 1 or 2): MIXDQ_ERR_ALIGNMENT otherwise — such layers keep one code per int8.
+extern "C" int mixdq_conv_w4a8_f16(const int8_t* x, int64_t x_cpitch, const uint8_t* w_packed,
+                                   const float* scale, const float* wsum_krs,
+                                   const float* bias0_k, const float* zp,
+                                   const mixdq_half_t* bias, mixdq_half_t* y, int N, int H, int W,
+                                   int C, int K, int R, int S, int stride, int pad,
+                                   int32_t* acc_out, mixdq_stream_t stream) {
+  return conv_common(x, x_cpitch, reinterpret_cast<const int8_t*>(w_packed), scale, wsum_krs,
+                     bias0_k, zp, nullptr, bias, nullptr, 0, nullptr, y, N, H, W, C, K, R, S,
+                     stride, pad, acc_out, static_cast<cudaStream_t>(stream), true);
+}
+
+extern "C" int mixdq_conv_w4a8_f16_dyn(const int8_t* x, int64_t x_cpitch, const uint8_t* w_packed,
+                                       const float* w_scale, const float* wsum_krs,
+                                       const float* wsum_k, const float* a_scale,
+                                       const float* a_zp, const mixdq_half_t* bias,
+                                       const mixdq_half_t* chan_add, int64_t ldca,
+                                       const mixdq_half_t* residual, mixdq_half_t* y, int N, int H,
+                                       int W, int C, int K, int R, int S, int stride, int pad,
+                                       int32_t* acc_out, mixdq_stream_t stream) {
+  if (!a_scale || !a_zp) return MIXDQ_ERR_INVALID_ARG;
+  return conv_common(x, x_cpitch, reinterpret_cast<const int8_t*>(w_packed), w_scale, wsum_krs,
+                     wsum_k, a_zp, a_scale, bias, chan_add, ldca, residual, y, N, H, W, C, K, R, S,
+                     stride, pad, acc_out, static_cast<cudaStream_t>(stream), true);
 }
 
 extern "C" int mixdq_conv_w8a8_f16(const int8_t* x, int64_t x_cpitch, const int8_t* w,

@@ -19,6 +19,15 @@
 //               half(h * half(gelu(gate))) like the stock GEGLU module, stores [M][N/2] fp16 and
 //               one min / max partial per CTA, so the quantiser that follows is a single pass
 //
+// W4 (template flag): the weight operand is PACKED signed 4-bit codes (two per byte, even k in
+//   the high nibble — the reference's only nibble convention, nn/utils.py:26-28). TMA moves the
+//   packed tile (64 bytes per row and k-block: half the HBM / L2 bytes) into the upper half of
+//   the stage's W slot; the eight epilogue warps — idle during the mainloop — expand it in place
+//   into the 128B-swizzled int8 layout the MMA reads (5 ALU instructions per 8 codes: each
+//   nibble is moved to the HIGH half of its byte, i.e. the int8 value 16*w, no sign extension
+//   needed) and signal the stage's full barrier. The accumulators are therefore exactly 16x the
+//   true ones and the epilogue shifts them right by 4 before the unchanged dequant arithmetic.
+//
 // Split-K over a thread-block cluster (p.splits > 1, cluster dims (1,1,splits)).
 //   Measured on B200 (tools/phase_timing.py): with both operands in shared memory one
 //   tcgen05.mma (M=128, K=32) occupies the tensor pipe ~160 cycles whatever N is — the A slab
@@ -125,7 +134,7 @@ struct TcKsub { static constexpr int value = (BN <= 128) ? 2 : 1; };
 template <int BN, int KIND>
 struct TcDual { static constexpr bool value = (BN <= 64) && (KIND != 2 /*KIND_SPLIT*/); };
 
-template <int BN, int STAGES, int KIND>
+template <int BN, int STAGES, int KIND, bool W4 = false>
 struct TcSmem {
   static constexpr int KSUB = TcKsub<BN>::value;
   static constexpr int A_SUB = BLOCK_M * BLOCK_K;
@@ -139,7 +148,7 @@ struct TcSmem {
   static constexpr int OFF_W = OFF_A + STAGES * A_BYTES;
   static constexpr int OFF_PARAM = OFF_W + STAGES * W_BYTES;
   static constexpr int OFF_BAR = OFF_PARAM + ((PARAM_FLOATS * 4 + 15) / 16) * 16;
-  static constexpr int NUM_BARS = 2 * STAGES + 1;
+  static constexpr int NUM_BARS = (W4 ? 3 : 2) * STAGES + 1;   // W4: + packed-tile-landed barriers
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024 B alignment
@@ -207,12 +216,13 @@ __device__ __forceinline__ uint4 epilogue_tail(const TcParams& p, uint4 v, int64
   return v;
 }
 
-template <int BN, int STAGES, int KIND>
+template <int BN, int STAGES, int KIND, bool W4 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
              const TcParams p) {
-  using L = TcSmem<BN, STAGES, KIND>;
+  using L = TcSmem<BN, STAGES, KIND, W4>;
+  static_assert(!W4 || KIND != KIND_SPLIT, "W4 split shortcuts run as two convolutions");
   constexpr bool DUAL = TcDual<BN, KIND>::value;
   static_assert(!DUAL || (STAGES % 2 == 0), "dual issue alternates stages: even ring depth");
   constexpr int TMEM_COLS_USED = ((KIND == KIND_SPLIT || DUAL) ? 2 : 1) * BN;
@@ -232,6 +242,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* raw_full = tmem_full_bar + 1;     // W4 only: packed weight tile of the stage landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM);
 
   const int warp = threadIdx.x >> 5;
@@ -247,6 +258,11 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int total_kb = p.num_kb + (KIND == KIND_SPLIT ? p.num_kb1 : 0);
   const int kb_begin = (splits > 1) ? (krank * total_kb) / splits : 0;
   const int kb_end = (splits > 1) ? ((krank + 1) * total_kb) / splits : total_kb;
+  // ring stage si holds k-blocks kb_begin + si*KSUB .. (+KSUB-1); the last one may be short
+  const int nkb = kb_end - kb_begin;
+  const int nst = (nkb + L::KSUB - 1) / L::KSUB;
+  const int npre = nst < STAGES ? nst : STAGES;   // stages whose weights are issued before the wait
+  auto nsub_of = [&](int si) { const int rem = nkb - si * L::KSUB; return rem < L::KSUB ? rem : L::KSUB; };
 
   // tile origin
   int m0 = 0, tn0 = 0, tp0 = 0, tq0 = 0;
@@ -263,7 +279,12 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
     if (KIND == KIND_SPLIT) { tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmW1); }
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < STAGES; ++i) {
+      // W4: the stage is full once the A bytes landed AND the 8 converter warps expanded W
+      mbar_init(&full_bar[i], W4 ? 1 + EPI_THREADS / 32 : 1);
+      mbar_init(&empty_bar[i], 1);
+      if (W4) mbar_init(&raw_full[i], 1);
+    }
     mbar_init(tmem_full_bar, DUAL ? 2 : 1);
     fence_mbar_init();
   }
@@ -284,16 +305,20 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // uniform-datapath instruction in a waterfall loop.
     {
       const uint32_t a_bytes = (KIND == KIND_CONV) ? p.a_tx_bytes : static_cast<uint32_t>(L::A_SUB);
+      // W4: the packed tile (BN rows x 64 bytes, unswizzled) lands in the UPPER half of the
+      // sub-slot and completes on raw_full; the converter warps expand it in place
+      constexpr int WK = W4 ? BLOCK_K / 2 : BLOCK_K;           // bytes of K per k-block in memory
       auto load_w = [&](int kb, int stage, int u) {
-        uint8_t* w_dst = sW + stage * L::W_BYTES + u * L::W_SUB;
+        uint8_t* w_dst = sW + stage * L::W_BYTES + u * L::W_SUB + (W4 ? L::W_SUB / 2 : 0);
+        uint64_t* bar = W4 ? &raw_full[stage] : &full_bar[stage];
         if (KIND == KIND_CONV) {
           const int tap = kb / p.kb_per_tap;
-          const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
-          tma_load_3d(w_dst, &tmW, &full_bar[stage], c0, tap, n_tile0);
+          const int c0 = (kb - tap * p.kb_per_tap) * WK;
+          tma_load_3d(w_dst, &tmW, bar, c0, tap, n_tile0);
         } else if (KIND == KIND_SPLIT && kb >= p.num_kb) {
-          tma_load_2d(w_dst, &tmW1, &full_bar[stage], (kb - p.num_kb) * BLOCK_K, n_tile0);
+          tma_load_2d(w_dst, &tmW1, bar, (kb - p.num_kb) * WK, n_tile0);
         } else {
-          tma_load_2d(w_dst, &tmW, &full_bar[stage], kb * BLOCK_K, n_tile0);
+          tma_load_2d(w_dst, &tmW, bar, kb * WK, n_tile0);
         }
       };
       auto load_a = [&](int kb, int stage, int u) {
@@ -310,18 +335,14 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BLOCK_K, m0);
         }
       };
-      const bool skip = (p.dbg_mode & 2) != 0;
-      // ring stage si holds k-blocks kb_begin + si*KSUB .. (+KSUB-1); the last one may be short
-      const int nkb = kb_end - kb_begin;
-      const int nst = (nkb + L::KSUB - 1) / L::KSUB;
-      auto nsub_of = [&](int si) { const int rem = nkb - si * L::KSUB; return rem < L::KSUB ? rem : L::KSUB; };
+      const bool skip = W4 ? false : (p.dbg_mode & 2) != 0;
       // prologue: weights of the first ring-full of stages do not depend on the preceding
       // kernel -> issue them before the programmatic-dependency wait
-      const int npre = nst < STAGES ? nst : STAGES;
       if (!skip && elect_one()) {
         for (int i = 0; i < npre; ++i) {
           const int ns = nsub_of(i);
-          mbar_expect_tx(&full_bar[i], ns * (a_bytes + L::W_SUB));
+          if (W4) mbar_expect_tx(&raw_full[i], ns * (L::W_SUB / 2));
+          else mbar_expect_tx(&full_bar[i], ns * (a_bytes + L::W_SUB));
           for (int u = 0; u < ns; ++u) load_w(kb_begin + i * L::KSUB + u, i, u);
         }
         // warm the path of the first A tile (L2 prefetch: its contents are not consumed)
@@ -346,6 +367,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int i = 0; i < npre; ++i) {
           if (skip) { mbar_arrive(&full_bar[i]); continue; }
           const int ns = nsub_of(i);
+          if (W4) mbar_expect_tx(&full_bar[i], ns * a_bytes);
           for (int u = 0; u < ns; ++u) load_a(kb_begin + i * L::KSUB + u, i, u);
         }
       }
@@ -359,7 +381,12 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             mbar_arrive(&full_bar[stage]);
           } else {
             const int ns = nsub_of(si);
-            mbar_expect_tx(&full_bar[stage], ns * (a_bytes + L::W_SUB));
+            if (W4) {
+              mbar_expect_tx(&raw_full[stage], ns * (L::W_SUB / 2));
+              mbar_expect_tx(&full_bar[stage], ns * a_bytes);
+            } else {
+              mbar_expect_tx(&full_bar[stage], ns * (a_bytes + L::W_SUB));
+            }
             for (int u = 0; u < ns; ++u) {
               load_w(kb_begin + si * L::KSUB + u, stage, u);
               load_a(kb_begin + si * L::KSUB + u, stage, u);
@@ -381,8 +408,6 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // address field (the low word) by constants
       const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
       const uint64_t w_desc0 = umma_desc_sw128(smem_u32(sW));
-      const int nkb = kb_end - kb_begin;
-      const int nst = (nkb + L::KSUB - 1) / L::KSUB;
       constexpr int STEP = DUAL ? 2 : 1;
       bool first = true;
       for (int si = which; si < nst; si += STEP) {
@@ -425,8 +450,55 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else {
     // ============ epilogue warps 2..9: stage the per-column operands, wait for the MMAs ========
-    pdl_wait();                            // dynamic-quantisation scalars come from the predecessor
     const int et = threadIdx.x - 64;  // 0..255
+    // W4: expand the packed weight tiles of ring stages [s0, s1) in place (see the header)
+    auto convert_stages = [&](int s0, int s1) {
+      constexpr int CPS = BN * 4;                        // 16-byte packed chunks per k-block
+      constexpr int PT = (L::KSUB * CPS + EPI_THREADS - 1) / EPI_THREADS;
+#pragma unroll 1
+      for (int si = s0; si < s1; ++si) {
+        const int stage = si % STAGES;
+        mbar_wait(&raw_full[stage], static_cast<uint32_t>(si / STAGES) & 1u);
+        const int nch = nsub_of(si) * CPS;
+        uint8_t* wst = sW + stage * L::W_BYTES;
+        uint4 pk[PT];
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+          const int i = et + j * EPI_THREADS;
+          if (i < nch) {
+            const int u = i / CPS, c = i - u * CPS;
+            pk[j] = *reinterpret_cast<const uint4*>(wst + u * L::W_SUB + L::W_SUB / 2 + c * 16);
+          }
+        }
+        epi_bar_sync();                    // every packed chunk is in registers: overwrite
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+          const int i = et + j * EPI_THREADS;
+          if (i < nch) {
+            const int u = i / CPS, c = i - u * CPS;
+            const int row = c >> 2, cpos = c & 3;
+            const uint32_t pw[4] = {pk[j].x, pk[j].y, pk[j].z, pk[j].w};
+            uint32_t o[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t e = pw[q] & 0xF0F0F0F0u;          // even k: already in the high half
+              const uint32_t d = (pw[q] << 4) & 0xF0F0F0F0u;   // odd k: low nibble moved up
+              o[2 * q] = __byte_perm(e, d, 0x5140);            // k0 k1 k2 k3
+              o[2 * q + 1] = __byte_perm(e, d, 0x7362);        // k4 k5 k6 k7
+            }
+            uint8_t* rowp = wst + u * L::W_SUB + row * 128;
+            const int sw = row & 7;                            // 128B swizzle: chunk ^= row % 8
+            *reinterpret_cast<uint4*>(rowp + (((2 * cpos) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(rowp + (((2 * cpos + 1) ^ sw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+        fence_proxy_async_smem();          // generic-proxy writes -> visible to the MMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[stage]);
+      }
+    };
+    if (W4) convert_stages(0, npre);       // weights do not depend on the predecessor
+    pdl_wait();                            // dynamic-quantisation scalars come from the predecessor
     for (int j = et; j < BN; j += EPI_THREADS) {
       const int n = n_tile0 + j;
       const bool ok = n < p.N;
@@ -476,6 +548,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
     epi_bar_sync();                        // named barrier among the 256 epilogue threads
+    if (W4) convert_stages(npre, nst);
   }
   // every epilogue path waits for the accumulators itself (after prefetching what it can)
   auto wait_accumulators = [&]() {
@@ -487,7 +560,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncwarp();
   const bool is_epi = warp >= 2 && warp < 10;
   // second accumulator in use? (DUAL kernels whose K range spans more than one ring stage)
-  const bool dual_used = DUAL && ((kb_end - kb_begin + L::KSUB - 1) / L::KSUB) > 1;
+  const bool dual_used = DUAL && nst > 1;
   const bool has_bias = p.bias != nullptr;
   const int quarter = warp & 3;          // TMEM lane quarter this warp may access
   const int ehalf = (warp - 2) >> 2;     // which half of the tile's columns this epilogue warp takes
@@ -563,6 +636,10 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int j = 0; j < 32; ++j) v[j] += v2[j];
         } else {
           tmem_ld_wait();
+        }
+        if (W4) {                      // codes were expanded as 16*w: exact arithmetic shift
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = static_cast<uint32_t>(static_cast<int32_t>(v[j]) >> 4);
         }
         const bool cols_ok = n_tile0 + c * 32 + 32 <= p.N;
         if (ri.ok && cols_ok) {
@@ -670,6 +747,10 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (DUAL && dual_used) {       // the two issuers' accumulators: exact int32 sum
 #pragma unroll
           for (int j = 0; j < CH; ++j) v[j] += v1[j];
+        }
+        if (W4) {                      // codes were expanded as 16*w: exact arithmetic shift
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = static_cast<uint32_t>(static_cast<int32_t>(v[j]) >> 4);
         }
         if (ri.ok) {
 #pragma unroll
@@ -794,6 +875,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int s = 0; s < 8; ++s) {
             acc[0] += x[u][s].x; acc[1] += x[u][s].y; acc[2] += x[u][s].z; acc[3] += x[u][s].w;
           }
+          if (W4) { acc[0] >>= 4; acc[1] >>= 4; acc[2] >>= 4; acc[3] >>= 4; }
           const int col = cc[u];
           if (p.acc_out != nullptr && n_tile0 + col + 4 <= p.N)
             *reinterpret_cast<int4*>(p.acc_out + ri2[u].out_row * p.N + n_tile0 + col) =

@@ -9,7 +9,8 @@ oracle: quant_utils/qdiff/models/quant_block_forward_func.py:54-66) so that
   * the op that produces a quantized layer's input is fused with the dynamic quantisation of its
     result: LayerNorm -> int8 (to_q/k/v, ff.net.0.proj), GroupNorm[+SiLU] -> int8 (resnet convs,
     proj_in), GEGLU -> int8 (ff.net.2)                        [csrc/fused_quant.cu];
-  * layers that consume the SAME tensor run as ONE contraction over N-concatenated weights:
+  * layers that consume the SAME tensor run as ONE contraction over N-concatenated weights (one
+    per weight kind when W8 and packed-W4 layers share an input):
     attn1.to_q/to_k/to_v; every attn2.to_k/to_v of the UNet (they all read
     `encoder_hidden_states`); every resnet `time_emb_proj` (they all read silu(temb));
   * the fp16 elementwise op that follows a layer runs in its epilogue: residual adds
@@ -19,8 +20,8 @@ Arithmetic is unchanged: with dynamic per-tensor scales the quantized codes of a
 identical for all its consumers, per-output-channel weight scales make N-concatenation exact, and
 every fused elementwise op keeps its own fp16 rounding (tests/test_gpu_fused.py,
 tests/test_gpu_modules.py::test_fused_unet_matches_unfused). A block is fused only if all the
-layers involved are dynamic W8A8 `QuantizedLinear` / `QuantizedConv2d` on the tcgen05 path;
-anything else (static checkpoints, W4 linears, fp16-protected layers) keeps the stock forward.
+layers involved are dynamic W8A8 / W4A8 `QuantizedLinear` / `QuantizedConv2d` on the tcgen05 path;
+anything else (static checkpoints, fp16-protected layers) keeps the stock forward.
 
 Call it after the model sits on its CUDA device: concatenated weights become the storage of the
 member layers' `weight_int` buffers (views), which a later `.to(device)` would split again.
@@ -43,8 +44,22 @@ from .nn.linear import QuantizedLinear
 # eligibility
 # ---------------------------------------------------------------------------------------------
 def _lin_ok(m) -> bool:
-    return (isinstance(m, QuantizedLinear) and m.valid_for_acceleration and m.dynamic
-            and m.w_kind == "w8" and m.in_features % 16 == 0 and m.out_features % 8 == 0)
+    if not (isinstance(m, QuantizedLinear) and m.valid_for_acceleration and m.dynamic):
+        return False
+    k_align = 32 if m.w_kind == "w4" else 16
+    return m.in_features % k_align == 0 and m.out_features % 8 == 0
+
+
+def _lin_weight(m: QuantizedLinear) -> torch.Tensor:
+    """int8 codes [N, K] (W8) or packed uint8 [N, K/2] (W4): ops dispatch on the dtype"""
+    return m.weight_int if m.w_kind == "w8" else m.weight_int4
+
+
+def _set_lin_weight(m: QuantizedLinear, w: torch.Tensor) -> None:
+    if m.w_kind == "w8":
+        m.weight_int = w
+    else:
+        m.weight_int4 = w
 
 
 def _conv_ok(m) -> bool:
@@ -52,6 +67,8 @@ def _conv_ok(m) -> bool:
         return False
     pad, stride, k = m.padding[0], m.stride[0], m.kernel_size[0]
     geom = stride in (1, 2) and (pad == 0 or (pad == 1 and k == 3))
+    if getattr(m, "weight_int4", None) is not None and m.split != 0:
+        return False                       # packed W4 split shortcut: two convolutions, unfused
     return geom and m.in_channels % 16 == 0 and m.out_channels % 8 == 0 and \
         (m.split == 0 or (m.split % 16 == 0 and k == 1 and pad == 0 and stride == 1))
 
@@ -72,52 +89,85 @@ def _ln_ok(norm: nn.LayerNorm) -> bool:
 # N-concatenated linears
 # ---------------------------------------------------------------------------------------------
 class CatLinear:
-    """Several dynamic W8A8 linears with the same in_features, run as one GEMM. The members'
-    buffers become views of the concatenated storage (no second copy of the weights)."""
+    """Several dynamic linears with the same in_features, run as one GEMM per weight kind (W8
+    codes / packed W4: N-concatenation needs one storage format). The members' buffers become
+    views of the concatenated storage (no second copy of the weights)."""
 
     def __init__(self, mods: List[QuantizedLinear]):
         assert len({m.in_features for m in mods}) == 1
         self.mods = mods
         self.sizes = [m.out_features for m in mods]
-        self.weight_int = torch.cat([m.weight_int for m in mods], dim=0)
-        self.weight_scales = torch.cat([m.weight_scales for m in mods])
-        self.wsum = torch.cat([m.weight_sum_by_input_channels for m in mods])
         has_bias = [m.bias is not None for m in mods]
         assert all(has_bias) or not any(has_bias)
-        self.bias = torch.cat([m.bias for m in mods]) if all(has_bias) else None
-        off = 0
-        self.offsets = []
-        for m, n in zip(mods, self.sizes):
-            m.weight_int = self.weight_int[off:off + n]
-            m.weight_scales = self.weight_scales[off:off + n]
-            m.weight_sum_by_input_channels = self.wsum[off:off + n]
-            if self.bias is not None:
-                m.bias = self.bias[off:off + n]
-            self.offsets.append(off)
-            off += n
-        self.n_total = off
+        self.parts = []                      # one (weight, scales, wsum, bias, n) per weight kind
+        self.where = []                      # member i -> (part index, column offset)
+        slot = {}
+        for kind in ("w8", "w4"):
+            members = [m for m in mods if m.w_kind == kind]
+            if not members:
+                continue
+            weight = torch.cat([_lin_weight(m) for m in members], dim=0)
+            scales = torch.cat([m.weight_scales for m in members])
+            wsum = torch.cat([m.weight_sum_by_input_channels for m in members])
+            bias = torch.cat([m.bias for m in members]) if all(has_bias) else None
+            off = 0
+            for m in members:
+                n = m.out_features
+                _set_lin_weight(m, weight[off:off + n])
+                m.weight_scales = scales[off:off + n]
+                m.weight_sum_by_input_channels = wsum[off:off + n]
+                if bias is not None:
+                    m.bias = bias[off:off + n]
+                slot[id(m)] = (len(self.parts), off)
+                off += n
+            self.parts.append((weight, scales, wsum, bias, off))
+        self.where = [slot[id(m)] for m in mods]
+        self.n_total = sum(self.sizes)
+        # single-kind views kept for callers / tests that look at the concatenated operands
+        self.weight_int, self.weight_scales, self.wsum, self.bias, _ = self.parts[0]
+
+    def run_parts(self, q8, scale, zp):
+        """one output tensor per weight kind"""
+        return [ops.qlinear_dynamic_fused(q8, w, sc, scale, zp, ws, b)
+                for (w, sc, ws, b, _) in self.parts]
 
     def run(self, q8, scale, zp):
-        return ops.qlinear_dynamic_fused(q8, self.weight_int, self.weight_scales, scale, zp,
-                                         self.wsum, self.bias)
+        """[..., n_total] in member order (single weight kind: the GEMM output itself)"""
+        outs = self.run_parts(q8, scale, zp)
+        if len(outs) == 1:
+            return outs[0]
+        return torch.cat([self.slice_of(outs, i) for i in range(len(self.mods))], dim=-1)
+
+    def slice_of(self, outs, i: int) -> torch.Tensor:
+        part, off = self.where[i]
+        return outs[part][..., off:off + self.sizes[i]]
 
 
 class GegluLinear:
-    """ff.net.0.proj with the GEGLU in its epilogue: an interleaved copy of the projection's
-    int8 rows / scales / sums / bias (16 value rows, then their 16 gate rows), so one accumulator
-    chunk holds both operands of 16 outputs. The module's own buffers stay untouched."""
+    """ff.net.0.proj with the GEGLU in its epilogue: the projection's rows / scales / sums / bias
+    re-ordered in place (16 value rows, then their 16 gate rows), so one accumulator chunk holds
+    both operands of 16 outputs. The interleaved order becomes the module's STORED layout —
+    `mod.geglu_interleaved = True` — instead of a second copy of a 13 MB weight per block; the
+    module's own (unfused) forward and its state_dict undo the permutation on the way out."""
 
     def __init__(self, mod: QuantizedLinear):
         inner = mod.out_features // 2
-        idx = ops.geglu_interleave_index(inner, mod.weight_int.device)
-        self.weight_int = mod.weight_int.index_select(0, idx).contiguous()
-        self.weight_scales = mod.weight_scales.index_select(0, idx).contiguous()
-        self.wsum = mod.weight_sum_by_input_channels.index_select(0, idx).contiguous()
-        self.bias = None if mod.bias is None else mod.bias.index_select(0, idx).contiguous()
+        idx = ops.geglu_interleave_index(inner, mod.weight_scales.device)
+        if not getattr(mod, "geglu_interleaved", False):
+            _set_lin_weight(mod, _lin_weight(mod).index_select(0, idx).contiguous())
+            mod.weight_scales = mod.weight_scales.index_select(0, idx).contiguous()
+            mod.weight_sum_by_input_channels = \
+                mod.weight_sum_by_input_channels.index_select(0, idx).contiguous()
+            if mod.bias is not None:
+                mod.bias = mod.bias.index_select(0, idx).contiguous()
+            mod.geglu_interleaved = True
+            mod.register_buffer("geglu_inverse_index", torch.argsort(idx), persistent=False)
+        self.mod = mod
 
     def run(self, q8, scale, zp):
-        return ops.qlinear_geglu_quantize_dynamic(q8, self.weight_int, self.weight_scales, scale,
-                                                  zp, self.wsum, self.bias)
+        m = self.mod
+        return ops.qlinear_geglu_quantize_dynamic(q8, _lin_weight(m), m.weight_scales, scale, zp,
+                                                  m.weight_sum_by_input_channels, m.bias)
 
 
 class SharedInputGroup:
@@ -138,7 +188,10 @@ class SharedInputGroup:
         self.pre = pre
         self.bos = bos
         if bos:
-            self.bos_rows = torch.cat([m.bos_pre_computed for m in mods], dim=-1)   # [1,1,Ntot]
+            # pre-computed first-token rows, one [1, 1, N_part] tensor per weight kind
+            self.bos_rows = [torch.cat([m.bos_pre_computed for m in mods if m.w_kind == kind],
+                                       dim=-1)
+                             for kind in ("w8", "w4") if any(m.w_kind == kind for m in mods)]
         self._key = None
         self._out = None
 
@@ -154,25 +207,24 @@ class SharedInputGroup:
                 xin = xin[:, 1:, :]
             q8, s, z = _quant_tokens(xin) if xin.dim() == 3 else \
                 ops.quantize_per_tensor_dynamic(xin)
-            out = self.cat.run(q8, s, z)
+            outs = self.cat.run_parts(q8, s, z)
             if self.bos:
-                out = torch.cat([self.bos_rows.expand(out.shape[0], -1, -1), out], dim=1)
+                outs = [torch.cat([rows.expand(o.shape[0], -1, -1), o], dim=1)
+                        for rows, o in zip(self.bos_rows, outs)]
             self._key = key
-            self._out = out
-        i = self.index[id(mod)]
-        off = self.cat.offsets[i]
-        return self._out[..., off:off + self.cat.sizes[i]]
+            self._out = outs
+        return self.cat.slice_of(self._out, self.index[id(mod)])
 
 
 def _run_linear(m: QuantizedLinear, q8, s, z, residual=None):
-    return ops.qlinear_dynamic_fused(q8, m.weight_int, m.weight_scales, s, z,
+    return ops.qlinear_dynamic_fused(q8, _lin_weight(m), m.weight_scales, s, z,
                                      m.weight_sum_by_input_channels, m.bias, residual)
 
 
 def _run_conv(m: QuantizedConv2d, q8, s, z, chan_add=None, residual=None):
     pad = m.padding[0]
     return ops.qconv2d_dynamic_fused(
-        q8, m.weight_int, m.weight_scales, s, z,
+        q8, m._weight(""), m.weight_scales, s, z,
         m.weight_sum_by_input_channels if pad > 0 else None,
         m.weight_sum_per_output_channel if pad == 0 else None,
         m.bias, m.stride[0], pad, chan_add, residual)
@@ -279,8 +331,10 @@ def fused_transformer_block_forward(self, hidden_states, *args, **kwargs):
     c = x.shape[-1]
     # --- self-attention ---
     q8, s, z = ops.layernorm_quantize_dynamic(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
-    qkv = f["qkv"].run(q8, s, z)
-    o = _attention(qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:], self.attn1.heads)
+    cat = f["qkv"]
+    outs = cat.run_parts(q8, s, z)
+    o = _attention(cat.slice_of(outs, 0), cat.slice_of(outs, 1), cat.slice_of(outs, 2),
+                   self.attn1.heads)
     o8, s, z = _quant_tokens(o)
     x = _run_linear(self.attn1.to_out[0], o8, s, z, residual=x)
     # --- cross-attention ---

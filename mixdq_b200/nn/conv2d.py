@@ -19,7 +19,8 @@ import torch.nn.functional as F
 from torch.ao.quantization import QConfig
 
 from .. import ops
-from .utils import create_qparams_from_dtype, minmax_weight_scales, quantize_weight, QParam
+from .utils import (create_qparams_from_dtype, minmax_weight_scales, pack_int4, quantize_weight,
+                    unpack_int4, QParam)
 
 __all__ = ["QuantizedConv2d"]
 
@@ -138,9 +139,14 @@ class QuantizedConv2d(nn.Module):
                         dtype=w_dtype).int_repr()
                 else:
                     w_int = quantize_weight(w, scales, new_mod.w_bits, exact_division=dynamic)
-                # KRSC storage: what the implicit-GEMM kernel consumes (qconv2d.cc:94-95)
-                new_mod.register_buffer("weight_int" + sfx,
-                                        w_int.contiguous(memory_format=torch.channels_last))
+                # KRSC storage: what the implicit-GEMM kernel consumes (qconv2d.cc:94-95).
+                # 4-bit layers the tcgen05 kernel can take are stored PACKED (KRS(C/2), even c in
+                # the high nibble) as `weight_int4`; the rest keep one code per int8.
+                w_int = w_int.contiguous(memory_format=torch.channels_last)
+                if new_mod.w_bits == 4 and new_mod._w4_packable(w.shape[1]):
+                    new_mod.register_buffer("weight_int4" + sfx, pack_int4(w_int, dim=1))
+                else:
+                    new_mod.register_buffer("weight_int" + sfx, w_int)
                 if pad0:
                     wsum = w_int.float().sum(dim=[1, 2, 3])
                     if new_mod.dynamic:
@@ -175,11 +181,31 @@ class QuantizedConv2d(nn.Module):
             return "QuantizedConv2dW8A8" if self.w_bits == 8 else "QuantizedConv2dW4A8"
         return "QuantizedConv2dFPFallback"
 
+    def _w4_packable(self, c_in: int) -> bool:
+        """geometry / alignment the packed-weight tcgen05 convolution takes (capi.cu conv_common)"""
+        stride, pad, k = self.stride[0], self.padding[0], self.kernel_size[0]
+        return (c_in % 32 == 0 and self.out_channels % 8 == 0 and stride in (1, 2)
+                and self.kernel_size[0] == self.kernel_size[1]
+                and (pad == 0 or (pad == 1 and k == 3)))
+
+    def _weight(self, sfx: str) -> torch.Tensor:
+        """the layer's weight operand: packed uint8 (`weight_int4*`) or int8 codes"""
+        w = getattr(self, "weight_int4" + sfx, None)
+        return w if w is not None else getattr(self, "weight_int" + sfx)
+
     # ------------------------------------------------------------------------------------
     def forward_fallback(self, x: torch.Tensor):
+        """Non-fp16 input: float conv on the DEQUANTISED weight — warns once per module."""
+        if not getattr(self, "_warned_fallback", False):
+            self._warned_fallback = True
+            logging.warning(f"{self._get_name()} {self.module_name}: input dtype {x.dtype} is not "
+                            "fp16; running F.conv2d on the dequantised weight (no int8 kernel)")
+
         def deq(sfx):
-            w = getattr(self, "weight_int" + sfx).float() * \
-                getattr(self, "weight_scales" + sfx)[:, None, None, None]
+            w = self._weight(sfx)
+            if w.dtype == torch.uint8:
+                w = unpack_int4(w, dim=1)
+            w = w.float() * getattr(self, "weight_scales" + sfx)[:, None, None, None]
             return w.to(x.dtype)
         bias = self.bias.to(x.dtype) if self.bias is not None else None
         args = (self.stride, self.padding, self.dilation, self.groups)
@@ -191,7 +217,7 @@ class QuantizedConv2d(nn.Module):
     def _half(self, x, sfx, c0, c1, bias):
         """quantise channels [c0,c1) of x and run one conv; returns fp16 channels_last."""
         stride, pad = self.stride[0], self.padding[0]
-        w_int = getattr(self, "weight_int" + sfx)
+        w_int = self._weight(sfx)
         if self.dynamic:
             xs = x if (c0 == 0 and c1 == x.shape[1]) else x[:, c0:c1]
             ksel = c1 - c0
@@ -237,8 +263,9 @@ class QuantizedConv2d(nn.Module):
         C = x.shape[1]
         if self.split == 0:
             return self._half(x, "", 0, C, self.bias)
-        fused = (not self.dynamic and self.kernel_size[0] == 1 and self.kernel_size[1] == 1
-                 and self.padding[0] == 0 and self.stride[0] == 1)
+        packed = getattr(self, "weight_int4", None) is not None   # W4: two convs + fp16 add
+        fused = (not self.dynamic and not packed and self.kernel_size[0] == 1
+                 and self.kernel_size[1] == 1 and self.padding[0] == 0 and self.stride[0] == 1)
         if fused:
             xa = ops.quantize_to_nhwc(x, self.act_scales_inv, self.act_zero_points, 0, self.split)
             xb = ops.quantize_to_nhwc(x, self.act_scales_inv_0, self.act_zero_points_0,
@@ -246,7 +273,7 @@ class QuantizedConv2d(nn.Module):
             return ops.qconv1x1_split_w8_a8_ohalf(xa, self.weight_int, self.scale, self.bias0,
                                                   xb, self.weight_int_0, self.scale_0,
                                                   self.bias0_0, self.bias)
-        fused_dyn = (self.dynamic and self.kernel_size[0] == 1 and self.kernel_size[1] == 1
+        fused_dyn = (self.dynamic and not packed and self.kernel_size[0] == 1 and self.kernel_size[1] == 1
                      and self.padding[0] == 0 and self.stride[0] == 1 and self.split % 16 == 0
                      and (C - self.split) % 16 == 0 and self.out_channels % 8 == 0)
         if fused_dyn:

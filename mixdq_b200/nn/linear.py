@@ -4,7 +4,8 @@ Same constructor / `from_float(float_mod, split=0, ckpt=None)` / buffer names / 
 / BOS special case, so `quantize.convert` and state_dicts are interchangeable. Differences:
   * the forward runs on the sm_100a kernels behind include/mixdq_b200.h (through mixdq_b200.ops);
   * 4-bit weights (`torch.quint4x2` qconfig, the reference's FP fallback, nn/Linear.py:28-36) run
-    as true W4A8 with packed weights (`weight_int4`);
+    as true W4A8: `weight_int4` holds the packed codes (uint8 [N, K/2], even k in the high nibble,
+    nn/utils.py:26-28), which the tcgen05 kernel unpacks on the fly;
   * `ckpt=None` selects dynamic mode: qdiff min-max weight scales computed here, activations
     quantised per call from their own min/max (reference base_quantizer.py:155-190).
 """
@@ -158,6 +159,12 @@ class QuantizedLinear(nn.Module):
         return (w * self.weight_scales[:, None]).to(dtype)
 
     def forward_fallback(self, x):
+        """Non-fp16 input: the int8 kernels only take fp16 activations, so the layer runs as a
+        float op on the DEQUANTISED weight — never silently: warns once per module."""
+        if not getattr(self, "_warned_fallback", False):
+            self._warned_fallback = True
+            logging.warning(f"{self._get_name()} {self.module_name}: input dtype {x.dtype} is not "
+                            "fp16; running F.linear on the dequantised weight (no int8 kernel)")
         return F.linear(x, self._dequantized_weight(x.dtype),
                         self.bias.to(x.dtype) if self.bias is not None else None)
 
@@ -168,9 +175,10 @@ class QuantizedLinear(nn.Module):
                 return ops.qlinear_w8_a8_ohalf_dynamic(
                     x_int, self.weight_int, self.weight_scales, a_scale, a_zp,
                     self.weight_sum_by_input_channels, self.bias)
-            scale = self.weight_scales * a_scale
-            bias0 = self.weight_sum_by_input_channels * a_zp
-            return ops.qlinear_w4_a8_ohalf(x_int, self.weight_int4, scale, bias0, self.bias)
+            # packed 4-bit weights, unpacked inside the tcgen05 kernel; the activation scalars
+            # are folded in its epilogue
+            return ops.qlinear_dynamic_fused(x_int, self.weight_int4, self.weight_scales, a_scale,
+                                             a_zp, self.weight_sum_by_input_channels, self.bias)
         x_int = ops.quantize_per_tensor_to_int8(x, self.act_scales_inv, self.act_zero_points)
         if self.w_kind == "w8":
             return ops.qlinear_w8_a8_ohalf(
@@ -179,13 +187,30 @@ class QuantizedLinear(nn.Module):
                 self.bias)
         return ops.qlinear_w4_a8_ohalf(x_int, self.weight_int4, self.scale, self.bias0, self.bias)
 
+    # ---- GEGLU-interleaved stored layout (mixdq_b200.fused.GegluLinear) ---------------------
+    # When the block-level fusion evaluates the GEGLU in this projection's epilogue the rows are
+    # STORED interleaved (16 value rows, their 16 gate rows, ...). The module's own forward and
+    # its state_dict keep the stock row order by undoing the permutation on the way out.
+    def _stock_order(self, t: torch.Tensor, dim: int) -> torch.Tensor:
+        if getattr(self, "geglu_interleaved", False):
+            return t.index_select(dim, self.geglu_inverse_index.to(t.device))
+        return t
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        if getattr(self, "geglu_interleaved", False):
+            for k in ("weight_int", "weight_int4", "weight_scales", "weight_zero_points",
+                      "weight_sum_by_input_channels", "scale", "bias0", "bias"):
+                if prefix + k in destination:
+                    destination[prefix + k] = self._stock_order(destination[prefix + k], 0)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not self.valid_for_acceleration:
             return F.linear(x, self.weight, self.bias)
         if x.dtype != torch.float16:
-            return self.forward_fallback(x)
+            return self._stock_order(self.forward_fallback(x), -1)
         if not getattr(self, "bos", False):
-            return self._qlinear(x)
+            return self._stock_order(self._qlinear(x), -1)
         # BOS-aware cross-attention K/V: the first text token bypasses quantisation and takes a
         # pre-computed fp16 output (reference nn/Linear.py:178-194).
         out_rest = self._qlinear(x[:, 1:, :])

@@ -111,16 +111,24 @@ def quantize_weight(weight: torch.Tensor, scales: torch.Tensor, n_bits: int = 8,
     return torch.clamp(q, lo, hi).to(torch.int8)
 
 
-def pack_int4(codes: torch.Tensor) -> torch.Tensor:
-    """int8 codes in [-8, 7] -> uint8 [..., K/2]: even index in the HIGH nibble (the reference's
-    only packing convention, nn/utils.py:26-28), two's-complement nibbles."""
-    assert codes.shape[-1] % 2 == 0
-    c = codes.to(torch.int16)
-    return (((c[..., 0::2] & 0xF) << 4) | (c[..., 1::2] & 0xF)).to(torch.uint8)
+def pack_int4(codes: torch.Tensor, dim: int = -1) -> torch.Tensor:
+    """int8 codes in [-8, 7] -> uint8 with `dim` halved: even index in the HIGH nibble (the
+    reference's only packing convention, nn/utils.py:26-28 — last dim, or dim 1 for 4-D conv
+    weights, :20-24), two's-complement nibbles. A channels_last 4-D input packed along dim 1 stays
+    channels_last, i.e. KRS(C/2) in memory — what the W4 convolution kernel consumes."""
+    assert codes.shape[dim] % 2 == 0
+    c = codes.to(torch.int16).movedim(dim, -1)
+    packed = (((c[..., 0::2] & 0xF) << 4) | (c[..., 1::2] & 0xF)).to(torch.uint8).movedim(-1, dim)
+    if codes.dim() == 4 and codes.is_contiguous(memory_format=torch.channels_last):
+        return packed.contiguous(memory_format=torch.channels_last)
+    return packed.contiguous()
 
 
-def unpack_int4(packed: torch.Tensor) -> torch.Tensor:
-    p = packed.to(torch.int16)
+def unpack_int4(packed: torch.Tensor, dim: int = -1) -> torch.Tensor:
+    p = packed.to(torch.int16).movedim(dim, -1)
     both = torch.stack([(p >> 4) & 0xF, p & 0xF], dim=-1)
-    both = both.reshape(*packed.shape[:-1], packed.shape[-1] * 2)
-    return torch.where(both >= 8, both - 16, both).to(torch.int8)
+    both = both.reshape(*p.shape[:-1], p.shape[-1] * 2)
+    out = torch.where(both >= 8, both - 16, both).to(torch.int8).movedim(-1, dim)
+    if packed.dim() == 4 and packed.is_contiguous(memory_format=torch.channels_last):
+        return out.contiguous(memory_format=torch.channels_last)
+    return out.contiguous()

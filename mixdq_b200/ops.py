@@ -433,6 +433,11 @@ def qlinear_w4_a8_ohalf(input_int8, weight_packed, scale, bias0, bias=None,
     return out
 
 
+def _is_w4(weight: torch.Tensor) -> bool:
+    """Packed 4-bit weights are uint8 (two codes per byte); int8 tensors are W8 codes."""
+    return weight.dtype == torch.uint8
+
+
 def qlinear_fp_reference(input: torch.Tensor, weight: torch.Tensor,
                          bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Debug fp16 GEMM input[M,K] @ weight[K,N] (qlinear.cc:141-204; the reference ignores bias).
@@ -478,7 +483,8 @@ def qconv2d_w8_a8_ohalf(input_int8, weight_int8, weight_scale, input_scale, inpu
     if bias is not None:
         _check(dev == bias.device, "input and bias should be on the same device.")
     _check(input_int8.dtype == torch.int8, "input_int8 should be int8 type")
-    _check(weight_int8.dtype == torch.int8, "weight_int8 should be int8 type")
+    w4 = _is_w4(weight_int8)     # extension: packed 4-bit weights, uint8 [K, C/2, R, S]
+    _check(w4 or weight_int8.dtype == torch.int8, "weight_int8 should be int8 type")
     _check(weight_scale.dtype == torch.float32,
            "Currently only support weight_scale with float32 type")
     _check(input_scale.dtype == torch.float32,
@@ -500,7 +506,8 @@ def qconv2d_w8_a8_ohalf(input_int8, weight_int8, weight_scale, input_scale, inpu
 
     n, c, h, w = input_int8.shape
     k, _, r, s = weight_int8.shape
-    _check(weight_int8.shape[1] == c, "input and weight channel counts should match")
+    _check(weight_int8.shape[1] * (2 if w4 else 1) == c,
+           "input and weight channel counts should match")
     p = (h + 2 * padding - dilation * (r - 1) - 1) // stride + 1
     q = (w + 2 * padding - dilation * (s - 1) - 1) // stride + 1
     _check(weight_scale.numel() == k,
@@ -529,12 +536,14 @@ def qconv2d_w8_a8_ohalf(input_int8, weight_int8, weight_scale, input_scale, inpu
                       memory_format=torch.channels_last)
     lib = _lib.load()
     with _DeviceGuard(x):
-        _launch("conv", lib.mixdq_conv_w8a8_f16,
+        _launch("conv_w4" if w4 else "conv",
+                lib.mixdq_conv_w4a8_f16 if w4 else lib.mixdq_conv_w8a8_f16,
                 (x.data_ptr(), pitch, wt.data_ptr(), scale.data_ptr(), _ptr(wsum),
                  _ptr(bias0) if padding == 0 else None, input_zero_point.data_ptr(), _ptr(bias),
                  out.data_ptr(), n, h, w, c, k, r, s, stride, padding, _ptr(_acc_out)), x,
                 keep=(x, wt, scale, wsum, bias0, input_zero_point, bias, out, _acc_out),
-                algo_bytes=_gemm_bytes(n * p * q, k, c * h * w // max(p * q, 1), k * c * r * s),
+                algo_bytes=_gemm_bytes(n * p * q, k, c * h * w // max(p * q, 1),
+                                       k * c * r * s // (2 if w4 else 1)),
                 algo_ops=2 * n * p * q * k * c * r * s)
     return out
 
@@ -582,8 +591,10 @@ def qlinear_dynamic_fused(input_int8, weight_int8, weight_scale, input_scale, in
                           weight_sum, bias=None, residual=None,
                           _acc_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """qlinear_w8_a8_ohalf_dynamic followed by `+ residual` (fp16, same shape as the output)
-    inside the epilogue: out = half(float(half(linear)) + float(residual))."""
-    N, K = weight_int8.shape
+    inside the epilogue: out = half(float(half(linear)) + float(residual)). `weight_int8` may be
+    a PACKED 4-bit weight (uint8 [N, K/2]): it then runs as W4A8, unpacked inside the kernel."""
+    w4 = _is_w4(weight_int8)
+    N, K = weight_int8.shape[0], weight_int8.shape[1] * (2 if w4 else 1)
     a = input_int8 if input_int8.is_contiguous() else input_int8.contiguous()
     M = a.numel() // K
     out = torch.empty((*input_int8.shape[:-1], N), dtype=torch.float16, device=a.device)
@@ -598,13 +609,15 @@ def qlinear_dynamic_fused(input_int8, weight_int8, weight_scale, input_scale, in
         residual = r2
     lib = _lib.load()
     with _DeviceGuard(a):
-        _launch("gemm", lib.mixdq_gemm_w8a8_f16_dyn_res,
+        _launch("gemm_w4" if w4 else "gemm",
+                lib.mixdq_gemm_w4a8_f16_dyn_res if w4 else lib.mixdq_gemm_w8a8_f16_dyn_res,
                 (a.data_ptr(), K, weight_int8.data_ptr(), weight_scale.data_ptr(),
                  weight_sum.data_ptr(), input_scale.data_ptr(), input_zero_point.data_ptr(),
                  _ptr(bias), res_ptr, ldr, out.data_ptr(), N, M, N, K, _ptr(_acc_out)), a,
                 keep=(a, weight_int8, weight_scale, weight_sum, input_scale, input_zero_point,
                       bias, residual, out, _acc_out),
-                algo_bytes=_gemm_bytes(M, N, K, N * K) + (2 * M * N if residual is not None else 0),
+                algo_bytes=_gemm_bytes(M, N, K, N * K // (2 if w4 else 1))
+                + (2 * M * N if residual is not None else 0),
                 algo_ops=2 * M * N * K)
     return out
 
@@ -615,7 +628,9 @@ def qconv2d_dynamic_fused(input_int8, weight_int8, weight_scale, input_scale, in
                           _acc_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Dynamic-scale conv (the activation scalars are folded in the epilogue) with the optional
     fused tails: `+ chan_add[:, :, None, None]` (fp16 [N, K]) then `+ residual` (fp16 NHWC
-    [N, K, P, Q]). input_int8 / weight_int8 must be channels_last."""
+    [N, K, P, Q]). input_int8 / weight_int8 must be channels_last. `weight_int8` may be a PACKED
+    4-bit weight (uint8 [K, C/2, R, S] channels_last = KRS(C/2) in memory)."""
+    w4 = _is_w4(weight_int8)
     n, c, h, w = input_int8.shape
     k, _, r, s = weight_int8.shape
     p = (h + 2 * padding - r) // stride + 1
@@ -642,14 +657,16 @@ def qconv2d_dynamic_fused(input_int8, weight_int8, weight_scale, input_scale, in
         ldca = chan_add.stride(0) if n > 1 else k
     lib = _lib.load()
     with _DeviceGuard(x):
-        _launch("conv", lib.mixdq_conv_w8a8_f16_dyn,
+        _launch("conv_w4" if w4 else "conv",
+                lib.mixdq_conv_w4a8_f16_dyn if w4 else lib.mixdq_conv_w8a8_f16_dyn,
                 (x.data_ptr(), pitch, wt.data_ptr(), weight_scale.data_ptr(), _ptr(wsum_krs),
                  _ptr(wsum_k), input_scale.data_ptr(), input_zero_point.data_ptr(), _ptr(bias),
                  _ptr(chan_add), ldca, _ptr(residual), out.data_ptr(), n, h, w, c, k, r, s, stride,
                  padding, _ptr(_acc_out)), x,
                 keep=(x, wt, weight_scale, wsum_krs, wsum_k, input_scale, input_zero_point, bias,
                       chan_add, residual, out, _acc_out),
-                algo_bytes=_gemm_bytes(n * p * q, k, c * h * w // max(p * q, 1), k * c * r * s)
+                algo_bytes=_gemm_bytes(n * p * q, k, c * h * w // max(p * q, 1),
+                                       k * c * r * s // (2 if w4 else 1))
                 + (2 * n * p * q * k if residual is not None else 0),
                 algo_ops=2 * n * p * q * k * c * r * s)
     return out
@@ -755,8 +772,10 @@ def qlinear_geglu_quantize_dynamic(input_int8, weight_il, weight_scale_il, input
                                    return_y: bool = False):
     """ff.net.0.proj (dynamic W8A8, rows interleaved by `geglu_interleave_index`) with the GEGLU in
     the GEMM epilogue, then the single-pass quantiser fed by the epilogue's min/max:
-    2 kernels for Linear -> GEGLU -> quantise. Returns (q int8 [..., inner], scale, zp[, y])."""
-    N2, K = weight_il.shape
+    2 kernels for Linear -> GEGLU -> quantise. Returns (q int8 [..., inner], scale, zp[, y]).
+    `weight_il` may be PACKED 4-bit (uint8 [N2, K/2], rows interleaved before packing)."""
+    w4 = _is_w4(weight_il)
+    N2, K = weight_il.shape[0], weight_il.shape[1] * (2 if w4 else 1)
     I = N2 // 2
     a = input_int8 if input_int8.is_contiguous() else input_int8.contiguous()
     M = a.numel() // K
@@ -766,13 +785,15 @@ def qlinear_geglu_quantize_dynamic(input_int8, weight_il, weight_scale_il, input
     lib = _lib.load()
     with _DeviceGuard(a):
         ws = _dynamic_workspace(a.device)
-        _launch("gemm_geglu", lib.mixdq_gemm_w8a8_geglu_f16_dyn,
+        _launch("gemm_geglu_w4" if w4 else "gemm_geglu",
+                lib.mixdq_gemm_w4a8_geglu_f16_dyn if w4 else lib.mixdq_gemm_w8a8_geglu_f16_dyn,
                 (a.data_ptr(), K, weight_il.data_ptr(), weight_scale_il.data_ptr(),
                  weight_sum_il.data_ptr(), input_scale.data_ptr(), input_zero_point.data_ptr(),
                  _ptr(bias_il), y.data_ptr(), I, M, N2, K, ws.data_ptr()), a,
                 keep=(a, weight_il, weight_scale_il, weight_sum_il, input_scale,
                       input_zero_point, bias_il, y, ws),
-                algo_bytes=M * K + N2 * K + 2 * M * I + 10 * N2, algo_ops=2 * M * N2 * K)
+                algo_bytes=M * K + N2 * K // (2 if w4 else 1) + 2 * M * I + 10 * N2,
+                algo_ops=2 * M * N2 * K)
         _launch("quant_premm", lib.mixdq_quant_i8_premm,
                 (y.data_ptr(), y.numel(), q.data_ptr(), qp.data_ptr(), qp.data_ptr() + 4,
                  ws.data_ptr()), y, keep=(y, q, qp, ws), algo_bytes=3 * y.numel())
