@@ -22,9 +22,10 @@ import bench  # noqa: E402
 
 def short(name: str) -> str:
     name = re.sub(r"^void\s+", "", name)
-    m = re.match(r"mixdq::tc_i8_kernel<(\d+),\s*(\d+),\s*(\d+)>", name)
+    m = re.match(r"mixdq::tc_i8_kernel<(\d+),\s*(\d+),\s*(\d+)(?:,\s*\(?\w*\)?(\w+))?>", name)
     if m:
-        return f"tc_i8<BN={m.group(1)},ST={m.group(2)},KIND={m.group(3)}>"
+        w4 = ",W4" if m.group(4) in ("true", "1") else ""
+        return f"tc_i8<BN={m.group(1)},ST={m.group(2)},KIND={m.group(3)}{w4}>"
     if name.startswith("at::"):
         parts = re.findall(r"at::native::(?:\(anonymous namespace\)::|<unnamed>::)?(\w+)", name)
         if parts:
