@@ -9,6 +9,7 @@
 
 #include "../../include/mixdq_b200.h"
 #include "simt.h"
+#include "persist.h"
 #include "tc_kernel.cuh"
 #include "quant_ws.cuh"
 
@@ -266,6 +267,21 @@ static void pick_tile(int m_tiles, int N, int total_kb, bool allow_split, cudaSt
   *splits_out = best_s;
 }
 
+static void read_force_env() {
+  if (g_force_bn < 0) {
+    const char* e = getenv("MIXDQ_FORCE_BN");
+    g_force_bn = e ? atoi(e) : 0;
+    const char* f = getenv("MIXDQ_FORCE_SPLITS");
+    if (f) g_force_splits = atoi(f);
+  }
+}
+// persistent kernel (tc_persist.cuh) for multi-wave problems, unless a tile shape is forced
+static int persist_bn(int m_tiles, int N, int num_kb, int kind) {
+  read_force_env();
+  if (g_force_bn > 0 || g_force_splits > 0) return 0;
+  return persist_pick_bn(m_tiles, N, num_kb, kind);
+}
+
 template <int KIND, bool W4 = false>
 static int dispatch_tc(int bn, dim3 grid, const CUtensorMap& a, const CUtensorMap& w,
                        const CUtensorMap& a1, const CUtensorMap& w1, const TcParams& p,
@@ -312,11 +328,13 @@ static int gemm_common(const int8_t* A, int64_t lda, const int8_t* W, const floa
 
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
-  int bn, splits;
-  pick_tile(m_tiles, N, num_kb, true, st, &bn, &splits);
+  const int pbn = persist_bn(m_tiles, N, num_kb, KIND_GEMM);
+  const int pcs = pbn ? persist_cluster_size(m_tiles) : 1;
+  int bn = pbn, splits = 1;
+  if (!pbn) pick_tile(m_tiles, N, num_kb, true, st, &bn, &splits);
   CUtensorMap tmA, tmW;
   if (!make_tmap_2d(&tmA, A, K, M, lda, BLOCK_M)) return MIXDQ_ERR_CUDA;
-  if (w4 ? !make_tmap_2d_w4(&tmW, W, K, N, bn) : !make_tmap_2d(&tmW, W, K, N, K, bn))
+  if (w4 ? !make_tmap_2d_w4(&tmW, W, K, N, bn / pcs) : !make_tmap_2d(&tmW, W, K, N, K, bn / pcs))
     return MIXDQ_ERR_CUDA;
   TcParams p{};
   p.dbg = g_dbg;
@@ -329,6 +347,11 @@ static int gemm_common(const int8_t* A, int64_t lda, const int8_t* W, const floa
   p.bias = reinterpret_cast<const __half*>(bias);
   p.D = reinterpret_cast<__half*>(D); p.ldd = ldd; p.acc_out = acc_out;
   p.residual = reinterpret_cast<const __half*>(residual); p.ldr = ldr;
+  if (pbn) {
+    p.tiles_m = m_tiles; p.tiles_n = (N + pbn - 1) / pbn;
+    g_last_path = w4 ? "tcgen05-w4-persist" : "tcgen05-persist";
+    return persist_launch(KIND_GEMM, pbn, w4, pcs, tmA, tmW, p, st);
+  }
   dim3 grid(m_tiles, (N + bn - 1) / bn, splits);
   if (w4) {
     g_last_path = splits > 1 ? "tcgen05-w4-splitk" : "tcgen05-w4";
@@ -393,9 +416,13 @@ static int geglu_common(const int8_t* A, int64_t lda, const int8_t* W_il,
       if (t < best) { best = t; bn = c; }
     }
   }
+  const int pbn = persist_bn(m_tiles, N2, num_kb, KIND_GEGLU);
+  const int pcs = pbn ? persist_cluster_size(m_tiles) : 1;
+  if (pbn) bn = pbn;
   CUtensorMap tmA, tmW;
   if (!make_tmap_2d(&tmA, A, K, M, lda, BLOCK_M)) return MIXDQ_ERR_CUDA;
-  if (w4 ? !make_tmap_2d_w4(&tmW, W_il, K, N2, bn) : !make_tmap_2d(&tmW, W_il, K, N2, K, bn))
+  if (w4 ? !make_tmap_2d_w4(&tmW, W_il, K, N2, bn / pcs)
+         : !make_tmap_2d(&tmW, W_il, K, N2, K, bn / pcs))
     return MIXDQ_ERR_CUDA;
   TcParams p{};
   p.dbg = g_dbg;
@@ -407,6 +434,18 @@ static int geglu_common(const int8_t* A, int64_t lda, const int8_t* W_il,
   p.bias = reinterpret_cast<const __half*>(bias_il);
   p.D = reinterpret_cast<__half*>(Y); p.ldd = ldy;
   p.mm_partial = static_cast<DynWs*>(ws)->partial;   // address arithmetic only (device pointer)
+  if (pbn) {
+    // one min / max partial per persistent CTA
+    p.tiles_m = m_tiles; p.tiles_n = (N2 + pbn - 1) / pbn;
+    const long groups = static_cast<long>((m_tiles + pcs - 1) / pcs) * p.tiles_n;
+    int sms = 148;
+    { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    long clusters = sms / pcs;
+    if (groups < clusters) clusters = groups;
+    partial_count_slot(ws) = static_cast<int>(clusters * pcs);
+    g_last_path = w4 ? "tcgen05-w4-geglu-persist" : "tcgen05-geglu-persist";
+    return persist_launch(KIND_GEGLU, pbn, w4, pcs, tmA, tmW, p, static_cast<cudaStream_t>(stream));
+  }
   dim3 grid(m_tiles, (N2 + bn - 1) / bn, 1);
   if (static_cast<int64_t>(grid.x) * grid.y > kMaxPartials) return MIXDQ_ERR_UNSUPPORTED;
   partial_count_slot(ws) = static_cast<int>(grid.x * grid.y);
@@ -539,8 +578,10 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
             tilesN = (N + boxN - 1) / boxN;
   const int m_tiles = tilesQ * tilesP * tilesN;
   const int kb_per_tap = (C + BLOCK_K - 1) / BLOCK_K;
-  int bn, splits;
-  pick_tile(m_tiles, K, R * S * kb_per_tap, true, st, &bn, &splits);
+  const int pbn = persist_bn(m_tiles, K, R * S * kb_per_tap, KIND_CONV);
+  const int pcs = pbn ? persist_cluster_size(m_tiles) : 1;
+  int bn = pbn, splits = 1;
+  if (!pbn) pick_tile(m_tiles, K, R * S * kb_per_tap, true, st, &bn, &splits);
 
   CUtensorMap tmA, tmW;
   {
@@ -559,7 +600,7 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
     uint64_t dims[3] = {cb, static_cast<uint64_t>(R) * S, static_cast<uint64_t>(K)};
     uint64_t strides[2] = {cb, cb * R * S};
     uint32_t box[3] = {static_cast<uint32_t>(w4 ? BLOCK_K / 2 : BLOCK_K), 1,
-                       static_cast<uint32_t>(bn)};
+                       static_cast<uint32_t>(bn / pcs)};
     if (!make_tmap(&tmW, w, 3, dims, strides, box, nullptr, !w4)) return MIXDQ_ERR_CUDA;
   }
   TcParams p{};
@@ -581,6 +622,11 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
   p.chan_add = reinterpret_cast<const __half*>(chan_add); p.ldca = ldca;
   p.rows_per_img = static_cast<int64_t>(P) * Q;
   p.residual = reinterpret_cast<const __half*>(residual); p.ldr = K;
+  if (pbn) {
+    p.tiles_m = m_tiles; p.tiles_n = (K + pbn - 1) / pbn;
+    g_last_path = w4 ? "tcgen05-w4-persist" : "tcgen05-persist";
+    return persist_launch(KIND_CONV, pbn, w4, pcs, tmA, tmW, p, st);
+  }
   dim3 grid(m_tiles, (K + bn - 1) / bn, splits);
   if (w4) {
     g_last_path = splits > 1 ? "tcgen05-w4-splitk" : "tcgen05-w4";

@@ -1,0 +1,126 @@
+// persist.cu — instantiations and launcher of the persistent tcgen05 contraction kernels.
+#include <stdlib.h>
+
+#include "../../include/mixdq_b200.h"
+#include "persist.h"
+#include "tc_persist.cuh"
+
+namespace mixdq {
+
+static int g_persist_mode = -1;     // env MIXDQ_PERSIST: 0 = never, 1 = heuristic (default)
+static int g_persist_cs = -1;       // env MIXDQ_PERSIST_CS: 1 / 2 (default 2: W multicast pairs)
+static void read_env() {
+  if (g_persist_mode < 0) {
+    const char* e = getenv("MIXDQ_PERSIST");
+    g_persist_mode = e ? atoi(e) : 1;
+    const char* c = getenv("MIXDQ_PERSIST_CS");
+    g_persist_cs = c ? atoi(c) : 2;
+    if (g_persist_cs != 1) g_persist_cs = 2;
+  }
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+// Cost model (cycles per tile): 4 tcgen05.mma per k-block at 64 / 80 / 126 cycles for
+// N = 128 / 160 / 256 (tools/mma_bench: the tensor pipe's own rate) + ~600 cycles per tile that the
+// three pipelines do not hide; tiles are dealt round-robin to one CTA per SM.
+int persist_pick_bn(int m_tiles, int N, int num_kb, int kind) {
+  read_env();
+  if (g_persist_mode == 0) return 0;
+  const int sms = num_sms();
+  const int cands[3] = {256, 160, 128};
+  const double cyc[3] = {126.0, 80.0, 64.0};
+  double best = 1e30;
+  int best_bn = 0;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (kind == KIND_GEGLU && bn != 256) continue;          // GEGLU projections: N2 % 256 == 0
+    if (kind == KIND_GEGLU && (N % 256)) continue;
+    const long tiles = static_cast<long>(m_tiles) * ((N + bn - 1) / bn);
+    if (tiles < sms) continue;                               // less than one tile per SM
+    const long rounds = (tiles + sms - 1) / sms;
+    if (rounds < 2 && g_persist_mode == 1) continue;         // a single wave gains nothing here
+    const double t = rounds * (num_kb * 4 * cyc[i] + 600.0);
+    if (t < best) { best = t; best_bn = bn; }
+  }
+  return best_bn;
+}
+
+int persist_cluster_size(int m_tiles) {
+  read_env();
+  return (g_persist_cs == 2 && m_tiles >= 2) ? 2 : 1;
+}
+
+template <int BN, int STAGES, int KIND, bool W4, int CS>
+static int launch(const CUtensorMap& a, const CUtensorMap& w, const TcParams& p, cudaStream_t st) {
+  using L = TpSmem<BN, STAGES, KIND, W4>;
+  auto kern = tc_i8_persist_kernel<BN, STAGES, KIND, W4, CS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) !=
+        cudaSuccess)
+      return MIXDQ_ERR_CUDA;
+    attr_set = true;
+  }
+  const int m_groups = (p.tiles_m + CS - 1) / CS;
+  const long groups = static_cast<long>(m_groups) * p.tiles_n;
+  long clusters = num_sms() / CS;
+  if (groups < clusters) clusters = groups;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * CS));
+  cfg.blockDim = dim3(W4 ? TP_THREADS_W4 : TP_THREADS);
+  cfg.dynamicSmemBytes = L::DYN_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, kern, a, w, p) == cudaSuccess ? MIXDQ_OK : MIXDQ_ERR_CUDA;
+}
+
+template <int KIND, bool W4, int CS>
+static int by_bn(int bn, const CUtensorMap& a, const CUtensorMap& w, const TcParams& p,
+                 cudaStream_t st) {
+  constexpr int ST256 = (KIND == KIND_CONV) ? 3 : 4;   // the conv border table takes 17 KB
+  switch (bn) {
+    case 256: return launch<256, ST256, KIND, W4, CS>(a, w, p, st);
+    case 160: if constexpr (KIND != KIND_GEGLU) return launch<160, 5, KIND, W4, CS>(a, w, p, st);
+              return MIXDQ_ERR_UNSUPPORTED;
+    case 128: if constexpr (KIND != KIND_GEGLU) return launch<128, 6, KIND, W4, CS>(a, w, p, st);
+              return MIXDQ_ERR_UNSUPPORTED;
+    default: return MIXDQ_ERR_UNSUPPORTED;
+  }
+}
+
+template <int KIND>
+static int by_flags(int bn, bool w4, int cs, const CUtensorMap& a, const CUtensorMap& w,
+                    const TcParams& p, cudaStream_t st) {
+  if (w4) return cs == 2 ? by_bn<KIND, true, 2>(bn, a, w, p, st) : by_bn<KIND, true, 1>(bn, a, w, p, st);
+  return cs == 2 ? by_bn<KIND, false, 2>(bn, a, w, p, st) : by_bn<KIND, false, 1>(bn, a, w, p, st);
+}
+
+int persist_launch(int kind, int bn, bool w4, int cs, const CUtensorMap& tmA,
+                   const CUtensorMap& tmW, TcParams p, cudaStream_t st) {
+  switch (kind) {
+    case KIND_GEMM: return by_flags<KIND_GEMM>(bn, w4, cs, tmA, tmW, p, st);
+    case KIND_CONV: return by_flags<KIND_CONV>(bn, w4, cs, tmA, tmW, p, st);
+    case KIND_GEGLU: return by_flags<KIND_GEGLU>(bn, w4, cs, tmA, tmW, p, st);
+    default: return MIXDQ_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace mixdq

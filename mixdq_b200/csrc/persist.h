@@ -1,0 +1,19 @@
+// persist.h — launcher of the persistent tcgen05 kernels (tc_persist.cuh), see persist.cu.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "tc_kernel.cuh"
+
+namespace mixdq {
+
+// Tile width the persistent kernel would use for an (m_tiles x N, num_kb k-blocks) problem, or 0
+// when the problem is too small to keep every SM busy for more than one tile (then the
+// one-tile-per-CTA kernel with its split-K / narrow-tile heuristic is the better fit).
+int persist_pick_bn(int m_tiles, int N, int num_kb, int kind);
+// cluster size along M (1 or 2) for the chosen configuration
+int persist_cluster_size(int m_tiles);
+// tmW must have been encoded with box rows = bn / cs. Returns 0 or a negative MIXDQ_ERR_* code.
+int persist_launch(int kind, int bn, bool w4, int cs, const CUtensorMap& tmA,
+                   const CUtensorMap& tmW, TcParams p, cudaStream_t st);
+
+}  // namespace mixdq

@@ -1,0 +1,565 @@
+// tc_persist.cuh — persistent form of the tcgen05 INT8 contraction for TENSOR-BOUND problems
+// (batch >= 8 UNet layers, the per-layer sweep): many output tiles per SM.
+//
+// tc_i8_kernel (tc_kernel.cuh) runs one 128 x BN tile per CTA: its prologue (barrier / TMEM setup,
+// first operands ~1.4 us) and its epilogue (TMEM -> dequant -> fp16 -> global, 1-2 us) are not
+// overlapped with any tensor work, which caps it at 25-55 % of the INT8 peak on multi-wave
+// problems (profiles/r01_tops_sweep.txt). Here each CTA is PERSISTENT and walks a strided list of
+// tiles with three decoupled pipelines:
+//
+//   warp 0      TMA producer   : A / W k-blocks of tile after tile through ONE continuous
+//                                STAGES-deep ring (the ring never drains between tiles)
+//   warp 1      MMA issuer     : tcgen05.mma kind::i8 128 x BN x 32 into one of TWO TMEM
+//                                accumulator slots (2 x 256 columns = the whole TMEM)
+//   warps 2..9  epilogue       : drain slot s (tcgen05.ld -> dequant -> fp16 -> per-warp staging
+//                                -> coalesced 16 B stores, fused tails) WHILE the issuer fills
+//                                slot s^1 with the next tile
+//   [W4] warps 10..13 converter: expand the packed 4-bit weight k-blocks in place (see
+//                                tc_kernel.cuh); the epilogue warps are busy here, so the nibble
+//                                expansion has warps of its own
+//
+// Cluster of 2 CTAs along M (CS = 2): the pair computes two vertically adjacent tiles that share
+// the W tile; each CTA fetches HALF of the W rows and TMA-multicasts them into both CTAs' rings,
+// so a 128 x 256 tile costs 16 KB (A) + 16 KB (W half) of L2 traffic per k-block instead of 48 KB
+// (256 instead of 170 op/B: the L2 -> SM fabric, ~6300 B/clk chip-wide, is what bounds a
+// 1-CTA 128 x 256 tiling at ~60 % of the INT8 peak). A ring slot is recycled only when BOTH CTAs
+// consumed it: tcgen05.commit arrives on the slot's empty barrier of both CTAs (multicast).
+//
+// Same operand layouts, tensor maps, KIND semantics (GEMM / CONV / GEGLU), epilogue arithmetic and
+// TcParams as tc_i8_kernel; p.tiles_m / p.tiles_n describe the tile grid.
+#pragma once
+#include "tc_kernel.cuh"
+
+namespace mixdq {
+
+constexpr int TP_EPI_WARPS = 8;
+constexpr int TP_THREADS = 32 * (2 + TP_EPI_WARPS);        // 320
+constexpr int TP_CONV_WARPS = 4;
+constexpr int TP_THREADS_W4 = TP_THREADS + 32 * TP_CONV_WARPS;   // 448
+constexpr int TP_SLOT_COLS = 256;                           // TMEM columns per accumulator slot
+
+template <int BN, int STAGES, int KIND, bool W4>
+struct TpSmem {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K;
+  static constexpr int W_BYTES = BN * BLOCK_K;
+  static constexpr int CH = 32;                              // accumulator columns per chunk
+  static constexpr int OUT_PITCH = CH * 2 + 16;              // fp16 staging row (+16 B pad)
+  static constexpr int OUT_WARP = 32 * OUT_PITCH;            // one warp: 32 rows
+  static constexpr int TAB_PITCH = BN + 4;
+  static constexpr int TAB_FLOATS = (KIND == KIND_CONV) ? 16 * TAB_PITCH : 0;
+  static constexpr int PARAM_FLOATS = 3 * BN + TAB_FLOATS;
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_W = OFF_A + STAGES * A_BYTES;
+  static constexpr int OFF_OUT = OFF_W + STAGES * W_BYTES;
+  static constexpr int OFF_PARAM = OFF_OUT + TP_EPI_WARPS * OUT_WARP;
+  static constexpr int OFF_BAR = OFF_PARAM + ((PARAM_FLOATS * 4 + 15) / 16) * 16;
+  static constexpr int NUM_BARS = (W4 ? 3 : 2) * STAGES + 4;
+  static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+  static constexpr int OFF_MM = OFF_TMEM + 16;               // GEGLU: per-warp min / max
+  static constexpr int TOTAL = OFF_MM + TP_EPI_WARPS * 8;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+  static_assert(DYN_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
+};
+
+// multicast TMA loads: the tile lands at the same shared-memory offset of every CTA in cta_mask
+// and completes transaction bytes on the mbarrier at the same offset of each of them
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar,
+                                               int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* m, uint64_t* bar,
+                                               int c0, int c1, int c2, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "h"(cta_mask)
+      : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
+      " [%0], %1;" ::"r"(smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int BN, int STAGES, int KIND, bool W4, int CS>
+__global__ void __launch_bounds__(W4 ? TP_THREADS_W4 : TP_THREADS, 1)
+tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                     const TcParams p) {
+  using L = TpSmem<BN, STAGES, KIND, W4>;
+  static_assert(KIND == KIND_GEMM || KIND == KIND_CONV || KIND == KIND_GEGLU, "unsupported kind");
+  static_assert(BN % 32 == 0 && BN >= 64 && BN <= TP_SLOT_COLS, "tile width (every epilogue warp owns >= 1 chunk)");
+  static_assert(CS == 1 || CS == 2, "cluster size along M");
+  static_assert(CS == 1 || BN % 16 == 0, "W halves");
+  constexpr uint32_t IDESC = umma_idesc_i8(BLOCK_M, BN);
+  constexpr int CH = L::CH;
+  constexpr int NCH = BN / CH;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem + L::OFF_A;
+  uint8_t* sW = smem + L::OFF_W;
+  float* s_scale = reinterpret_cast<float*>(smem + L::OFF_PARAM);
+  float* s_bias0 = s_scale + BN;
+  float* s_bias = s_bias0 + BN;
+  float* s_table = s_bias + BN;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint64_t* raw_full = tmem_empty + 2;           // [STAGES], W4 only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+
+  // ---- tile schedule: groups of CS vertically adjacent tiles, m fastest, strided over clusters
+  const int crank = (CS > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cid = blockIdx.x / CS;
+  const int nclusters = gridDim.x / CS;
+  const int m_groups = (p.tiles_m + CS - 1) / CS;
+  const int total_groups = m_groups * p.tiles_n;
+  const int num_kb = p.num_kb;
+  constexpr uint16_t MC_MASK = (CS > 1) ? 0x3 : 0x1;
+
+  struct Tile { int m0, tn0, tp0, tq0, n_tile0; };
+  auto tile_of = [&](int g) {
+    Tile t;
+    const int nt = g / m_groups;
+    const int mt = (g - nt * m_groups) * CS + crank;     // may be >= tiles_m (odd tile count): an
+    t.n_tile0 = nt * BN;                                 // all-out-of-bounds tile, nothing stored
+    t.m0 = mt * BLOCK_M; t.tn0 = t.tp0 = t.tq0 = 0;
+    if (KIND == KIND_CONV) {
+      int x = mt;
+      const int tq = x % p.tilesQ; x /= p.tilesQ;
+      const int tp = x % p.tilesP; x /= p.tilesP;
+      t.tq0 = tq * p.boxW; t.tp0 = tp * p.boxH; t.tn0 = x * p.boxN;
+    }
+    return t;
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], W4 ? 1 + TP_CONV_WARPS : 1);
+      mbar_init(&empty_bar[i], CS);                // every CTA of the pair must have consumed it
+      if (W4) mbar_init(&raw_full[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], TP_EPI_WARPS); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * TP_SLOT_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CS > 1) cluster_sync_all();        // the peer's barriers exist before anything multicasts
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    const uint32_t a_bytes = (KIND == KIND_CONV) ? p.a_tx_bytes : static_cast<uint32_t>(L::A_BYTES);
+    constexpr int WK = W4 ? BLOCK_K / 2 : BLOCK_K;       // bytes of K per k-block in memory
+    constexpr int WROWS = BN / CS;                       // W rows this CTA fetches (and multicasts)
+    constexpr uint32_t W_TX = W4 ? L::W_BYTES / 2 : L::W_BYTES;   // bytes landing per CTA and k-block
+    auto load_w = [&](const Tile& t, int kb, int stage) {
+      // W4: packed rows (64 B) land in the upper half of the slot, unswizzled
+      uint8_t* w_dst = sW + stage * L::W_BYTES + (W4 ? L::W_BYTES / 2 : 0) + crank * WROWS * WK;
+      uint64_t* bar = W4 ? &raw_full[stage] : &full_bar[stage];
+      const int row0 = t.n_tile0 + crank * WROWS;
+      if (KIND == KIND_CONV) {
+        const int tap = kb / p.kb_per_tap;
+        const int c0 = (kb - tap * p.kb_per_tap) * WK;
+        if (CS > 1) tma_load_3d_mc(w_dst, &tmW, bar, c0, tap, row0, MC_MASK);
+        else tma_load_3d(w_dst, &tmW, bar, c0, tap, row0);
+      } else {
+        if (CS > 1) tma_load_2d_mc(w_dst, &tmW, bar, kb * WK, row0, MC_MASK);
+        else tma_load_2d(w_dst, &tmW, bar, kb * WK, row0);
+      }
+    };
+    auto load_a = [&](const Tile& t, int kb, int stage) {
+      uint8_t* a_dst = sA + stage * L::A_BYTES;
+      if (KIND == KIND_CONV) {
+        const int tap = kb / p.kb_per_tap;
+        const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
+        const int r = tap / p.S, s = tap - r * p.S;
+        tma_load_4d(a_dst, &tmA, &full_bar[stage], c0, t.tq0 * p.stride - p.pad + s,
+                    t.tp0 * p.stride - p.pad + r, t.tn0);
+      } else {
+        tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BLOCK_K, t.m0);
+      }
+    };
+    // The first ring-full of WEIGHT k-blocks does not depend on the preceding kernel: issue it
+    // before the programmatic-dependency wait (activations follow after it).
+    uint32_t it = 0;                                     // k-block iterations issued so far
+    int pre = 0;
+    if (cid < total_groups) {
+      const Tile t0 = tile_of(cid);
+      pre = num_kb < STAGES ? num_kb : STAGES;
+      if (elect_one()) {
+        for (int i = 0; i < pre; ++i) {
+          if (W4) mbar_expect_tx(&raw_full[i], W_TX);
+          else mbar_expect_tx(&full_bar[i], a_bytes + W_TX);
+          load_w(t0, i, i);
+        }
+      }
+      __syncwarp();
+    }
+    pdl_wait();
+    for (int g = cid; g < total_groups; g += nclusters) {
+      const Tile t = tile_of(g);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int stage = it % STAGES;
+        const bool early_w = (g == cid) && (kb < pre);   // W already in flight
+        if (it >= static_cast<uint32_t>(STAGES)) mbar_wait(&empty_bar[stage], ((it / STAGES) & 1u) ^ 1u);
+        if (elect_one()) {
+          if (early_w) {
+            if (W4) mbar_expect_tx(&full_bar[stage], a_bytes);
+          } else {
+            if (W4) { mbar_expect_tx(&raw_full[stage], W_TX); mbar_expect_tx(&full_bar[stage], a_bytes); }
+            else mbar_expect_tx(&full_bar[stage], a_bytes + W_TX);
+            load_w(t, kb, stage);
+          }
+          load_a(t, kb, stage);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
+    const uint64_t w_desc0 = umma_desc_sw128(smem_u32(sW));
+    uint32_t it = 0, tl = 0;
+    for (int g = cid; g < total_groups; g += nclusters, ++tl) {
+      const uint32_t slot = tl & 1u;
+      if (tl >= 2) mbar_wait(&tmem_empty[slot], ((tl >> 1) & 1u) ^ 1u);   // epilogue drained it
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + slot * TP_SLOT_COLS;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int stage = it % STAGES;
+        mbar_wait(&full_bar[stage], (it / STAGES) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(stage * (L::A_BYTES >> 4));
+          const uint64_t w_desc = w_desc0 + static_cast<uint64_t>(stage * (L::W_BYTES >> 4));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_i8(d_tmem, a_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)),
+                    w_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)), IDESC, (kb | k) ? 1u : 0u);
+          if (CS > 1) umma_commit_mc(&empty_bar[stage], MC_MASK);   // frees the slot in BOTH CTAs
+          else umma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit(&tmem_full[slot]);      // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 2 + TP_EPI_WARPS) {
+    // ===================== epilogue warps =====================
+    pdl_wait();                            // dynamic-quantisation scalars come from the predecessor
+    const int ew = warp - 2;
+    const int et = threadIdx.x - 64;       // 0..255
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int ehalf = ew >> 2;             // which half of the tile's columns
+    const bool has_bias = p.bias != nullptr;
+    uint8_t* stage_out = smem + L::OFF_OUT + ew * L::OUT_WARP;   // warp-private staging
+    const int row = quarter * 32 + lane;
+    constexpr int LPR = CH / 8;            // lanes (16-byte chunks) per row of a chunk
+    constexpr int RPI = 32 / LPR;          // rows per copy-out instruction
+    int cur_n = -1;
+    float mn = 0.f, mx = 0.f;              // GEGLU: running min / max of this CTA's outputs
+    uint32_t tl = 0;
+    for (int g = cid; g < total_groups; g += nclusters, ++tl) {
+      const Tile t = tile_of(g);
+      const uint32_t slot = tl & 1u;
+      // ---- per-column operands of this n-tile (reloaded only when the n-tile changes) ----
+      if (t.n_tile0 != cur_n) {
+        named_bar_sync(1, 32 * TP_EPI_WARPS);          // everyone is done with the old values
+        for (int j = et; j < BN; j += 32 * TP_EPI_WARPS) {
+          const int n = t.n_tile0 + j;
+          const bool ok = n < p.N;
+          float sc = 0.f, b0 = 0.f, bs = 0.f;
+          if (ok) {
+            if (p.a_scale != nullptr) {
+              sc = __fmul_rn(__ldg(p.scale + n), __ldcg(p.a_scale));
+              b0 = __fmul_rn(__ldg(p.bias0 + n), __ldcg(p.a_zp));
+            } else {
+              sc = __ldg(p.scale + n);
+              if (!(KIND == KIND_CONV) || !p.has_table) b0 = __ldg(p.bias0 + n);
+            }
+            if (has_bias) bs = __half2float(p.bias[n]);
+          }
+          s_scale[j] = sc; s_bias0[j] = b0; s_bias[j] = bs;
+          if (KIND == KIND_CONV && p.has_table) {
+            float w9[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) w9[q] = ok ? __ldg(p.bias0 + static_cast<int64_t>(n) * 9 + q) : 0.f;
+            const float zp = __ldcg(p.a_zp);
+#pragma unroll
+            for (int rc = 0; rc < 4; ++rc)
+#pragma unroll
+              for (int sc4 = 0; sc4 < 4; ++sc4) {
+                float acc = 0.f;
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                  for (int s = 0; s < 3; ++s) {
+                    const bool rv = !((rc & 1) && r == 0) && !((rc & 2) && r == 2);
+                    const bool sv = !((sc4 & 1) && s == 0) && !((sc4 & 2) && s == 2);
+                    if (rv && sv) acc = __fadd_rn(acc, w9[r * 3 + s]);
+                  }
+                s_table[(rc * 4 + sc4) * L::TAB_PITCH + j] = __fmul_rn(acc, zp);
+              }
+          }
+        }
+        named_bar_sync(1, 32 * TP_EPI_WARPS);
+        cur_n = t.n_tile0;
+      }
+      const RowInfo ri = row_info<KIND>(p, row, t.m0, t.tn0, t.tp0, t.tq0);
+      const int c_lo = ehalf ? (NCH + 1) / 2 : 0;
+      const int c_hi = ehalf ? NCH : (NCH + 1) / 2;
+      const uint32_t t_base = tmem_base + slot * TP_SLOT_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
+
+      auto dequant8 = [&](int cls, int col, const int32_t* a, __half* h) {
+#pragma unroll
+        for (int j0 = 0; j0 < 8; j0 += 4) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + col + j0);
+          const float* b0src = (KIND == KIND_CONV && p.has_table)
+                                   ? (s_table + cls * L::TAB_PITCH + col + j0) : (s_bias0 + col + j0);
+          const float4 b0 = *reinterpret_cast<const float4*>(b0src);
+          float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_bias) bs = *reinterpret_cast<const float4*>(s_bias + col + j0);
+          const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
+          const float b0v[4] = {b0.x, b0.y, b0.z, b0.w};
+          const float bsv[4] = {bs.x, bs.y, bs.z, bs.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float f = dequant_f32(a[j0 + j], b0v[j], scv[j]);
+            if (has_bias) f = __fadd_rn(f, bsv[j]);
+            h[j0 + j] = __float2half_rn(f);
+          }
+        }
+      };
+
+      if (KIND == KIND_GEGLU) {
+        // 32 accumulator columns = 16 value + 16 gate columns of the same 16 outputs
+        RowInfo ro[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          ro[i] = row_info<KIND>(p, quarter * 32 + i * 16 + (lane >> 1), t.m0, t.tn0, t.tp0, t.tq0);
+        mbar_wait(&tmem_full[slot], (tl >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_base + c * 32, reinterpret_cast<uint32_t(&)[32]>(v));
+          tmem_ld_wait();
+          if (c == c_hi - 1) {                         // this warp has read its part of the slot
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+          }
+          if (W4) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = static_cast<uint32_t>(static_cast<int32_t>(v[j]) >> 4);
+          }
+          const bool cols_ok = t.n_tile0 + c * 32 + 32 <= p.N;
+          if (ri.ok && cols_ok) {
+            __align__(16) __half h[32];
+#pragma unroll
+            for (int j8 = 0; j8 < 32; j8 += 8)
+              dequant8(0, c * 32 + j8, reinterpret_cast<const int32_t*>(v) + j8, h + j8);
+            __align__(16) __half y[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              y[j] = geglu_half(h[j], h[16 + j]);
+              const float f = __half2float(y[j]);
+              mn = fminf(mn, f);
+              mx = fmaxf(mx, f);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(stage_out + lane * L::OUT_PITCH);
+            dst[0] = reinterpret_cast<const uint4*>(y)[0];
+            dst[1] = reinterpret_cast<const uint4*>(y)[1];
+          }
+          __syncwarp();
+          if (cols_ok) {
+            const int64_t ocol = ((t.n_tile0 + c * 32) >> 1) + (lane & 1) * 8;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              if (!ro[i].ok) continue;
+              const int r = i * 16 + (lane >> 1);
+              *reinterpret_cast<uint4*>(p.D + ro[i].out_row * p.ldd + ocol) =
+                  *reinterpret_cast<const uint4*>(stage_out + r * L::OUT_PITCH + (lane & 1) * 16);
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        RowInfo ro[LPR];
+        int64_t ca_off[LPR];
+#pragma unroll
+        for (int i = 0; i < LPR; ++i) {
+          ro[i] = row_info<KIND>(p, quarter * 32 + i * RPI + lane / LPR, t.m0, t.tn0, t.tp0, t.tq0);
+          ca_off[i] = (p.chan_add != nullptr && ro[i].ok) ? (ro[i].out_row / p.rows_per_img) * p.ldca : 0;
+        }
+        const bool has_tail = (p.chan_add != nullptr) || (p.residual != nullptr);
+        uint4 t_ca[LPR], t_rs[LPR];
+        auto fetch_tail = [&](int c) {
+          const int ccol = t.n_tile0 + c * CH + (lane % LPR) * 8;
+          if (c < c_hi && ccol + 8 <= p.N) {
+#pragma unroll
+            for (int i = 0; i < LPR; ++i) {
+              if (!ro[i].ok) continue;
+              if (p.chan_add != nullptr)
+                t_ca[i] = __ldcg(reinterpret_cast<const uint4*>(p.chan_add + ca_off[i] + ccol));
+              if (p.residual != nullptr)
+                t_rs[i] = __ldcg(reinterpret_cast<const uint4*>(p.residual + ro[i].out_row * p.ldr + ccol));
+            }
+          }
+        };
+        if (has_tail) fetch_tail(c_lo);
+        mbar_wait(&tmem_full[slot], (tl >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; ++c) {
+          uint32_t v[CH];
+          tmem_ld_32x32(t_base + c * CH, reinterpret_cast<uint32_t(&)[32]>(v));
+          tmem_ld_wait();
+          if (c == c_hi - 1) {                         // this warp has read its part of the slot
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+          }
+          if (W4) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = static_cast<uint32_t>(static_cast<int32_t>(v[j]) >> 4);
+          }
+          if (ri.ok) {
+#pragma unroll
+            for (int j8 = 0; j8 < CH; j8 += 8) {
+              const int col = c * CH + j8;
+              if (p.acc_out != nullptr && t.n_tile0 + col + 8 <= p.N) {
+                int32_t* arow = p.acc_out + ri.out_row * p.N + t.n_tile0 + col;
+                *reinterpret_cast<int4*>(arow) = make_int4(v[j8], v[j8 + 1], v[j8 + 2], v[j8 + 3]);
+                *reinterpret_cast<int4*>(arow + 4) = make_int4(v[j8 + 4], v[j8 + 5], v[j8 + 6], v[j8 + 7]);
+              }
+              __align__(16) __half h[8];
+              dequant8(ri.cls, col, reinterpret_cast<const int32_t*>(v) + j8, h);
+              *reinterpret_cast<uint4*>(stage_out + lane * L::OUT_PITCH + j8 * 2) =
+                  *reinterpret_cast<const uint4*>(h);
+            }
+          }
+          __syncwarp();
+          const int ccol = c * CH + (lane % LPR) * 8;
+          uint4 o[LPR];
+          const bool col_ok = t.n_tile0 + ccol + 8 <= p.N;
+          if (col_ok) {
+#pragma unroll
+            for (int i = 0; i < LPR; ++i) {
+              if (!ro[i].ok) continue;
+              const int r = i * RPI + lane / LPR;
+              o[i] = *reinterpret_cast<const uint4*>(stage_out + r * L::OUT_PITCH + (lane % LPR) * 16);
+              if (p.chan_add != nullptr) o[i] = add_half8(o[i], t_ca[i]);
+              if (p.residual != nullptr) o[i] = add_half8(o[i], t_rs[i]);
+            }
+          }
+          if (has_tail) fetch_tail(c + 1);
+          if (col_ok) {
+#pragma unroll
+            for (int i = 0; i < LPR; ++i) {
+              if (!ro[i].ok) continue;
+              *reinterpret_cast<uint4*>(p.D + ro[i].out_row * p.ldd + t.n_tile0 + ccol) = o[i];
+            }
+          }
+          __syncwarp();                                // staging is reused by the next chunk
+        }
+      }
+    }
+    tc_fence_before();
+    if (KIND == KIND_GEGLU) {
+      // one min / max partial per CTA (consumed by quant_rows_premm_kernel, quant2.cu)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      float* s_mm = reinterpret_cast<float*>(smem + L::OFF_MM);
+      if (lane == 0) { s_mm[ew * 2] = mn; s_mm[ew * 2 + 1] = mx; }
+      named_bar_sync(1, 32 * TP_EPI_WARPS);
+      if (threadIdx.x == 64) {
+#pragma unroll
+        for (int w = 0; w < TP_EPI_WARPS; ++w) { mn = fminf(mn, s_mm[2 * w]); mx = fmaxf(mx, s_mm[2 * w + 1]); }
+        p.mm_partial[blockIdx.x] = make_float2(mn, mx);
+      }
+    }
+  } else {
+    // ===================== W4 converter warps (10..13) =====================
+    if constexpr (W4) {
+      const int ct = threadIdx.x - 32 * (2 + TP_EPI_WARPS);       // 0..127
+      constexpr int NT = 32 * TP_CONV_WARPS;
+      constexpr int CPS = BN * 4;                                  // 16-byte packed chunks per k-block
+      constexpr int PT = (CPS + NT - 1) / NT;
+      uint32_t it = 0;
+      for (int g = cid; g < total_groups; g += nclusters) {
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int stage = it % STAGES;
+          mbar_wait(&raw_full[stage], (it / STAGES) & 1u);
+          uint8_t* wst = sW + stage * L::W_BYTES;
+          uint4 pk[PT];
+#pragma unroll
+          for (int j = 0; j < PT; ++j) {
+            const int c = ct + j * NT;
+            if (c < CPS) pk[j] = *reinterpret_cast<const uint4*>(wst + L::W_BYTES / 2 + c * 16);
+          }
+          named_bar_sync(2, NT);               // every packed chunk is in registers: overwrite
+#pragma unroll
+          for (int j = 0; j < PT; ++j) {
+            const int c = ct + j * NT;
+            if (c < CPS) {
+              const int row = c >> 2, cpos = c & 3;
+              const uint32_t pw[4] = {pk[j].x, pk[j].y, pk[j].z, pk[j].w};
+              uint32_t o[8];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t e = pw[q] & 0xF0F0F0F0u;
+                const uint32_t d = (pw[q] << 4) & 0xF0F0F0F0u;
+                o[2 * q] = __byte_perm(e, d, 0x5140);
+                o[2 * q + 1] = __byte_perm(e, d, 0x7362);
+              }
+              uint8_t* rowp = wst + row * 128;
+              const int sw = row & 7;
+              *reinterpret_cast<uint4*>(rowp + (((2 * cpos) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(rowp + (((2 * cpos + 1) ^ sw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[stage]);
+        }
+      }
+    }
+  }
+
+  __syncthreads();
+  if (CS > 1) cluster_sync_all();      // no CTA exits while its peer may still multicast into it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * TP_SLOT_COLS);
+  }
+}
+
+}  // namespace mixdq
