@@ -56,6 +56,11 @@ void        mixdq_force_simt(int on);
 /* Force the output-tile width of the tcgen05 kernels (16/32/64/128/256; 0 = heuristic). Tuning and
    test aid (also settable through the MIXDQ_FORCE_BN environment variable). */
 void        mixdq_debug_force_bn(int bn);
+/* Persistent form of the tcgen05 kernels (tensor-bound, multi-wave problems): mode 0 = never,
+   1 = heuristic (default; env MIXDQ_PERSIST), 2 = whenever the shape is supported (tests);
+   cluster = 1 / 2 CTAs sharing a weight tile through TMA multicast (default 2; env
+   MIXDQ_PERSIST_CS); other values leave the setting unchanged. Results are identical. */
+void        mixdq_debug_set_persist(int mode, int cluster);
 /* Force the split-K factor (cluster size) of the tcgen05 kernels (1/2/4/8; 0 = heuristic). */
 void        mixdq_debug_force_splits(int splits);
 /* Give the tcgen05 kernels a device buffer of 8 uint64 PER CTA of the largest grid launched:

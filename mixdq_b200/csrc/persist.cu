@@ -7,7 +7,8 @@
 
 namespace mixdq {
 
-static int g_persist_mode = -1;     // env MIXDQ_PERSIST: 0 = never, 1 = heuristic (default)
+static int g_persist_mode = -1;     // env MIXDQ_PERSIST: 0 = never, 1 = heuristic (default),
+                                    // 2 = whenever the shape is supported (tests)
 static int g_persist_cs = -1;       // env MIXDQ_PERSIST_CS: 1 / 2 (default 2: W multicast pairs)
 static void read_env() {
   if (g_persist_mode < 0) {
@@ -46,13 +47,18 @@ int persist_pick_bn(int m_tiles, int N, int num_kb, int kind) {
     if (kind == KIND_GEGLU && bn != 256) continue;          // GEGLU projections: N2 % 256 == 0
     if (kind == KIND_GEGLU && (N % 256)) continue;
     const long tiles = static_cast<long>(m_tiles) * ((N + bn - 1) / bn);
-    if (tiles < sms) continue;                               // less than one tile per SM
     const long rounds = (tiles + sms - 1) / sms;
-    if (rounds < 2 && g_persist_mode == 1) continue;         // a single wave gains nothing here
+    if (g_persist_mode == 1 && (tiles < sms || rounds < 2)) continue;   // a single wave gains nothing
     const double t = rounds * (num_kb * 4 * cyc[i] + 600.0);
     if (t < best) { best = t; best_bn = bn; }
   }
   return best_bn;
+}
+
+void persist_set_mode(int mode, int cs) {
+  read_env();
+  if (mode >= 0) g_persist_mode = mode;
+  if (cs == 1 || cs == 2) g_persist_cs = cs;
 }
 
 int persist_cluster_size(int m_tiles) {

@@ -10,6 +10,8 @@ namespace mixdq {
 // when the problem is too small to keep every SM busy for more than one tile (then the
 // one-tile-per-CTA kernel with its split-K / narrow-tile heuristic is the better fit).
 int persist_pick_bn(int m_tiles, int N, int num_kb, int kind);
+// test / tuning hook: mode 0 = never, 1 = heuristic, 2 = whenever supported; cs = 1 / 2 (else kept)
+void persist_set_mode(int mode, int cs);
 // cluster size along M (1 or 2) for the chosen configuration
 int persist_cluster_size(int m_tiles);
 // tmW must have been encoded with box rows = bn / cs. Returns 0 or a negative MIXDQ_ERR_* code.
