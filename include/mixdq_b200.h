@@ -61,6 +61,9 @@ void        mixdq_debug_force_bn(int bn);
    cluster = 1 / 2 CTAs sharing a weight tile through TMA multicast (default 2; env
    MIXDQ_PERSIST_CS); other values leave the setting unchanged. Results are identical. */
 void        mixdq_debug_set_persist(int mode, int cluster);
+/* Tuning hook: restrict the persistent kernel's tile-width choice to `bn` (128 / 160 / 256; 0 =
+   cost model). */
+void        mixdq_debug_set_persist_bn(int bn);
 /* Force the split-K factor (cluster size) of the tcgen05 kernels (1/2/4/8; 0 = heuristic). */
 void        mixdq_debug_force_splits(int splits);
 /* Give the tcgen05 kernels a device buffer of 8 uint64 PER CTA of the largest grid launched:
@@ -76,12 +79,9 @@ void        mixdq_debug_set_mode(int mode);
    kernels. Results are identical either way; A/B timing and test aid (env MIXDQ_NO_CLUSTER=1). */
 void        mixdq_debug_set_cluster(int on);
 /* Form of the dynamic quantisers: 1 (default) = a min/max pass + a quantise pass chained by
-   programmatic dependent launch; 2 = lean one-kernel form (values in registers, tagged-partial
-   grid barrier) where the tensor fits a co-resident grid (faster in isolation, slower inside the
-   whole-UNet graph: see profiles/README.md); 3 = compact one-cluster kernels (DSMEM + hardware
-   cluster barrier) where the tensor fits 16 CTAs' registers (also slower inside the graph);
-   0 = first-generation single kernels with the counter barrier. Identical results in every mode;
-   A/B timing and test aid (env MIXDQ_QUANT_MODE). */
+   programmatic dependent launch; 0 = first-generation single kernels with the counter barrier
+   (fallback for callers without a scratch buffer, A/B reference of the parity tests). Identical
+   results in both modes (env MIXDQ_QUANT_MODE). */
 void        mixdq_debug_set_two_pass(int mode);
 /* Point the dynamic-quantisation workspace `ws` at a device buffer of
    launches x 1024 CTAs x 8 uint64 (or NULL = off): every quantiser launch that uses `ws` then
@@ -284,20 +284,6 @@ int mixdq_gemm_w8a8_geglu_f16_dyn(const int8_t* A, int64_t lda, const int8_t* W_
 int mixdq_quant_i8_premm(const mixdq_half_t* x, int64_t numel, int8_t* q, float* scale_out,
                          float* zp_out, void* ws, mixdq_stream_t stream);
 
-/* Cross-attention of the fused transformer block (stock PyTorch SDPA in the reference: diffusers
-   Attention between attn2.to_q/to_k/to_v and attn2.to_out, run on fp16): head dim 64, <= 96
-   context tokens, no mask. q / k / v are fp16 with the heads side by side in a row (row pitch ld*,
-   batch stride bs*, in elements; k / v may be column slices of a wider matrix); out = dense fp16
-   [B][T][H*64] = softmax(scale * q k^T) v per head, fp32 scores / softmax / accumulation, one
-   rounding. The min(0, min) / max(0, max) of `out` are left in `ws` as per-CTA partials for exactly
-   one mixdq_quant_i8_premm call on the same stream (as mixdq_gemm_w8a8_geglu_f16_dyn does).
-   MIXDQ_ERR_UNSUPPORTED for Lk > 96 or more than 4096 (query block, head, batch) CTAs. */
-int mixdq_cross_attn_d64_f16(const mixdq_half_t* q, int64_t ldq, int64_t bsq,
-                             const mixdq_half_t* k, int64_t ldk, int64_t bsk,
-                             const mixdq_half_t* v, int64_t ldv, int64_t bsv,
-                             mixdq_half_t* out, int B, int T, int Lk, int H, float scale,
-                             void* ws, mixdq_stream_t stream);
-
 /* wsum_krs fp32 [K][R][S] iff pad > 0; wsum_k fp32 [K] (sum over taps and channels) iff pad == 0 */
 int mixdq_conv_w8a8_f16_dyn(const int8_t* x_nhwc, int64_t x_cpitch, const int8_t* w_krsc,
                             const float* w_scale, const float* wsum_krs, const float* wsum_k,
@@ -339,6 +325,19 @@ int mixdq_conv1x1_split_w8a8_f16_dyn(const int8_t* xa, int64_t lda, const int8_t
  * nn/Linear.py:180, strided attention outputs). cols % 8 == 0, ldx % 8 == 0. */
 int mixdq_quant_i8_dynamic_rows(const mixdq_half_t* x, int64_t ldx, int M, int cols, int8_t* q,
                                 float* scale_out, float* zp_out, void* ws, mixdq_stream_t stream);
+/* A10 with a code range (N3: the 4-bit activation layers of kernels/cfgs/act/act_7.xx.yaml, which
+   the reference gates to fp16, nn/Linear.py:28-36 / nn/Conv2d.py:38-46). n_bits = 8: identical to
+   mixdq_quant_i8_dynamic_rows. n_bits = 4: delta = (max - min) / 15, z = round(-min / delta),
+   q = clamp(round(x / delta) + z, 0, 15) stored as it is (no -128 shift), *zp_out = z: the codes
+   feed the same int8 kernels. cols % 8 == 0, ldx % 8 == 0. */
+int mixdq_quant_i8_dynamic_bits(const mixdq_half_t* x, int64_t ldx, int64_t M, int64_t cols,
+                                int n_bits, float* scale_out, float* zp_out, int8_t* q, void* ws,
+                                mixdq_stream_t stream);
+/* A1 with an explicit code range: q = clamp(lrintf(x * scale_inv + zp), lo, hi), flat dense.
+   [lo, hi] = [0, 15] with the unshifted zero point for static 4-bit activations. */
+int mixdq_quant_i8_static_range(const mixdq_half_t* x, int64_t numel, const float* scale_inv,
+                                const float* zp, int lo, int hi, int8_t* q,
+                                mixdq_stream_t stream);
 int mixdq_ln_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int M, int C,
                               const mixdq_half_t* gamma, const mixdq_half_t* beta, float eps,
                               int8_t* q, mixdq_half_t* y_out, float* scale_out, float* zp_out,

@@ -18,7 +18,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libmixdq_b200.so"
 # every symbol include/mixdq_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "mixdq_abi_version", "mixdq_set_workspace", "mixdq_stream_capture_id", "mixdq_debug_set_pdl", "mixdq_strerror", "mixdq_last_path", "mixdq_force_simt",
-    "mixdq_debug_force_bn", "mixdq_debug_force_splits", "mixdq_debug_set_persist", "mixdq_debug_set_timing_buffer",
+    "mixdq_debug_force_bn", "mixdq_debug_force_splits", "mixdq_debug_set_persist", "mixdq_debug_set_persist_bn", "mixdq_debug_set_timing_buffer",
     "mixdq_debug_set_mode", "mixdq_debug_set_cluster", "mixdq_debug_set_two_pass", "mixdq_debug_set_quant_timing_buffer",
     "mixdq_quant_i8_static", "mixdq_quant_i8_static_strided", "mixdq_quant_i8_nchw2nhwc",
     "mixdq_quant_dynamic_ws_bytes", "mixdq_quant_i8_dynamic",
@@ -26,9 +26,9 @@ ABI_SYMBOLS = [
     "mixdq_conv_w8a8_f16", "mixdq_conv1x1_split_w8a8_f16",
     "mixdq_gemm_w8a8_f16_dyn_res", "mixdq_conv_w8a8_f16_dyn", "mixdq_conv1x1_split_w8a8_f16_dyn",
     "mixdq_quant_i8_dynamic_rows", "mixdq_ln_quant_i8_dynamic", "mixdq_geglu_quant_i8_dynamic", "mixdq_gn_quant_i8_dynamic",
-    "mixdq_gemm_w8a8_geglu_f16_dyn", "mixdq_quant_i8_premm", "mixdq_cross_attn_d64_f16",
+    "mixdq_gemm_w8a8_geglu_f16_dyn", "mixdq_quant_i8_premm",
     "mixdq_gemm_w4a8_f16_dyn_res", "mixdq_gemm_w4a8_geglu_f16_dyn", "mixdq_conv_w4a8_f16",
-    "mixdq_conv_w4a8_f16_dyn",
+    "mixdq_conv_w4a8_f16_dyn", "mixdq_quant_i8_dynamic_bits", "mixdq_quant_i8_static_range",
 ]
 
 
@@ -56,6 +56,12 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mixdq_debug_force_bn.argtypes = [c_int]
     lib.mixdq_debug_set_persist.restype = None
     lib.mixdq_debug_set_persist.argtypes = [c_int, c_int]
+    lib.mixdq_debug_set_persist_bn.restype = None
+    lib.mixdq_debug_set_persist_bn.argtypes = [c_int]
+    lib.mixdq_quant_i8_dynamic_bits.restype = c_int
+    lib.mixdq_quant_i8_dynamic_bits.argtypes = [P, c_int64, c_int64, c_int64, c_int, P, P, P, P, P]
+    lib.mixdq_quant_i8_static_range.restype = c_int
+    lib.mixdq_quant_i8_static_range.argtypes = [P, c_int64, P, P, c_int, c_int, P, P]
     lib.mixdq_debug_force_splits.restype = None
     lib.mixdq_debug_force_splits.argtypes = [c_int]
     lib.mixdq_debug_set_timing_buffer.restype = None
@@ -123,9 +129,6 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mixdq_gemm_w8a8_geglu_f16_dyn.restype = c_int
     lib.mixdq_gemm_w8a8_geglu_f16_dyn.argtypes = [P, c_int64, P, P, P, P, P, P, P, c_int64,
                                                   c_int, c_int, c_int, P, P]
-    lib.mixdq_cross_attn_d64_f16.restype = c_int
-    lib.mixdq_cross_attn_d64_f16.argtypes = [P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64,
-                                             c_int64, P, c_int, c_int, c_int, c_int, c_float, P, P]
     for w8, w4 in (("mixdq_gemm_w8a8_f16_dyn_res", "mixdq_gemm_w4a8_f16_dyn_res"),
                    ("mixdq_gemm_w8a8_geglu_f16_dyn", "mixdq_gemm_w4a8_geglu_f16_dyn"),
                    ("mixdq_conv_w8a8_f16", "mixdq_conv_w4a8_f16"),

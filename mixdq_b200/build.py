@@ -16,7 +16,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libmixdq_b200.so"
 STAMP = PKG_DIR / ".libmixdq_b200.stamp"
-SOURCES = ["quant.cu", "quant2.cu", "fused_quant.cu", "attn.cu", "simt.cu", "capi.cu", "persist.cu"]
+SOURCES = ["quant.cu", "quant2.cu", "fused_quant.cu", "simt.cu", "capi.cu", "persist.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -203,6 +203,7 @@ extern "C" int mixdq_stream_capture_id(mixdq_stream_t stream, unsigned long long
   return MIXDQ_OK;
 }
 extern "C" void mixdq_debug_set_persist(int mode, int cluster) { persist_set_mode(mode, cluster); }
+extern "C" void mixdq_debug_set_persist_bn(int bn) { persist_force_bn(bn); }
 extern "C" void mixdq_debug_force_bn(int bn) { g_force_bn = bn; }
 extern "C" void mixdq_debug_force_splits(int s) { g_force_splits = s; }
 // MIXDQ_A_PREFETCH=1 enables an L2 prefetch of the first A tile before the dependency wait.

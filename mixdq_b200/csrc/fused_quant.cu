@@ -490,7 +490,7 @@ using namespace mixdq;
 
 // quant2.cu / quant.cu
 int mixdq_q2_rows(const __half* x, int64_t ldx, int64_t M, int cols, int8_t* q, float* scale_out,
-                  float* zp_out, void* ws, cudaStream_t st);
+                  float* zp_out, void* ws, cudaStream_t st, int n_bits = 8);
 int mixdq_q2_premm(const __half* x, int64_t numel, int8_t* q, float* scale_out, float* zp_out,
                    void* ws, int nparts, unsigned long long* zero_words, int zero_n,
                    cudaStream_t st);

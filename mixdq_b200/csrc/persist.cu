@@ -9,7 +9,8 @@ namespace mixdq {
 
 static int g_persist_mode = -1;     // env MIXDQ_PERSIST: 0 = never, 1 = heuristic (default),
                                     // 2 = whenever the shape is supported (tests)
-static int g_persist_cs = -1;       // env MIXDQ_PERSIST_CS: 1 / 2 (default 2: W multicast pairs)
+static int g_persist_cs = -1;       // env MIXDQ_PERSIST_CS: 1 / 2 (default 2: cta_group::2 CTA pairs)
+static int g_persist_bn = 0;        // tuning hook: force this tile width (0 = cost model)
 static void read_env() {
   if (g_persist_mode < 0) {
     const char* e = getenv("MIXDQ_PERSIST");
@@ -44,6 +45,7 @@ int persist_pick_bn(int m_tiles, int N, int num_kb, int kind) {
   int best_bn = 0;
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
+    if (g_persist_bn > 0 && bn != g_persist_bn) continue;
     if (kind == KIND_GEGLU && bn != 256) continue;          // GEGLU projections: N2 % 256 == 0
     if (kind == KIND_GEGLU && (N % 256)) continue;
     const long tiles = static_cast<long>(m_tiles) * ((N + bn - 1) / bn);
@@ -54,6 +56,8 @@ int persist_pick_bn(int m_tiles, int N, int num_kb, int kind) {
   }
   return best_bn;
 }
+
+void persist_force_bn(int bn) { g_persist_bn = bn; }
 
 void persist_set_mode(int mode, int cs) {
   read_env();
@@ -68,7 +72,7 @@ int persist_cluster_size(int m_tiles) {
 
 template <int BN, int STAGES, int KIND, bool W4, int CS>
 static int launch(const CUtensorMap& a, const CUtensorMap& w, const TcParams& p, cudaStream_t st) {
-  using L = TpSmem<BN, STAGES, KIND, W4>;
+  using L = TpSmem<BN, STAGES, KIND, W4, CS>;
   auto kern = tc_i8_persist_kernel<BN, STAGES, KIND, W4, CS>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -98,15 +102,25 @@ static int launch(const CUtensorMap& a, const CUtensorMap& w, const TcParams& p,
   return cudaLaunchKernelEx(&cfg, kern, a, w, p) == cudaSuccess ? MIXDQ_OK : MIXDQ_ERR_CUDA;
 }
 
+// ring depth: what fits 227 KB next to the staging tiles and the per-column operands. A CTA of a
+// pair (CS = 2) stages only half of the W rows, so its ring is 1.3-1.5x deeper.
+template <int BN, int KIND, int CS>
+struct TpStages {
+  static constexpr int value =
+      CS == 1 ? (BN == 256 ? (KIND == KIND_CONV ? 3 : 4) : BN == 160 ? 5 : 6)
+              : (BN == 256 ? (KIND == KIND_CONV ? 5 : 6) : BN == 160 ? 7 : 8);
+};
+
 template <int KIND, bool W4, int CS>
 static int by_bn(int bn, const CUtensorMap& a, const CUtensorMap& w, const TcParams& p,
                  cudaStream_t st) {
-  constexpr int ST256 = (KIND == KIND_CONV) ? 3 : 4;   // the conv border table takes 17 KB
   switch (bn) {
-    case 256: return launch<256, ST256, KIND, W4, CS>(a, w, p, st);
-    case 160: if constexpr (KIND != KIND_GEGLU) return launch<160, 5, KIND, W4, CS>(a, w, p, st);
+    case 256: return launch<256, TpStages<256, KIND, CS>::value, KIND, W4, CS>(a, w, p, st);
+    case 160: if constexpr (KIND != KIND_GEGLU)
+                return launch<160, TpStages<160, KIND, CS>::value, KIND, W4, CS>(a, w, p, st);
               return MIXDQ_ERR_UNSUPPORTED;
-    case 128: if constexpr (KIND != KIND_GEGLU) return launch<128, 6, KIND, W4, CS>(a, w, p, st);
+    case 128: if constexpr (KIND != KIND_GEGLU)
+                return launch<128, TpStages<128, KIND, CS>::value, KIND, W4, CS>(a, w, p, st);
               return MIXDQ_ERR_UNSUPPORTED;
     default: return MIXDQ_ERR_UNSUPPORTED;
   }

@@ -12,6 +12,8 @@ namespace mixdq {
 int persist_pick_bn(int m_tiles, int N, int num_kb, int kind);
 // test / tuning hook: mode 0 = never, 1 = heuristic, 2 = whenever supported; cs = 1 / 2 (else kept)
 void persist_set_mode(int mode, int cs);
+// tuning hook: restrict the cost model to one tile width (0 = free choice)
+void persist_force_bn(int bn);
 // cluster size along M (1 or 2) for the chosen configuration
 int persist_cluster_size(int m_tiles);
 // tmW must have been encoded with box rows = bn / cs. Returns 0 or a negative MIXDQ_ERR_* code.

@@ -19,13 +19,14 @@ struct QParams {
   float a;  // static: 1/delta      dynamic: delta
   float b;  // static: zp (-128 shifted)   dynamic: z (unshifted, in [0,255])
   float inv;  // dynamic: 1/delta (set by quant_vec8 / the callers of quant_one)
+  int lo, hi; // static: code range ([-128, 127]; [0, 15] for 4-bit activations)
 };
 
 template <int MODE>
 __device__ __forceinline__ int quant_one(float x, QParams p) {
   if (MODE == kStaticFma) {
     int v = __float2int_rn(__fmaf_rn(x, p.a, p.b));
-    return min(max(v, -128), 127);
+    return min(max(v, p.lo), p.hi);
   } else {
     return qdiff_code(x, p.a, p.inv, p.b);
   }
@@ -37,6 +38,8 @@ __device__ __forceinline__ QParams load_qparams(const float* a, const float* b) 
   p.a = __ldg(a);
   p.b = __ldg(b);
   p.inv = 0.0f;
+  p.lo = -128;
+  p.hi = 127;
   if (MODE == kDynamicDiv) {
     p.b = p.b + 128.0f;  // stored zero point is z-128; exact in fp32
     p.inv = __frcp_rn(p.a);
@@ -76,9 +79,11 @@ constexpr int kQuantUnroll = 4;  // 16-byte loads in flight per thread
 template <int MODE>
 __global__ void __launch_bounds__(kQuantThreads)
 quant_flat_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int64_t numel,
-                  const float* __restrict__ pa, const float* __restrict__ pb) {
+                  const float* __restrict__ pa, const float* __restrict__ pb, int lo, int hi) {
   pdl_launch_dependents();   // the GEMM/conv that consumes q may start its weight prefetch now
-  const QParams p = load_qparams<MODE>(pa, pb);
+  QParams p = load_qparams<MODE>(pa, pb);
+  p.lo = lo;
+  p.hi = hi;
   const int64_t nvec = numel >> 3;
   const int4* xv = reinterpret_cast<const int4*>(x);
   uint2* qv = reinterpret_cast<uint2*>(q);
@@ -102,8 +107,11 @@ quant_flat_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int64_t 
 template <int MODE>
 __global__ void __launch_bounds__(kQuantThreads)
 quant_flat_scalar_kernel(const __half* __restrict__ x, int8_t* __restrict__ q, int64_t numel,
-                         const float* __restrict__ pa, const float* __restrict__ pb) {
-  const QParams p = load_qparams<MODE>(pa, pb);
+                         const float* __restrict__ pa, const float* __restrict__ pb, int lo,
+                         int hi) {
+  QParams p = load_qparams<MODE>(pa, pb);
+  p.lo = lo;
+  p.hi = hi;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kQuantThreads;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * kQuantThreads + threadIdx.x; i < numel;
        i += stride)
@@ -264,29 +272,26 @@ using namespace mixdq;
 
 // quant2.cu: the two-kernel (min/max pass + quantise pass) implementations
 int mixdq_q2_rows(const __half* x, int64_t ldx, int64_t M, int cols, int8_t* q, float* scale_out,
-                  float* zp_out, void* ws, cudaStream_t st);
+                  float* zp_out, void* ws, cudaStream_t st, int n_bits = 8);
 int mixdq_q2_premm(const __half* x, int64_t numel, int8_t* q, float* scale_out, float* zp_out,
                    void* ws, int nparts, unsigned long long* zero_words, int zero_n,
                    cudaStream_t st);
-// 0 = single-kernel quantisers with the counter barrier (first generation), 1 (default) = min/max
-// pass + quantise pass, 2 = additionally the lean one-kernel form (tagged-partial barrier) for
-// tensors that fit the registers of one co-resident grid: 1.5 us of barrier in an isolated chain
-// (tools/quant_phase.py) but 8.8 us per kernel inside the whole-UNet graph (9.06 vs 7.87 ms per
-// step), so it is not the default; 3 = compact ONE-CLUSTER kernels (16 CTAs x 512 threads, values
-// in registers, DSMEM + hardware cluster barrier) where the tensor fits: 9.1 us (LayerNorm) / 6.4
-// us (plain) per kernel inside the graph (8.16 ms per step) — gang-scheduling 16 CTAs into one GPC
-// while early-launched GEMM CTAs hold most SMs costs more than a kernel boundary.
+// 1 (default) = min/max pass + quantise pass chained by programmatic dependent launch; 0 = the
+// first-generation single-kernel quantisers with the counter barrier, kept as the fallback for
+// callers without a scratch buffer and as the A/B reference of the parity tests. Two further
+// one-kernel designs (tagged-partial barrier, one-cluster DSMEM) were measured slower inside the
+// whole-UNet graph and removed (profiles/README.md section 3 keeps the numbers).
 // MIXDQ_QUANT_MODE / mixdq_debug_set_two_pass select the mode.
 static int g_two_pass = -1;
 int mixdq_quant_mode() {
   if (g_two_pass < 0) {
     const char* e = getenv("MIXDQ_QUANT_MODE");
-    g_two_pass = (e && e[0] >= '0' && e[0] <= '3') ? (e[0] - '0') : 1;
+    g_two_pass = (e && e[0] == '0') ? 0 : 1;
   }
   return g_two_pass;
 }
 bool mixdq_two_pass_enabled() { return mixdq_quant_mode() != 0; }
-extern "C" void mixdq_debug_set_two_pass(int mode) { g_two_pass = mode < 0 ? 0 : (mode > 3 ? 3 : mode); }
+extern "C" void mixdq_debug_set_two_pass(int mode) { g_two_pass = mode <= 0 ? 0 : 1; }
 
 extern "C" void mixdq_debug_set_cluster(int on) { cluster_mode_flag() = on ? 1 : 0; }
 // profiling: point the workspace at a stamp buffer (or NULL) and restart the launch sequence;
@@ -317,15 +322,15 @@ static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>
 
 template <int MODE>
 static int launch_flat(const __half* x, int64_t numel, const float* a, const float* b, int8_t* q,
-                       cudaStream_t st) {
+                       cudaStream_t st, int lo = -128, int hi = 127) {
   if (numel == 0) return MIXDQ_OK;
   const int max_blocks = 148 * 8;
   if (aligned16(x) && aligned8(q)) {
     int grid = grid_for(numel >> 3, kQuantThreads * kQuantUnroll, max_blocks);
-    quant_flat_kernel<MODE><<<grid, kQuantThreads, 0, st>>>(x, q, numel, a, b);
+    quant_flat_kernel<MODE><<<grid, kQuantThreads, 0, st>>>(x, q, numel, a, b, lo, hi);
   } else {
     int grid = grid_for(numel, kQuantThreads, max_blocks);
-    quant_flat_scalar_kernel<MODE><<<grid, kQuantThreads, 0, st>>>(x, q, numel, a, b);
+    quant_flat_scalar_kernel<MODE><<<grid, kQuantThreads, 0, st>>>(x, q, numel, a, b, lo, hi);
   }
   MIXDQ_CHECK_LAUNCH();
   return MIXDQ_OK;
@@ -336,6 +341,18 @@ extern "C" int mixdq_quant_i8_static(const mixdq_half_t* x, int64_t numel, const
   if (numel < 0 || (numel > 0 && (!x || !q)) || !scale_inv || !zp) return MIXDQ_ERR_INVALID_ARG;
   return launch_flat<kStaticFma>(reinterpret_cast<const __half*>(x), numel, scale_inv, zp, q,
                                  static_cast<cudaStream_t>(stream));
+}
+
+// A1 with an explicit code range: q = clamp(lrintf(x * scale_inv + zp), lo, hi). The 4-bit
+// activation layers use [0, 15] with the UNSHIFTED zero point of the PTQ checkpoint.
+extern "C" int mixdq_quant_i8_static_range(const mixdq_half_t* x, int64_t numel,
+                                           const float* scale_inv, const float* zp, int lo,
+                                           int hi, int8_t* q, mixdq_stream_t stream) {
+  if (numel < 0 || (numel > 0 && (!x || !q)) || !scale_inv || !zp || lo < -128 || hi > 127 ||
+      lo > hi)
+    return MIXDQ_ERR_INVALID_ARG;
+  return launch_flat<kStaticFma>(reinterpret_cast<const __half*>(x), numel, scale_inv, zp, q,
+                                 static_cast<cudaStream_t>(stream), lo, hi);
 }
 
 extern "C" int mixdq_quant_i8_static_strided(const mixdq_half_t* x, int64_t d0, int64_t d1,
@@ -429,4 +446,20 @@ extern "C" int mixdq_quant_i8_premm(const mixdq_half_t* x, int64_t numel, int8_t
   if ((numel & 7) || !aligned16(x) || !aligned8(q)) return MIXDQ_ERR_ALIGNMENT;
   return mixdq_q2_premm(reinterpret_cast<const __half*>(x), numel, q, scale_out, zp_out, ws,
                         partial_count_slot(ws), nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+// A10 with a code range: n_bits = 8 -> codes - 128 (same as mixdq_quant_i8_dynamic_rows), n_bits = 4
+// -> codes 0..15 stored as they are, *zp_out = z (the 4-bit activation layers of the act_7.xx bit
+// configs, which the reference gates to fp16, nn/Linear.py:28-36). Row-pitched view [M][cols].
+extern "C" int mixdq_quant_i8_dynamic_bits(const mixdq_half_t* x, int64_t ldx, int64_t M,
+                                           int64_t cols, int n_bits, float* scale_out,
+                                           float* zp_out, int8_t* q, void* ws,
+                                           mixdq_stream_t stream) {
+  if (M <= 0 || cols <= 0 || ldx < cols || !x || !q || !scale_out || !zp_out || !ws)
+    return MIXDQ_ERR_INVALID_ARG;
+  if (n_bits != 8 && n_bits != 4) return MIXDQ_ERR_UNSUPPORTED;
+  if ((cols & 7) || (ldx & 7) || !aligned16(x) || !aligned8(q) || cols > (1ll << 30))
+    return MIXDQ_ERR_ALIGNMENT;
+  return mixdq_q2_rows(reinterpret_cast<const __half*>(x), ldx, M, static_cast<int>(cols), q,
+                       scale_out, zp_out, ws, static_cast<cudaStream_t>(stream), n_bits);
 }

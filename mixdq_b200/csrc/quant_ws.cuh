@@ -100,8 +100,9 @@ struct QDbg {
 
 // qdiff asymmetric 8-bit min-max parameters (base_quantizer.py:155-190), fp32:
 //   delta = max((x_max - x_min) / 255, 1e-6),  z = rint(-x_min / delta)
-__device__ __forceinline__ void qdiff_params(float mn, float mx, float& delta, float& z) {
-  delta = __fdiv_rn(__fsub_rn(mx, mn), 255.0f);
+__device__ __forceinline__ void qdiff_params(float mn, float mx, float& delta, float& z,
+                                             float qmax = 255.0f) {
+  delta = __fdiv_rn(__fsub_rn(mx, mn), qmax);
   if (delta < 1e-6f) delta = 1e-6f;
   z = rintf(__fdiv_rn(-mn, delta));
 }

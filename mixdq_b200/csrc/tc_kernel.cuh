@@ -293,6 +293,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
+  __syncwarp();                          // lane 0 of warp 0 rejoins before the CTA barrier
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -745,6 +746,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (second) tmem_ld_32x16(taddr + BN, reinterpret_cast<uint32_t(&)[16]>(v1));
         }
         tmem_ld_wait();
+        if (threadIdx.x == 64 && c == c_lo) MIXDQ_DBG(12);  // first accumulator chunk in registers
         if (DUAL && dual_used) {       // the two issuers' accumulators: exact int32 sum
 #pragma unroll
           for (int j = 0; j < CH; ++j) v[j] += v1[j];
@@ -770,6 +772,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
         __syncwarp();
+        if (threadIdx.x == 64 && c == c_lo) MIXDQ_DBG(13);  // first chunk dequantised and staged
         const int ccol = c * CH + (lane % LPR) * 8;
         uint4 o[LPR];
         const bool col_ok = n_tile0 + ccol + 8 <= p.N;
@@ -910,6 +913,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
   if (threadIdx.x == 64) MIXDQ_DBG(7);    // epilogue done
 
+  __syncwarp();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();

@@ -18,12 +18,17 @@
 //                                tc_kernel.cuh); the epilogue warps are busy here, so the nibble
 //                                expansion has warps of its own
 //
-// Cluster of 2 CTAs along M (CS = 2): the pair computes two vertically adjacent tiles that share
-// the W tile; each CTA fetches HALF of the W rows and TMA-multicasts them into both CTAs' rings,
-// so a 128 x 256 tile costs 16 KB (A) + 16 KB (W half) of L2 traffic per k-block instead of 48 KB
-// (256 instead of 170 op/B: the L2 -> SM fabric, ~6300 B/clk chip-wide, is what bounds a
-// 1-CTA 128 x 256 tiling at ~60 % of the INT8 peak). A ring slot is recycled only when BOTH CTAs
-// consumed it: tcgen05.commit arrives on the slot's empty barrier of both CTAs (multicast).
+// CTA pair (CS = 2): two CTAs of one TPC run ONE 256 x BN tile with tcgen05.mma.cta_group::2. Each
+// CTA stages its own 128 A rows and HALF of the W rows (BN / 2) — the tensor cores of the pair
+// read the other half from the peer's shared memory — so a k-block costs 16 KB (A) + BN / 2 x 128 B
+// of L2 -> SM traffic and of ring space per SM instead of 16 KB + BN x 128 B: 1.5x fewer operand
+// bytes for BN = 256 and a 6-deep instead of a 4-deep ring (the L2 -> SM fabric and the ring depth,
+// not the tensor pipe, bound the single-CTA form: tools/persist_modes.py). Protocol (as CUTLASS's
+// 2-SM kernels): both CTAs' TMA loads complete on the LEADER's full barrier (cp.async.bulk.tensor
+// .cta_group::2), the leader's single MMA thread issues for both SMs and its tcgen05.commit
+// multicasts to the empty / accumulator-full barriers of both CTAs; both CTAs' epilogue warps
+// arrive on the leader's accumulator-empty barrier. A first version of CS = 2 only multicast the
+// W tile to two independent cta_group::1 CTAs: same speed as CS = 1 (profiles/README.md).
 //
 // Same operand layouts, tensor maps, KIND semantics (GEMM / CONV / GEGLU), epilogue arithmetic and
 // TcParams as tc_i8_kernel; p.tiles_m / p.tiles_n describe the tile grid.
@@ -38,10 +43,11 @@ constexpr int TP_CONV_WARPS = 4;
 constexpr int TP_THREADS_W4 = TP_THREADS + 32 * TP_CONV_WARPS;   // 448
 constexpr int TP_SLOT_COLS = 256;                           // TMEM columns per accumulator slot
 
-template <int BN, int STAGES, int KIND, bool W4>
+template <int BN, int STAGES, int KIND, bool W4, int CS = 1>
 struct TpSmem {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K;
-  static constexpr int W_BYTES = BN * BLOCK_K;
+  static constexpr int W_ROWS = BN / CS;                     // W rows staged by this CTA
+  static constexpr int W_BYTES = W_ROWS * BLOCK_K;
   static constexpr int CH = 32;                              // accumulator columns per chunk
   static constexpr int OUT_PITCH = CH * 2 + 16;              // fp16 staging row (+16 B pad)
   static constexpr int OUT_WARP = 32 * OUT_PITCH;            // one warp: 32 rows
@@ -61,32 +67,72 @@ struct TpSmem {
   static_assert(DYN_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 };
 
-// multicast TMA loads: the tile lands at the same shared-memory offset of every CTA in cta_mask
-// and completes transaction bytes on the mbarrier at the same offset of each of them
-__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar,
-                                               int c0, int c1, uint16_t cta_mask) {
+// ---- CTA-pair (cta_group::2) forms ------------------------------------------------------------
+// TMA loads whose completion bytes go to an mbarrier of EITHER CTA of the pair (`bar_cluster_addr`
+// is a shared::cluster address, e.g. the leader's full barrier obtained with mapa)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m,
+                                                 uint32_t bar_cluster_addr, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* m, uint64_t* bar,
-                                               int c0, int c1, int c2, uint16_t cta_mask) {
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* m,
+                                                 uint32_t bar_cluster_addr, int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
-      "h"(cta_mask)
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// tcgen05.commit arriving on the mbarrier at this offset in every CTA of cta_mask
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* m,
+                                                 uint32_t bar_cluster_addr, int c0, int c1, int c2,
+                                                 int c3) {
   asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+// one 256 x N x 32 MMA across the pair: issued by ONE thread of the leader CTA; descriptors are
+// shared-memory offsets valid in both CTAs, D is the same TMEM address in both
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// tcgen05.commit of the pair's MMAs arriving on the mbarrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
       " [%0], %1;" ::"r"(smem_u32(bar)),
       "h"(cta_mask)
       : "memory");
+}
+// plain arrive on an mbarrier given by its shared::cluster address (own or peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -96,12 +142,13 @@ template <int BN, int STAGES, int KIND, bool W4, int CS>
 __global__ void __launch_bounds__(W4 ? TP_THREADS_W4 : TP_THREADS, 1)
 tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                      const TcParams p) {
-  using L = TpSmem<BN, STAGES, KIND, W4>;
+  using L = TpSmem<BN, STAGES, KIND, W4, CS>;
   static_assert(KIND == KIND_GEMM || KIND == KIND_CONV || KIND == KIND_GEGLU, "unsupported kind");
   static_assert(BN % 32 == 0 && BN >= 64 && BN <= TP_SLOT_COLS, "tile width (every epilogue warp owns >= 1 chunk)");
   static_assert(CS == 1 || CS == 2, "cluster size along M");
-  static_assert(CS == 1 || BN % 16 == 0, "W halves");
-  constexpr uint32_t IDESC = umma_idesc_i8(BLOCK_M, BN);
+  static_assert(CS == 1 || BN % 32 == 0, "W halves");
+  constexpr bool PAIR = CS == 2;
+  constexpr uint32_t IDESC = umma_idesc_i8(PAIR ? 2 * BLOCK_M : BLOCK_M, BN);
   constexpr int CH = L::CH;
   constexpr int NCH = BN / CH;
 
@@ -132,7 +179,11 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int m_groups = (p.tiles_m + CS - 1) / CS;
   const int total_groups = m_groups * p.tiles_n;
   const int num_kb = p.num_kb;
-  constexpr uint16_t MC_MASK = (CS > 1) ? 0x3 : 0x1;
+  const bool leader = crank == 0;
+  // the leader's barriers as shared::cluster addresses (identity for the leader itself)
+  auto leader_addr = [&](const void* bar) {
+    return PAIR ? dsmem_map(smem_u32(bar), 0u) : smem_u32(bar);
+  };
 
   struct Tile { int m0, tn0, tp0, tq0, n_tile0; };
   auto tile_of = [&](int g) {
@@ -154,20 +205,26 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], W4 ? 1 + TP_CONV_WARPS : 1);
-      mbar_init(&empty_bar[i], CS);                // every CTA of the pair must have consumed it
+      // full: the producer's expect_tx arrival (+ the converter warps of BOTH CTAs for W4); in
+      // pair mode only the leader's full barriers are used
+      mbar_init(&full_bar[i], W4 ? 1 + CS * TP_CONV_WARPS : 1);
+      mbar_init(&empty_bar[i], 1);                 // one tcgen05.commit (multicast to both CTAs)
       if (W4) mbar_init(&raw_full[i], 1);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], TP_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], CS * TP_EPI_WARPS);   // pair: both CTAs' epilogue warps
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 2 * TP_SLOT_COLS);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_pair(tmem_slot, 2 * TP_SLOT_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, 2 * TP_SLOT_COLS); tmem_relinquish(); }
   }
+  __syncwarp();                          // lane 0 of warp 0 rejoins before the CTA barrier
   tc_fence_before();
   __syncthreads();
-  if (CS > 1) cluster_sync_all();        // the peer's barriers exist before anything multicasts
+  if (PAIR) cluster_sync_all();          // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -175,21 +232,21 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ===================== TMA producer =====================
     const uint32_t a_bytes = (KIND == KIND_CONV) ? p.a_tx_bytes : static_cast<uint32_t>(L::A_BYTES);
     constexpr int WK = W4 ? BLOCK_K / 2 : BLOCK_K;       // bytes of K per k-block in memory
-    constexpr int WROWS = BN / CS;                       // W rows this CTA fetches (and multicasts)
-    constexpr uint32_t W_TX = W4 ? L::W_BYTES / 2 : L::W_BYTES;   // bytes landing per CTA and k-block
+    constexpr int WROWS = L::W_ROWS;                     // W rows this CTA stages
+    constexpr uint32_t W_TX = W4 ? L::W_BYTES / 2 : L::W_BYTES;   // W bytes landing per CTA and k-block
     auto load_w = [&](const Tile& t, int kb, int stage) {
-      // W4: packed rows (64 B) land in the upper half of the slot, unswizzled
-      uint8_t* w_dst = sW + stage * L::W_BYTES + (W4 ? L::W_BYTES / 2 : 0) + crank * WROWS * WK;
-      uint64_t* bar = W4 ? &raw_full[stage] : &full_bar[stage];
+      // W4: packed rows (64 B) land in the upper half of the slot, unswizzled, and complete on
+      // this CTA's own raw_full barrier (the converter warps signal the leader's full barrier)
+      uint8_t* w_dst = sW + stage * L::W_BYTES + (W4 ? L::W_BYTES / 2 : 0);
       const int row0 = t.n_tile0 + crank * WROWS;
       if (KIND == KIND_CONV) {
         const int tap = kb / p.kb_per_tap;
         const int c0 = (kb - tap * p.kb_per_tap) * WK;
-        if (CS > 1) tma_load_3d_mc(w_dst, &tmW, bar, c0, tap, row0, MC_MASK);
-        else tma_load_3d(w_dst, &tmW, bar, c0, tap, row0);
+        if (W4 || !PAIR) tma_load_3d(w_dst, &tmW, W4 ? &raw_full[stage] : &full_bar[stage], c0, tap, row0);
+        else tma_load_3d_pair(w_dst, &tmW, leader_addr(&full_bar[stage]), c0, tap, row0);
       } else {
-        if (CS > 1) tma_load_2d_mc(w_dst, &tmW, bar, kb * WK, row0, MC_MASK);
-        else tma_load_2d(w_dst, &tmW, bar, kb * WK, row0);
+        if (W4 || !PAIR) tma_load_2d(w_dst, &tmW, W4 ? &raw_full[stage] : &full_bar[stage], kb * WK, row0);
+        else tma_load_2d_pair(w_dst, &tmW, leader_addr(&full_bar[stage]), kb * WK, row0);
       }
     };
     auto load_a = [&](const Tile& t, int kb, int stage) {
@@ -198,23 +255,30 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int tap = kb / p.kb_per_tap;
         const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
         const int r = tap / p.S, s = tap - r * p.S;
-        tma_load_4d(a_dst, &tmA, &full_bar[stage], c0, t.tq0 * p.stride - p.pad + s,
-                    t.tp0 * p.stride - p.pad + r, t.tn0);
+        if (PAIR) tma_load_4d_pair(a_dst, &tmA, leader_addr(&full_bar[stage]), c0,
+                                   t.tq0 * p.stride - p.pad + s, t.tp0 * p.stride - p.pad + r, t.tn0);
+        else tma_load_4d(a_dst, &tmA, &full_bar[stage], c0, t.tq0 * p.stride - p.pad + s,
+                         t.tp0 * p.stride - p.pad + r, t.tn0);
       } else {
-        tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BLOCK_K, t.m0);
+        if (PAIR) tma_load_2d_pair(a_dst, &tmA, leader_addr(&full_bar[stage]), kb * BLOCK_K, t.m0);
+        else tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BLOCK_K, t.m0);
       }
     };
+    // bytes the LEADER's full barrier of a stage expects: A (+ unpacked W) of every CTA of the pair
+    const uint32_t full_tx = static_cast<uint32_t>(CS) * (a_bytes + (W4 ? 0u : W_TX));
     // The first ring-full of WEIGHT k-blocks does not depend on the preceding kernel: issue it
     // before the programmatic-dependency wait (activations follow after it).
     uint32_t it = 0;                                     // k-block iterations issued so far
     int pre = 0;
-    if (cid < total_groups) {
+    // profiling only (results are garbage): bit1 = no TMA loads, bit0 = no MMA issue
+    const bool skip_tma = !W4 && (p.dbg_mode & 2) != 0;
+    if (cid < total_groups && !skip_tma) {
       const Tile t0 = tile_of(cid);
       pre = num_kb < STAGES ? num_kb : STAGES;
       if (elect_one()) {
         for (int i = 0; i < pre; ++i) {
           if (W4) mbar_expect_tx(&raw_full[i], W_TX);
-          else mbar_expect_tx(&full_bar[i], a_bytes + W_TX);
+          else if (leader) mbar_expect_tx(&full_bar[i], full_tx);
           load_w(t0, i, i);
         }
       }
@@ -228,20 +292,25 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const bool early_w = (g == cid) && (kb < pre);   // W already in flight
         if (it >= static_cast<uint32_t>(STAGES)) mbar_wait(&empty_bar[stage], ((it / STAGES) & 1u) ^ 1u);
         if (elect_one()) {
-          if (early_w) {
-            if (W4) mbar_expect_tx(&full_bar[stage], a_bytes);
+          if (skip_tma) {
+            if (leader) mbar_arrive(&full_bar[stage]);
           } else {
-            if (W4) { mbar_expect_tx(&raw_full[stage], W_TX); mbar_expect_tx(&full_bar[stage], a_bytes); }
-            else mbar_expect_tx(&full_bar[stage], a_bytes + W_TX);
-            load_w(t, kb, stage);
+            if (early_w) {
+              if (W4 && leader) mbar_expect_tx(&full_bar[stage], full_tx);
+            } else {
+              if (W4) mbar_expect_tx(&raw_full[stage], W_TX);
+              if (leader) mbar_expect_tx(&full_bar[stage], full_tx);
+              load_w(t, kb, stage);
+            }
+            load_a(t, kb, stage);
           }
-          load_a(t, kb, stage);
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (pair: the leader CTA's only) =====================
+    if (leader) {
     const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
     const uint64_t w_desc0 = umma_desc_sw128(smem_u32(sW));
     uint32_t it = 0, tl = 0;
@@ -257,16 +326,26 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (elect_one()) {
           const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(stage * (L::A_BYTES >> 4));
           const uint64_t w_desc = w_desc0 + static_cast<uint64_t>(stage * (L::W_BYTES >> 4));
+          if (!(p.dbg_mode & 1)) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_i8(d_tmem, a_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)),
-                    w_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)), IDESC, (kb | k) ? 1u : 0u);
-          if (CS > 1) umma_commit_mc(&empty_bar[stage], MC_MASK);   // frees the slot in BOTH CTAs
-          else umma_commit(&empty_bar[stage]);
-          if (kb == num_kb - 1) umma_commit(&tmem_full[slot]);      // accumulator complete
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              if (PAIR) umma_i8_pair(d_tmem, a_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)),
+                                     w_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)), IDESC,
+                                     (kb | k) ? 1u : 0u);
+              else umma_i8(d_tmem, a_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)),
+                           w_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)), IDESC, (kb | k) ? 1u : 0u);
+          }
+          if (PAIR) {
+            umma_commit_pair(&empty_bar[stage], 0x3);                // frees the slot in BOTH CTAs
+            if (kb == num_kb - 1) umma_commit_pair(&tmem_full[slot], 0x3);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit(&tmem_full[slot]);    // accumulator complete
+          }
         }
         __syncwarp();
       }
+    }
     }
   } else if (warp < 2 + TP_EPI_WARPS) {
     // ===================== epilogue warps =====================
@@ -371,7 +450,7 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (c == c_hi - 1) {                         // this warp has read its part of the slot
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+            if (lane == 0) mbar_arrive_cluster(leader_addr(&tmem_empty[slot]));
           }
           if (W4) {
 #pragma unroll
@@ -442,7 +521,7 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (c == c_hi - 1) {                         // this warp has read its part of the slot
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+            if (lane == 0) mbar_arrive_cluster(leader_addr(&tmem_empty[slot]));
           }
           if (W4) {
 #pragma unroll
@@ -511,7 +590,7 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if constexpr (W4) {
       const int ct = threadIdx.x - 32 * (2 + TP_EPI_WARPS);       // 0..127
       constexpr int NT = 32 * TP_CONV_WARPS;
-      constexpr int CPS = BN * 4;                                  // 16-byte packed chunks per k-block
+      constexpr int CPS = L::W_ROWS * 4;                           // 16-byte packed chunks per k-block
       constexpr int PT = (CPS + NT - 1) / NT;
       uint32_t it = 0;
       for (int g = cid; g < total_groups; g += nclusters) {
@@ -548,17 +627,19 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&full_bar[stage]);
+          if (lane == 0) mbar_arrive_cluster(leader_addr(&full_bar[stage]));
         }
       }
     }
   }
 
+  __syncwarp();
   __syncthreads();
-  if (CS > 1) cluster_sync_all();      // no CTA exits while its peer may still multicast into it
+  if (PAIR) cluster_sync_all();        // no CTA exits (or frees TMEM) while the pair still runs
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * TP_SLOT_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 2 * TP_SLOT_COLS);
+    else tmem_dealloc(tmem_base, 2 * TP_SLOT_COLS);
   }
 }
 

@@ -46,6 +46,8 @@ from .nn.linear import QuantizedLinear
 def _lin_ok(m) -> bool:
     if not (isinstance(m, QuantizedLinear) and m.valid_for_acceleration and m.dynamic):
         return False
+    if m.a_bits != 8:
+        return False                       # 4-bit activation layers run module by module
     k_align = 32 if m.w_kind == "w4" else 16
     return m.in_features % k_align == 0 and m.out_features % 8 == 0
 
@@ -250,14 +252,9 @@ def _heads(t: torch.Tensor, heads: int):
 
 
 import os as _os
-# MIXDQ_CUSTOM_CROSS_ATTN=1: cross-attention (<= 96 context tokens, head dim 64) through
-# csrc/attn.cu (mma.sync + min/max partials of its output) instead of the library SDPA + a separate
-# min/max pass. Measured on B200: 0.8 us faster per block in an isolated chain
-# (tools/attn_chain.py: 17.0 vs 17.8 us), but 13.2 us per launch against 5.7 + 2.4 us inside the
-# whole-UNet graph, where its 30 KB of straight-line code is fetched cold every time (8.16 vs 7.82
-# ms per step) — so the library call stays the default.
-CUSTOM_CROSS_ATTENTION = _os.environ.get("MIXDQ_CUSTOM_CROSS_ATTN", "0") == "1"
-
+# An own cross-attention kernel (mma.sync, min/max partials of its output) was measured slower than
+# the library SDPA + a separate min/max pass inside the whole-UNet graph (13.2 us vs 5.7 + 2.4 us,
+# profiles/README.md section 3) and removed in round 2.
 _SDPA_BACKEND = None      # None = PyTorch's own choice; set by MIXDQ_SDPA_BACKEND (tuning aid)
 
 
@@ -343,13 +340,8 @@ def fused_transformer_block_forward(self, hidden_states, *args, **kwargs):
     kv = f["kv"]
     kk, vv = kv.get(self.attn2.to_k, ctx), kv.get(self.attn2.to_v, ctx)
     heads = self.attn2.heads
-    if CUSTOM_CROSS_ATTENTION and q.shape[-1] == heads * 64 and kk.shape[1] <= 96 \
-            and ((q.shape[1] + 63) // 64) * heads * q.shape[0] <= 4096:
-        # own kernel: cross-attention + min/max partials of its output (csrc/attn.cu)
-        o8, s, z = ops.cross_attention_quantize_dynamic(q, kk, vv, heads)
-    else:
-        o = _attention(q, kk, vv, heads)
-        o8, s, z = _quant_tokens(o)
+    o = _attention(q, kk, vv, heads)
+    o8, s, z = _quant_tokens(o)
     x = _run_linear(self.attn2.to_out[0], o8, s, z, residual=x)
     # --- feed-forward ---
     q8, s, z = ops.layernorm_quantize_dynamic(x, self.norm3.weight, self.norm3.bias, self.norm3.eps)

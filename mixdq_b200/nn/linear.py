@@ -7,7 +7,11 @@ Same constructor / `from_float(float_mod, split=0, ckpt=None)` / buffer names / 
     as true W4A8: `weight_int4` holds the packed codes (uint8 [N, K/2], even k in the high nibble,
     nn/utils.py:26-28), which the tcgen05 kernel unpacks on the fly;
   * `ckpt=None` selects dynamic mode: qdiff min-max weight scales computed here, activations
-    quantised per call from their own min/max (reference base_quantizer.py:155-190).
+    quantised per call from their own min/max (reference base_quantizer.py:155-190);
+  * 4-bit ACTIVATIONS (`a_bit: 4` in kernels/cfgs/act/act_7.xx.yaml — every such layer of the
+    shipped configs is a Linear; the reference runs them in fp16, nn/Linear.py:28-36) are
+    quantised to codes 0..15 kept one per int8, with the unshifted zero point, and run on the
+    same int8 kernels (`a_bits = 4`, `_get_name()` -> "...A4").
 """
 from __future__ import annotations
 
@@ -41,14 +45,17 @@ def _weight_kind(w_qparams):
 
 
 def _act_ok(a_qparams):
-    return (a_qparams is not None and a_qparams.dtype in _W8
+    return (a_qparams is not None and a_qparams.dtype in _W8 + _W4
             and a_qparams.qscheme == torch.per_tensor_affine)
 
 
 class QuantizedLinear(nn.Module):
     def __init__(self, in_features: int, out_features: int, bias: bool = True, device=None,
-                 w_qparams=None, a_qparams=None, module_name=None, dynamic: bool = False) -> None:
+                 w_qparams=None, a_qparams=None, module_name=None, dynamic: bool = False,
+                 a_bits: int = 8) -> None:
         super().__init__()
+        assert a_bits in (4, 8)
+        self.a_bits = a_bits
         self.module_name = module_name
         self.in_features = in_features
         self.out_features = out_features
@@ -91,7 +98,7 @@ class QuantizedLinear(nn.Module):
             else:
                 w_qparams = None
             a_qparams = None
-            use_dynamic = hasattr(float_mod, "a_bit") and act_dtype in _W8
+            use_dynamic = hasattr(float_mod, "a_bit") and act_dtype in _W8 + _W4
         else:
             w_pair = create_qparams_from_dtype(dtype=w_dtype, device=device, is_channel_wise=True,
                                                num_kernels=n_out, ckpt=ckpt,
@@ -107,11 +114,15 @@ class QuantizedLinear(nn.Module):
                                                    quant_type="act", bit_width=float_mod.a_bit,
                                                    split=split)
                 a_qparams = a_pair[0] if a_pair is not None else None
+                if a_qparams is not None and act_dtype in _W4:
+                    # 4-bit codes stay unsigned 0..15: undo the uint8 -> int8 shift of get_quant_para
+                    a_qparams = a_qparams._replace(zero_points=a_qparams.zero_points + 128)
             use_dynamic = False
 
         new_mod = cls(float_mod.in_features, float_mod.out_features, float_mod.bias is not None,
                       device=device, w_qparams=w_qparams, a_qparams=a_qparams,
-                      module_name=float_mod.module_name, dynamic=use_dynamic)
+                      module_name=float_mod.module_name, dynamic=use_dynamic,
+                      a_bits=4 if act_dtype in _W4 else 8)
 
         name = float_mod.module_name or ""
         if "attn2" in name and ("to_k" in name or "to_v" in name) and hasattr(float_mod, "bos"):
@@ -146,7 +157,7 @@ class QuantizedLinear(nn.Module):
 
     def _get_name(self):
         if self.valid_for_acceleration:
-            return "QuantizedLinearW8A8" if self.w_kind == "w8" else "QuantizedLinearW4A8"
+            return f"QuantizedLinear{'W8' if self.w_kind == 'w8' else 'W4'}A{self.a_bits}"
         return "QuantizedLinearFPFallback"
 
     # ------------------------------------------------------------------------------------
@@ -170,7 +181,7 @@ class QuantizedLinear(nn.Module):
 
     def _qlinear(self, x: torch.Tensor) -> torch.Tensor:
         if self.dynamic:
-            x_int, a_scale, a_zp = ops.quantize_per_tensor_dynamic(x)
+            x_int, a_scale, a_zp = ops.quantize_per_tensor_dynamic_bits(x, self.a_bits)
             if self.w_kind == "w8":
                 return ops.qlinear_w8_a8_ohalf_dynamic(
                     x_int, self.weight_int, self.weight_scales, a_scale, a_zp,
@@ -179,7 +190,11 @@ class QuantizedLinear(nn.Module):
             # are folded in its epilogue
             return ops.qlinear_dynamic_fused(x_int, self.weight_int4, self.weight_scales, a_scale,
                                              a_zp, self.weight_sum_by_input_channels, self.bias)
-        x_int = ops.quantize_per_tensor_to_int8(x, self.act_scales_inv, self.act_zero_points)
+        if self.a_bits == 4:
+            x_int = ops.quantize_per_tensor_to_int4_codes(x, self.act_scales_inv,
+                                                          self.act_zero_points)
+        else:
+            x_int = ops.quantize_per_tensor_to_int8(x, self.act_scales_inv, self.act_zero_points)
         if self.w_kind == "w8":
             return ops.qlinear_w8_a8_ohalf(
                 x_int, self.weight_int, self.weight_scales, self.act_scales,

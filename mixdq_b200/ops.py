@@ -323,6 +323,48 @@ def quantize_per_tensor_dynamic(input: torch.Tensor) -> Tuple[torch.Tensor, torc
     return res
 
 
+def quantize_per_tensor_dynamic_bits(input: torch.Tensor, n_bits: int
+                                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """qdiff asymmetric n-bit min-max quantisation (base_quantizer.py:155-190) in the kernel format.
+    n_bits = 8: same as quantize_per_tensor_dynamic. n_bits = 4 (N3, the 4-bit activation layers of
+    kernels/cfgs/act/act_7.xx.yaml that the reference runs in fp16, nn/Linear.py:28-36): codes
+    0..15 stored in int8 as they are, zero_point = z (unshifted) — consumed by the same int8
+    kernels. Returns (q int8, scale fp32[], zero_point fp32[])."""
+    if n_bits == 8:
+        return quantize_per_tensor_dynamic(input)
+    _check(n_bits == 4, "activation bit width should be 8 or 4")
+    _check(input.device.type == "cuda", "input should be on CUDA")
+    _check(input.dtype == torch.float16, "input should be fp16")
+    x = input if _is_dense(input) else input.contiguous()
+    _check(x.numel() % 8 == 0 and x.numel() > 0, "4-bit activation quantisation needs numel % 8 == 0")
+    lib = _lib.load()
+    out = torch.empty_like(x, dtype=torch.int8)
+    qp = torch.empty(2, dtype=torch.float32, device=x.device)
+    with _DeviceGuard(x):
+        ws = _dynamic_workspace(x.device)
+        _launch("quant_dyn", lib.mixdq_quant_i8_dynamic_bits,
+                (x.data_ptr(), x.numel(), 1, x.numel(), 4, qp.data_ptr(), qp.data_ptr() + 4,
+                 out.data_ptr(), ws.data_ptr()), x, kernels=2, keep=(x, qp, out, ws),
+                algo_bytes=3 * x.numel())
+    return out, qp[0], qp[1]
+
+
+def quantize_per_tensor_to_int4_codes(input: torch.Tensor, scale_inv: torch.Tensor,
+                                      zero_point: torch.Tensor) -> torch.Tensor:
+    """Static 4-bit activation codes: q = clamp(lrintf(x * scale_inv + zero_point), 0, 15) with
+    the UNSHIFTED zero point of the PTQ checkpoint (zero_point_list[1]), one code per int8."""
+    _check_quant_args(input, scale_inv, zero_point)
+    x = input if _is_dense(input) else input.contiguous()
+    lib = _lib.load()
+    out = torch.empty_like(x, dtype=torch.int8)
+    with _DeviceGuard(x):
+        _launch("quant", lib.mixdq_quant_i8_static_range,
+                (x.data_ptr(), x.numel(), scale_inv.data_ptr(), zero_point.data_ptr(), 0, 15,
+                 out.data_ptr()), x, keep=(x, scale_inv, zero_point, out),
+                algo_bytes=3 * x.numel())
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # A2  qlinear_w8_a8_ohalf
 # ---------------------------------------------------------------------------------------------
@@ -798,41 +840,6 @@ def qlinear_geglu_quantize_dynamic(input_int8, weight_il, weight_scale_il, input
                 (y.data_ptr(), y.numel(), q.data_ptr(), qp.data_ptr(), qp.data_ptr() + 4,
                  ws.data_ptr()), y, keep=(y, q, qp, ws), algo_bytes=3 * y.numel())
     return (q, sc, zp, y) if return_y else (q, sc, zp)
-
-
-def cross_attention_quantize_dynamic(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
-                                     heads: int, return_y: bool = False):
-    """softmax(q k^T / sqrt(64)) v per head (head dim 64, <= 96 context tokens) + dynamic
-    quantisation of the result for attn2.to_out: an attention kernel that also publishes min/max
-    partials, then the single-pass quantiser. q [B,T,C], k / v [B,Lk,C] fp16 with unit inner stride
-    (k / v may be column slices of a wider matrix). Returns (o int8 [B,T,C], scale, zp[, o fp16])."""
-    b, t, c = q.shape
-    lk = k.shape[1]
-    _check(q.dtype == torch.float16 and k.dtype == torch.float16 and v.dtype == torch.float16,
-           "cross_attention_quantize_dynamic expects fp16")
-    _check(c == heads * 64 and lk <= 96 and k.shape == v.shape and k.shape[0] == b and k.shape[2] == c,
-           "cross_attention_quantize_dynamic: head dim 64, <= 96 context tokens")
-    if q.stride(2) != 1:
-        q = q.contiguous()
-    if k.stride(2) != 1:
-        k = k.contiguous()
-    if v.stride(2) != 1:
-        v = v.contiguous()
-    o = torch.empty((b, t, c), dtype=torch.float16, device=q.device)
-    o8 = torch.empty((b, t, c), dtype=torch.int8, device=q.device)
-    qp, sc, zp = _qp_pair(q.device)
-    lib = _lib.load()
-    with _DeviceGuard(q):
-        ws = _dynamic_workspace(q.device)
-        _launch("attn_cross", lib.mixdq_cross_attn_d64_f16,
-                (q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
-                 v.data_ptr(), v.stride(1), v.stride(0), o.data_ptr(), b, t, lk, heads, 0.125,
-                 ws.data_ptr()), q, keep=(q, k, v, o, ws),
-                algo_bytes=2 * (2 * b * t * c + 2 * b * lk * c))
-        _launch("quant_premm", lib.mixdq_quant_i8_premm,
-                (o.data_ptr(), o.numel(), o8.data_ptr(), qp.data_ptr(), qp.data_ptr() + 4,
-                 ws.data_ptr()), o, keep=(o, o8, qp, ws), algo_bytes=3 * o.numel())
-    return (o8, sc, zp, o) if return_y else (o8, sc, zp)
 
 
 def groupnorm_quantize_dynamic(x: torch.Tensor, num_groups: int, weight: torch.Tensor,

@@ -146,8 +146,8 @@ def test_cluster_and_grid_quantisers_agree(ops, dev):
 
 
 def test_two_pass_and_single_kernel_quantisers_agree(ops, dev):
-    """lean one-kernel form == min/max pass + quantise pass (csrc/quant2.cu) == the first-generation
-    single-kernel quantisers, bit for bit, for plain / row-pitched / LayerNorm / GroupNorm inputs."""
+    """min/max pass + quantise pass (csrc/quant2.cu) == the first-generation single-kernel
+    quantisers, bit for bit, for plain / row-pitched / LayerNorm / GroupNorm inputs."""
     from mixdq_b200 import _lib
     lib = _lib.load()
     g = torch.Generator().manual_seed(11)
@@ -159,7 +159,7 @@ def test_two_pass_and_single_kernel_quantisers_agree(ops, dev):
         memory_format=torch.channels_last)
     outs = []
     try:
-        for mode in (0, 1, 2, 3, 0, 3, 2, 1):
+        for mode in (0, 1, 0, 1):
             lib.mixdq_debug_set_two_pass(mode)
             ops.clear_dynamic_quant_cache()
             o = list(ops.layernorm_quantize_dynamic(x, w, b, 1e-5, return_y=True))
@@ -176,37 +176,6 @@ def test_two_pass_and_single_kernel_quantisers_agree(ops, dev):
     for o in outs[1:]:
         for a_, b_ in zip(o, outs[0]):
             assert torch.equal(a_, b_)
-
-
-@pytest.mark.parametrize("B,T,Lk,H,sliced", [(1, 256, 77, 20, True), (1, 1024, 77, 10, True),
-                                             (2, 300, 77, 5, False), (1, 7, 1, 1, False),
-                                             (1, 4096, 96, 5, True), (8, 1024, 77, 10, True)])
-def test_cross_attention_quant(ops, dev, B, T, Lk, H, sliced):
-    """csrc/attn.cu: softmax(q k^T / 8) v per 64-dim head + the single-pass quantiser fed by its
-    min/max partials. The attention output is a floating-point restatement of SDPA (fp32 scores
-    and accumulation, one rounding): |diff| <= 2e-3 of the output range; the quantisation of the
-    kernel's own fp16 output is bit-exact against the oracle."""
-    import torch.nn.functional as F
-    g = torch.Generator().manual_seed(B * 1000 + T + Lk + H)
-    C = H * 64
-    q = (torch.randn(B, T, C, generator=g) * 1.2).half().to(dev)
-    if sliced:      # K / V as column slices of a wider matrix (the hoisted to_k / to_v GEMM output)
-        wide = (torch.randn(B, Lk, 3 * C + 64, generator=g)).half().to(dev)
-        k, v = wide[..., 64:64 + C], wide[..., 64 + C:64 + 2 * C]
-    else:
-        k = torch.randn(B, Lk, C, generator=g).half().to(dev)
-        v = torch.randn(B, Lk, C, generator=g).half().to(dev)
-    o8, s, z, o = ops.cross_attention_quantize_dynamic(q, k, v, H, return_y=True)
-
-    def heads(t):
-        b, n, c = t.shape
-        return t.reshape(b, n, H, 64).transpose(1, 2).float()
-    ref = F.scaled_dot_product_attention(heads(q), heads(k), heads(v)).transpose(1, 2).reshape(B, T, C)
-    err = (o.float() - ref).abs().max().item()
-    assert err <= 2e-3 * max(ref.abs().max().item(), 1.0), err
-    qr, sr, zr = O.quantize_dynamic_kernel(o.cpu())
-    assert torch.equal(s.cpu(), sr) and torch.equal(z.cpu(), zr)
-    assert torch.equal(o8.cpu(), qr)
 
 
 @pytest.mark.parametrize("N,C,H,W,G,silu", [

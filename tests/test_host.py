@@ -90,9 +90,15 @@ def test_fp_fallback_gates(ref):
     assert set(q.state_dict()) == {"weight", "bias"}
     x = torch.randn(3, 32)
     assert torch.equal(q(x), torch.nn.functional.linear(x, fm.weight, fm.bias))
-    # 4-bit activations are not accelerated (reference nn/Linear.py:28-36)
+    # 4-bit activations (N3): the reference gates them to fp16 (nn/Linear.py:28-36); here they
+    # run on the int8 kernels with codes 0..15 and the UNSHIFTED 4-bit zero point of the ckpt
     q = QuantizedLinear.from_float(_prep(fm, name, a_dtype=torch.quint4x2, a_bit=4), ckpt=ck)
-    assert not q.valid_for_acceleration
+    assert q.valid_for_acceleration and q.a_bits == 4 and q._get_name() == "QuantizedLinearW8A4"
+    zl = ck[name + ".act_quantizer"]["zero_point_list"]
+    dl = ck[name + ".act_quantizer"]["delta_list"]
+    assert float(q.act_zero_points) == float(zl[1]) and 0 <= float(q.act_zero_points) <= 15
+    assert float(q.act_scales) == float(dl[1])
+    assert torch.equal(q.bias0, q.weight_sum_by_input_channels * q.act_zero_points)
     # misaligned features -> warning + fallback (nn/Linear.py:37-43)
     odd = nn.Linear(30, 1280)
     q = QuantizedLinear.from_float(_prep(odd, name), ckpt=ck)
