@@ -87,6 +87,20 @@ static bool make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64
   uint32_t box[2] = {BLOCK_K, box_rows};
   return make_tmap(m, base, 2, dims, strides, box);
 }
+// fp16 output matrix [rows][cols] (row pitch ld halves) for the TMA-store epilogue of the
+// persistent kernel: 16-column x 32-row boxes in the SWIZZLE_32B shared-memory layout
+static bool make_tmap_out(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows,
+                          uint64_t ld) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {16, 32};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 // packed 4-bit weights [rows][k/2 bytes]: 64-byte (one k-block) wide boxes, no swizzle — the
 // converter warps read the tile linearly and write the swizzled int8 layout themselves
 static bool make_tmap_2d_w4(CUtensorMap* m, const void* base, uint64_t k, uint64_t rows,
@@ -351,8 +365,11 @@ static int gemm_common(const int8_t* A, int64_t lda, const int8_t* W, const floa
   p.residual = reinterpret_cast<const __half*>(residual); p.ldr = ldr;
   if (pbn) {
     p.tiles_m = m_tiles; p.tiles_n = (N + pbn - 1) / pbn;
+    CUtensorMap tmD;
+    if (!make_tmap_out(&tmD, D, N, M, ldd)) return MIXDQ_ERR_CUDA;
+    p.d_tma = 1; p.d_cols = N;
     g_last_path = w4 ? "tcgen05-w4-persist" : "tcgen05-persist";
-    return persist_launch(KIND_GEMM, pbn, w4, pcs, tmA, tmW, p, st);
+    return persist_launch(KIND_GEMM, pbn, w4, pcs, tmA, tmW, tmD, p, st);
   }
   dim3 grid(m_tiles, (N + bn - 1) / bn, splits);
   if (w4) {
@@ -445,8 +462,11 @@ static int geglu_common(const int8_t* A, int64_t lda, const int8_t* W_il,
     long clusters = sms / pcs;
     if (groups < clusters) clusters = groups;
     partial_count_slot(ws) = static_cast<int>(clusters * pcs);
+    CUtensorMap tmD;
+    if (!make_tmap_out(&tmD, Y, N2 / 2, M, ldy)) return MIXDQ_ERR_CUDA;
+    p.d_tma = 1; p.d_cols = N2 / 2;
     g_last_path = w4 ? "tcgen05-w4-geglu-persist" : "tcgen05-geglu-persist";
-    return persist_launch(KIND_GEGLU, pbn, w4, pcs, tmA, tmW, p, static_cast<cudaStream_t>(stream));
+    return persist_launch(KIND_GEGLU, pbn, w4, pcs, tmA, tmW, tmD, p, static_cast<cudaStream_t>(stream));
   }
   dim3 grid(m_tiles, (N2 + bn - 1) / bn, 1);
   if (static_cast<int64_t>(grid.x) * grid.y > kMaxPartials) return MIXDQ_ERR_UNSUPPORTED;
@@ -626,8 +646,15 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
   p.residual = reinterpret_cast<const __half*>(residual); p.ldr = K;
   if (pbn) {
     p.tiles_m = m_tiles; p.tiles_n = (K + pbn - 1) / pbn;
+    // TMA-store epilogue: the 128 rows of every tile must be 128 CONTIGUOUS output pixels
+    // (whole output rows, no ragged tile inside an image); else the staged copy-out
+    const bool rows_contig = (boxW == Q) && (boxW * boxH * boxN == BLOCK_M) &&
+                             (boxN > 1 ? (boxH == P) : (P % boxH == 0));
+    CUtensorMap tmD;
+    if (!make_tmap_out(&tmD, y, K, static_cast<uint64_t>(N) * P * Q, K)) return MIXDQ_ERR_CUDA;
+    p.d_tma = rows_contig ? 1 : 0; p.d_cols = K;
     g_last_path = w4 ? "tcgen05-w4-persist" : "tcgen05-persist";
-    return persist_launch(KIND_CONV, pbn, w4, pcs, tmA, tmW, p, st);
+    return persist_launch(KIND_CONV, pbn, w4, pcs, tmA, tmW, tmD, p, st);
   }
   dim3 grid(m_tiles, (K + bn - 1) / bn, splits);
   if (w4) {

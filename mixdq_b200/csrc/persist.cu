@@ -32,26 +32,38 @@ static int num_sms() {
   return n;
 }
 
-// Cost model (cycles per tile): 4 tcgen05.mma per k-block at 64 / 80 / 126 cycles for
-// N = 128 / 160 / 256 (tools/mma_bench: the tensor pipe's own rate) + ~600 cycles per tile that the
-// three pipelines do not hide; tiles are dealt round-robin to one CTA per SM.
+// When, and with which tile width. Fitted to tools/tune_persist.py (every SDXL layer shape at
+// batch 1 and 8, one-tile-per-CTA kernel vs the persistent kernel at each width, B200):
+//   * the persistent kernel wins once the problem has >= ~120 tiles of 128 x 128 (a wave of work for
+//     every SM); below that the one-tile kernel with its narrow tiles / split-K is faster;
+//   * time ~ 2.5 us + rounds x max(k-blocks x t_kb, t_epi) + t_epi, where per k-block a CTA of a
+//     pair is bound by the L2 -> SM fabric (~84 GB/s per SM when all 148 stream: 16 KB of A + its
+//     half of W) rather than by the tensor pipe: t_kb = 0.38 / 0.31 / 0.29 us for 256 / 160 / 128
+//     wide tiles (measured 0.39 us on M=8192 N=K=2560), and the epilogue drains a 128 x 256 tile
+//     in ~2.9 us (1.9 / 1.5 us for 160 / 128);
+//   * 128-wide tiles never win for convolutions.
 int persist_pick_bn(int m_tiles, int N, int num_kb, int kind) {
   read_env();
   if (g_persist_mode == 0) return 0;
   const int sms = num_sms();
+  // (M = 256 problems: the batch-1 GEGLU projection measured 9.9 us persistent vs 9.3 us one-tile
+  // inside the UNet graph although it wins in isolation)
+  if (g_persist_mode == 1 && (m_tiles < 4 || static_cast<long>(m_tiles) * ((N + 127) / 128) < 120))
+    return 0;
   const int cands[3] = {256, 160, 128};
-  const double cyc[3] = {126.0, 80.0, 64.0};
+  const double t_kb[3] = {0.38, 0.31, 0.29};
+  const double t_epi[3] = {2.9, 1.9, 1.5};
   double best = 1e30;
   int best_bn = 0;
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     if (g_persist_bn > 0 && bn != g_persist_bn) continue;
-    if (kind == KIND_GEGLU && bn != 256) continue;          // GEGLU projections: N2 % 256 == 0
-    if (kind == KIND_GEGLU && (N % 256)) continue;
+    if (kind == KIND_GEGLU && (bn == 128 || (N % bn))) continue;   // whole 32-column GEGLU groups
+    if (kind == KIND_CONV && bn == 128 && g_persist_bn == 0) continue;
     const long tiles = static_cast<long>(m_tiles) * ((N + bn - 1) / bn);
     const long rounds = (tiles + sms - 1) / sms;
-    if (g_persist_mode == 1 && (tiles < sms || rounds < 2)) continue;   // a single wave gains nothing
-    const double t = rounds * (num_kb * 4 * cyc[i] + 600.0);
+    const double main = num_kb * t_kb[i];
+    const double t = rounds * (main > t_epi[i] ? main : t_epi[i]) + t_epi[i];
     if (t < best) { best = t; best_bn = bn; }
   }
   return best_bn;
@@ -71,7 +83,8 @@ int persist_cluster_size(int m_tiles) {
 }
 
 template <int BN, int STAGES, int KIND, bool W4, int CS>
-static int launch(const CUtensorMap& a, const CUtensorMap& w, const TcParams& p, cudaStream_t st) {
+static int launch(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& d, const TcParams& p,
+                  cudaStream_t st) {
   using L = TpSmem<BN, STAGES, KIND, W4, CS>;
   auto kern = tc_i8_persist_kernel<BN, STAGES, KIND, W4, CS>;
   static bool attr_set = false;
@@ -99,28 +112,27 @@ static int launch(const CUtensorMap& a, const CUtensorMap& w, const TcParams& p,
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  return cudaLaunchKernelEx(&cfg, kern, a, w, p) == cudaSuccess ? MIXDQ_OK : MIXDQ_ERR_CUDA;
+  return cudaLaunchKernelEx(&cfg, kern, a, w, d, p) == cudaSuccess ? MIXDQ_OK : MIXDQ_ERR_CUDA;
 }
 
 // ring depth: what fits 227 KB next to the staging tiles and the per-column operands. A CTA of a
 // pair (CS = 2) stages only half of the W rows, so its ring is 1.3-1.5x deeper.
 template <int BN, int KIND, int CS>
 struct TpStages {
+  static constexpr bool CONV = KIND == KIND_CONV;          // + the 16-class border table
   static constexpr int value =
-      CS == 1 ? (BN == 256 ? (KIND == KIND_CONV ? 3 : 4) : BN == 160 ? 5 : 6)
-              : (BN == 256 ? (KIND == KIND_CONV ? 5 : 6) : BN == 160 ? 7 : 8);
+      CS == 1 ? (BN == 256 ? 3 : BN == 160 ? (CONV ? 4 : 5) : (CONV ? 5 : 6))
+              : (BN == 256 ? 5 : BN == 160 ? 6 : 7);
 };
 
 template <int KIND, bool W4, int CS>
-static int by_bn(int bn, const CUtensorMap& a, const CUtensorMap& w, const TcParams& p,
-                 cudaStream_t st) {
+static int by_bn(int bn, const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& d,
+                 const TcParams& p, cudaStream_t st) {
   switch (bn) {
-    case 256: return launch<256, TpStages<256, KIND, CS>::value, KIND, W4, CS>(a, w, p, st);
-    case 160: if constexpr (KIND != KIND_GEGLU)
-                return launch<160, TpStages<160, KIND, CS>::value, KIND, W4, CS>(a, w, p, st);
-              return MIXDQ_ERR_UNSUPPORTED;
+    case 256: return launch<256, TpStages<256, KIND, CS>::value, KIND, W4, CS>(a, w, d, p, st);
+    case 160: return launch<160, TpStages<160, KIND, CS>::value, KIND, W4, CS>(a, w, d, p, st);
     case 128: if constexpr (KIND != KIND_GEGLU)
-                return launch<128, TpStages<128, KIND, CS>::value, KIND, W4, CS>(a, w, p, st);
+                return launch<128, TpStages<128, KIND, CS>::value, KIND, W4, CS>(a, w, d, p, st);
               return MIXDQ_ERR_UNSUPPORTED;
     default: return MIXDQ_ERR_UNSUPPORTED;
   }
@@ -128,17 +140,17 @@ static int by_bn(int bn, const CUtensorMap& a, const CUtensorMap& w, const TcPar
 
 template <int KIND>
 static int by_flags(int bn, bool w4, int cs, const CUtensorMap& a, const CUtensorMap& w,
-                    const TcParams& p, cudaStream_t st) {
-  if (w4) return cs == 2 ? by_bn<KIND, true, 2>(bn, a, w, p, st) : by_bn<KIND, true, 1>(bn, a, w, p, st);
-  return cs == 2 ? by_bn<KIND, false, 2>(bn, a, w, p, st) : by_bn<KIND, false, 1>(bn, a, w, p, st);
+                    const CUtensorMap& d, const TcParams& p, cudaStream_t st) {
+  if (w4) return cs == 2 ? by_bn<KIND, true, 2>(bn, a, w, d, p, st) : by_bn<KIND, true, 1>(bn, a, w, d, p, st);
+  return cs == 2 ? by_bn<KIND, false, 2>(bn, a, w, d, p, st) : by_bn<KIND, false, 1>(bn, a, w, d, p, st);
 }
 
 int persist_launch(int kind, int bn, bool w4, int cs, const CUtensorMap& tmA,
-                   const CUtensorMap& tmW, TcParams p, cudaStream_t st) {
+                   const CUtensorMap& tmW, const CUtensorMap& tmD, TcParams p, cudaStream_t st) {
   switch (kind) {
-    case KIND_GEMM: return by_flags<KIND_GEMM>(bn, w4, cs, tmA, tmW, p, st);
-    case KIND_CONV: return by_flags<KIND_CONV>(bn, w4, cs, tmA, tmW, p, st);
-    case KIND_GEGLU: return by_flags<KIND_GEGLU>(bn, w4, cs, tmA, tmW, p, st);
+    case KIND_GEMM: return by_flags<KIND_GEMM>(bn, w4, cs, tmA, tmW, tmD, p, st);
+    case KIND_CONV: return by_flags<KIND_CONV>(bn, w4, cs, tmA, tmW, tmD, p, st);
+    case KIND_GEGLU: return by_flags<KIND_GEGLU>(bn, w4, cs, tmA, tmW, tmD, p, st);
     default: return MIXDQ_ERR_UNSUPPORTED;
   }
 }

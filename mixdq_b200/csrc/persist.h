@@ -16,8 +16,10 @@ void persist_set_mode(int mode, int cs);
 void persist_force_bn(int bn);
 // cluster size along M (1 or 2) for the chosen configuration
 int persist_cluster_size(int m_tiles);
-// tmW must have been encoded with box rows = bn / cs. Returns 0 or a negative MIXDQ_ERR_* code.
+// tmW must have been encoded with box rows = bn / cs; tmD (used when p.d_tma != 0) is the fp16
+// output as a 2-D tensor {columns, rows} with 16 x 32 boxes, SWIZZLE_32B. Returns 0 or a negative
+// MIXDQ_ERR_* code.
 int persist_launch(int kind, int bn, bool w4, int cs, const CUtensorMap& tmA,
-                   const CUtensorMap& tmW, TcParams p, cudaStream_t st);
+                   const CUtensorMap& tmW, const CUtensorMap& tmD, TcParams p, cudaStream_t st);
 
 }  // namespace mixdq

@@ -32,34 +32,45 @@ __device__ __noinline__ float exact_round_quot(float x, float delta) {
   return rintf(__fdiv_rn(x, delta));
 }
 
-// 8 halves -> 8 codes, compact: fast reciprocal path for all, exact fix-up only when any element
-// of the vector sits within 1e-4 of a rounding boundary (see qdiff_round_quot in quant_ws.cuh;
-// 1e-4 > the 5e-5 error bound, and keeps the out-of-line path to ~5 % of the warps)
+// two saturated s8 from two s32, merged above the low half of c: d = (c << 16) | (sat8(a) << 8) | sat8(b)
+__device__ __forceinline__ uint32_t pack_sat_s8(int a, int b, uint32_t c) {
+  uint32_t d;
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// 8 halves -> 8 codes, ~8 instructions per element (it was 21: FRND / F2I / clamp / shift / mask per
+// element made the quantise pass issue-bound at batch 8, ncu: 250 warp instructions per vector):
+//   t = x * (1/delta); r = rint(t) by the 1.5 * 2^23 trick (two FADDs, exact for |t| < 2^22; here
+//   |t| <= 255 by construction of delta); the exact division only when some element of the vector
+//   sits within 1e-4 of a rounding boundary (see qdiff_round_quot in quant_ws.cuh; ~6 % of the
+//   warps); code - shift = clamp(r + (z - shift), lo, hi) where for 8 bit [lo, hi] = [-128, 127] is
+//   exactly the s8 saturation of cvt.pack (r + z - shift is an integer, exact in fp32).
 __device__ __forceinline__ uint2 quant8_compact(const int4& raw, float delta, float inv, float z,
                                                 float qmax = 255.0f, int shift = 128) {
   const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+  constexpr float kMagic = 12582912.0f;    // 1.5 * 2^23
   float x[8], r[8];
-  unsigned int near = 0u;                  // bit i: element i needs the exact quotient
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float2 f = __half22float2(h2[i]);
     x[2 * i] = f.x;
     x[2 * i + 1] = f.y;
   }
+  float worst = 0.0f;                      // max |t - rint(t)| over the vector
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float t = __fmul_rn(x[i], inv);
-    r[i] = rintf(t);
-    near |= (fabsf(__fsub_rn(t, r[i])) > 0.4999f ? 1u : 0u) << i;   // |t - x/delta| < 5e-5
+    r[i] = __fsub_rn(__fadd_rn(t, kMagic), kMagic);
+    worst = fmaxf(worst, fabsf(__fsub_rn(t, r[i])));
   }
-  if (near != 0u) {
+  if (worst > 0.4999f) {                   // |t - x/delta| < 5e-5: some element needs the quotient
     // the arrays are ROTATED so that the loop body only touches element 0 (static register
     // indexing, one call site); only flagged elements pay for the division
 #pragma unroll 1
     for (int i = 0; i < 8; ++i) {
       float e = r[0];
-      if (near & 1u) e = exact_round_quot(x[0], delta);
-      near >>= 1;
+      if (fabsf(__fsub_rn(__fmul_rn(x[0], inv), e)) > 0.4999f) e = exact_round_quot(x[0], delta);
       const float x0 = x[0];
 #pragma unroll
       for (int j = 0; j < 7; ++j) { x[j] = x[j + 1]; r[j] = r[j + 1]; }
@@ -67,15 +78,20 @@ __device__ __forceinline__ uint2 quant8_compact(const int4& raw, float delta, fl
       r[7] = e;
     }
   }
-  uint32_t w[2] = {0u, 0u};
+  const float zs = __fsub_rn(z, static_cast<float>(shift));     // exact
+  int c[8];
+  if (shift == 128 && qmax == 255.0f) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float c = __fadd_rn(r[i], z);
-    c = fminf(fmaxf(c, 0.0f), qmax);
-    const uint32_t b = static_cast<uint32_t>(static_cast<int>(c) - shift) & 0xffu;
-    w[i >> 2] |= b << (8 * (i & 3));
+    for (int i = 0; i < 8; ++i) c[i] = __float2int_rn(__fadd_rn(r[i], zs));   // saturated by the pack
+  } else {
+    const float lo = -static_cast<float>(shift), hi = qmax - static_cast<float>(shift);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = __float2int_rn(fminf(fmaxf(__fadd_rn(r[i], zs), lo), hi));
   }
-  return make_uint2(w[0], w[1]);
+  uint2 out;
+  out.x = pack_sat_s8(c[1], c[0], pack_sat_s8(c[3], c[2], 0u));
+  out.y = pack_sat_s8(c[5], c[4], pack_sat_s8(c[7], c[6], 0u));
+  return out;
 }
 
 // Touch an address BEFORE the programmatic-dependency wait: the line may still be stale (the
@@ -168,7 +184,7 @@ minmax_rows_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int nchun
 // qmax / shift: code range [0, qmax] stored as code - shift (255 / 128 for 8 bit, 15 / 0 for the
 // 4-bit activation layers).
 template <int U>
-__global__ void __launch_bounds__(kQ2Threads)
+__global__ void __launch_bounds__(kQ2Threads, U > 1 ? 2 : 1)
 quant_rows_premm_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int nchunks,
                         unsigned int items, int8_t* __restrict__ q, DynWs* __restrict__ ws,
                         int nparts, float* __restrict__ scale_out, float* __restrict__ zp_out,
@@ -235,19 +251,13 @@ quant_rows_premm_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int 
       it = nxt;
     }
   } else {
-    // batches of U vectors: the next batch is in flight while this one is converted; the
-    // conversion loop is NOT unrolled (one inlined copy of the quantiser, registers rotated)
+    // batches of U vectors per thread, all U loads in flight together; two CTAs per SM (64
+    // registers) overlap one CTA's conversion with the other's loads. The conversion loop is NOT
+    // unrolled (one inlined copy of the quantiser, registers rotated).
     const unsigned long long step = static_cast<unsigned long long>(U) * stride;
     unsigned long long base = it;
 #pragma unroll 1
     while (base < items) {
-      int4 nx[U];
-      const unsigned long long nb = base + step;
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const unsigned long long i = nb + static_cast<unsigned long long>(u) * stride;
-        if (i < items) nx[u] = __ldcg(vec_ptr(static_cast<unsigned int>(i)));
-      }
       unsigned long long i = base;
 #pragma unroll 1
       for (int u = 0; u < U; ++u) {
@@ -256,9 +266,12 @@ quant_rows_premm_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int 
         for (int j = 0; j + 1 < U; ++j) v[j] = v[j + 1];
         i += stride;
       }
+      base += step;
 #pragma unroll
-      for (int u = 0; u < U; ++u) v[u] = nx[u];
-      base = nb;
+      for (int u = 0; u < U; ++u) {
+        const unsigned long long k = base + static_cast<unsigned long long>(u) * stride;
+        if (k < items) v[u] = __ldcg(vec_ptr(static_cast<unsigned int>(k)));
+      }
     }
   }
   dbg.stamp(3);
@@ -391,19 +404,19 @@ using namespace mixdq;
 static const int64_t kMaxItems = (1ll << 31) - 1;
 
 
-// pass 2 launch. One vector per thread while the whole tensor fits ONE wave of the 2 resident
-// 512-thread CTAs per SM; beyond that, four vectors in flight per thread on one CTA per SM (78
-// registers): every extra wave of the one-vector form pays the whole dependent chain again
-// (partials -> CTA reduction -> first load, ~2 us; measured at batch 8: 3 waves = 7.7 us for a
-// 2.6 M-element tensor).
+// pass 2 launch. One vector per thread while the tensor fits ~2.5 waves of the 2 resident
+// 512-thread CTAs per SM (every batch-1 tensor); beyond that, four vectors in flight per thread on
+// a resident grid of 2 CTAs per SM: every extra wave of the one-vector form pays the whole
+// dependent chain again (partials -> CTA reduction -> first load, ~2 us; measured at batch 8: 3
+// waves = 7.7 us for a 2.6 M-element tensor).
 static int launch_pass2(const __half* x, int64_t ldx, unsigned int nchunks, unsigned int n,
                         int8_t* q, void* ws, int nparts, float* scale_out, float* zp_out,
                         unsigned long long* zero_words, int zero_n, int n_bits, cudaStream_t st) {
   const float qmax = n_bits == 4 ? 15.0f : 255.0f;
   const int shift = n_bits == 4 ? 0 : 128;
   cudaError_t e;
-  if (n > 148u * 2u * kQ2Threads) {
-    const int g2 = grid_for2(n, kQ2Threads * 4, 148);
+  if (n > 148u * 5u * kQ2Threads / 2u) {               // > 2.5 waves of the one-vector form
+    const int g2 = grid_for2(n, kQ2Threads * 4, 148 * 2);
     e = launch_pdl(quant_rows_premm_kernel<4>, g2, kQ2Threads, 0, st, x, ldx, nchunks, n, q,
                    static_cast<DynWs*>(ws), nparts, scale_out, zp_out, zero_words, zero_n, qmax,
                    shift);

@@ -76,6 +76,8 @@ struct TcParams {
   int boxW, boxH, boxN; // pixels covered by one A box: boxN x boxH x boxW (<= 128 rows)
   int tilesQ, tilesP;   // tiles along q and p (tiles along n = gridDim.x / (tilesQ*tilesP))
   int tiles_m, tiles_n; // persistent kernel (tc_persist.cuh): tile grid walked by each CTA
+  int d_tma;            // persistent kernel: 1 = outputs leave through TMA stores (tmD)
+  int d_cols;           // persistent kernel: columns of the output matrix (N, or N / 2 for GEGLU)
   uint32_t a_tx_bytes;  // bytes one A box delivers
   int has_table;        // 1: pad > 0 -> border table from wsum_krs * zp ; 0: per-channel bias0
   // epilogue operands

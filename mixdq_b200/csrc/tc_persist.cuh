@@ -37,8 +37,14 @@
 
 namespace mixdq {
 
-constexpr int TP_EPI_WARPS = 8;
-constexpr int TP_THREADS = 32 * (2 + TP_EPI_WARPS);        // 320
+// 16 epilogue warps = 4 per TMEM lane quarter (a warp may only read the 32 lanes 32 * (warp % 4)),
+// each draining a quarter of the tile's columns in 16-column chunks. With 8 warps (2 per scheduler)
+// the epilogue's dependent chain (tcgen05.ld -> I2F -> dequant -> staging -> store) issued one
+// instruction per ~4 cycles and took 5.2 us per 128 x 256 tile, more than the tile's MMAs for
+// K <= 2560 (ncu: tensor pipe 22 % active on M=8192 N=5120 K=640, profiles/README.md).
+constexpr int TP_EPI_WARPS = 16;
+constexpr int TP_EPI_PARTS = TP_EPI_WARPS / 4;             // column partitions of a tile
+constexpr int TP_THREADS = 32 * (2 + TP_EPI_WARPS);        // 576
 constexpr int TP_CONV_WARPS = 4;
 constexpr int TP_THREADS_W4 = TP_THREADS + 32 * TP_CONV_WARPS;   // 448
 constexpr int TP_SLOT_COLS = 256;                           // TMEM columns per accumulator slot
@@ -48,9 +54,12 @@ struct TpSmem {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K;
   static constexpr int W_ROWS = BN / CS;                     // W rows staged by this CTA
   static constexpr int W_BYTES = W_ROWS * BLOCK_K;
-  static constexpr int CH = 32;                              // accumulator columns per chunk
-  static constexpr int OUT_PITCH = CH * 2 + 16;              // fp16 staging row (+16 B pad)
-  static constexpr int OUT_WARP = 32 * OUT_PITCH;            // one warp: 32 rows
+  // accumulator columns per chunk (GEGLU: 16 value + 16 gate columns -> 16 outputs)
+  static constexpr int CH = (KIND == KIND_GEGLU) ? 32 : 16;
+  // fp16 staging row: 16 outputs = two 16-byte halves, stored XOR-swizzled by bit 2 of the row so
+  // that both the row-per-lane writes and the two-lanes-per-row reads are bank-conflict free
+  static constexpr int OUT_PITCH = 32;
+  static constexpr int OUT_WARP = 2 * 32 * OUT_PITCH;        // one warp: two tiles of 32 rows
   static constexpr int TAB_PITCH = BN + 4;
   static constexpr int TAB_FLOATS = (KIND == KIND_CONV) ? 16 * TAB_PITCH : 0;
   static constexpr int PARAM_FLOATS = 3 * BN + TAB_FLOATS;
@@ -134,17 +143,55 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
                : "memory");
 }
+// explicit shared-memory accesses (generic ld/st through a char* pays the generic-address path)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w) : "memory");
+}
+// TMA store of one box from shared memory (tile mode, clipped at the tensor bounds) as a bulk
+// async-group; wait_group.read<N>: at most N groups may still be READING shared memory
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// profiling stamps (p.dbg != nullptr): 16 slots of %globaltimer per CTA, steady-state tile 2 / 3
+#define TP_DBG(cond, slot)                                                        \
+  do {                                                                            \
+    if (p.dbg != nullptr && (cond)) p.dbg[blockIdx.x * 16 + (slot)] = gtime_ns(); \
+  } while (0)
+
 template <int BN, int STAGES, int KIND, bool W4, int CS>
 __global__ void __launch_bounds__(W4 ? TP_THREADS_W4 : TP_THREADS, 1)
 tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                     const TcParams p) {
+                     const __grid_constant__ CUtensorMap tmD, const TcParams p) {
   using L = TpSmem<BN, STAGES, KIND, W4, CS>;
   static_assert(KIND == KIND_GEMM || KIND == KIND_CONV || KIND == KIND_GEGLU, "unsupported kind");
-  static_assert(BN % 32 == 0 && BN >= 64 && BN <= TP_SLOT_COLS, "tile width (every epilogue warp owns >= 1 chunk)");
+  static_assert(BN % 32 == 0 && BN / L::CH >= TP_EPI_PARTS && BN <= TP_SLOT_COLS,
+                "tile width (every epilogue warp owns >= 1 chunk)");
   static_assert(CS == 1 || CS == 2, "cluster size along M");
   static_assert(CS == 1 || BN % 32 == 0, "W halves");
   constexpr bool PAIR = CS == 2;
@@ -172,12 +219,21 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int lane = threadIdx.x & 31;
   pdl_launch_dependents();
 
-  // ---- tile schedule: groups of CS vertically adjacent tiles, m fastest, strided over clusters
+  // ---- tile schedule: groups of CS vertically adjacent tiles, m fastest; every cluster takes a
+  //      CONTIGUOUS range of groups, so that consecutive tiles of a CTA share their n-tile and the
+  //      per-column epilogue operands (two named barriers + dependent L2 loads, ~1.5 us that no
+  //      pipeline hides) are reloaded once or twice per CTA instead of once per tile
   const int crank = (CS > 1) ? static_cast<int>(cluster_ctarank()) : 0;
   const int cid = blockIdx.x / CS;
   const int nclusters = gridDim.x / CS;
+  int g_begin, g_end;
   const int m_groups = (p.tiles_m + CS - 1) / CS;
   const int total_groups = m_groups * p.tiles_n;
+  {
+    const int base = total_groups / nclusters, rem = total_groups - base * nclusters;
+    g_begin = cid * base + (cid < rem ? cid : rem);
+    g_end = g_begin + base + (cid < rem ? 1 : 0);
+  }
   const int num_kb = p.num_kb;
   const bool leader = crank == 0;
   // the leader's barriers as shared::cluster addresses (identity for the leader itself)
@@ -204,6 +260,7 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
+    if (p.d_tma) tma_prefetch_desc(&tmD);
     for (int i = 0; i < STAGES; ++i) {
       // full: the producer's expect_tx arrival (+ the converter warps of BOTH CTAs for W4); in
       // pair mode only the leader's full barriers are used
@@ -272,8 +329,8 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int pre = 0;
     // profiling only (results are garbage): bit1 = no TMA loads, bit0 = no MMA issue
     const bool skip_tma = !W4 && (p.dbg_mode & 2) != 0;
-    if (cid < total_groups && !skip_tma) {
-      const Tile t0 = tile_of(cid);
+    if (g_begin < g_end && !skip_tma) {
+      const Tile t0 = tile_of(g_begin);
       pre = num_kb < STAGES ? num_kb : STAGES;
       if (elect_one()) {
         for (int i = 0; i < pre; ++i) {
@@ -285,11 +342,11 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       __syncwarp();
     }
     pdl_wait();
-    for (int g = cid; g < total_groups; g += nclusters) {
+    for (int g = g_begin; g < g_end; ++g) {
       const Tile t = tile_of(g);
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int stage = it % STAGES;
-        const bool early_w = (g == cid) && (kb < pre);   // W already in flight
+        const bool early_w = (g == g_begin) && (kb < pre);   // W already in flight
         if (it >= static_cast<uint32_t>(STAGES)) mbar_wait(&empty_bar[stage], ((it / STAGES) & 1u) ^ 1u);
         if (elect_one()) {
           if (skip_tma) {
@@ -314,14 +371,16 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
     const uint64_t w_desc0 = umma_desc_sw128(smem_u32(sW));
     uint32_t it = 0, tl = 0;
-    for (int g = cid; g < total_groups; g += nclusters, ++tl) {
+    for (int g = g_begin; g < g_end; ++g, ++tl) {
       const uint32_t slot = tl & 1u;
       if (tl >= 2) mbar_wait(&tmem_empty[slot], ((tl >> 1) & 1u) ^ 1u);   // epilogue drained it
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + slot * TP_SLOT_COLS;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int stage = it % STAGES;
+        TP_DBG(lane == 0 && kb == 0 && (tl == 2 || tl == 3), tl == 2 ? 7 : 9);   // tile's first wait
         mbar_wait(&full_bar[stage], (it / STAGES) & 1u);
+        TP_DBG(lane == 0 && kb == 0 && tl == 2, 10);                             // first stage landed
         tc_fence_after();
         if (elect_one()) {
           const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(stage * (L::A_BYTES >> 4));
@@ -344,25 +403,36 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
         }
         __syncwarp();
+        TP_DBG(lane == 0 && kb == num_kb - 1 && tl == 2, 8);                     // last MMA issued
       }
     }
     }
   } else if (warp < 2 + TP_EPI_WARPS) {
     // ===================== epilogue warps =====================
+    // Each warp drains 32 tile rows (lane == row) x its quarter of the columns in 16-output chunks:
+    // tcgen05.ld -> dequant (+ the fused elementwise tails, applied in the same row-per-lane
+    // layout: 32 B = one sector per row and tail) -> fp16 -> a 1 KB staging tile in the layout of a
+    // SWIZZLE_32B TMA box -> ONE cp.async.bulk.tensor store per chunk issued by lane 0 (the TMA
+    // unit clips at the tensor edges, so no per-row / per-column predicates and no address
+    // arithmetic remain in the warps). Two staging tiles per warp: the store of chunk c drains
+    // while chunk c + 1 is computed. p.d_tma == 0 (output rows of a tile not contiguous: conv
+    // geometries with ragged tiles): staged copy-out with 16-byte stores instead.
     pdl_wait();                            // dynamic-quantisation scalars come from the predecessor
     const int ew = warp - 2;
-    const int et = threadIdx.x - 64;       // 0..255
+    const int et = threadIdx.x - 64;       // 0..511
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int ehalf = ew >> 2;             // which half of the tile's columns
+    const int epart = ew >> 2;             // which quarter of the tile's columns
     const bool has_bias = p.bias != nullptr;
-    uint8_t* stage_out = smem + L::OFF_OUT + ew * L::OUT_WARP;   // warp-private staging
+    const uint32_t stage_u32 = smem_u32(smem + L::OFF_OUT + ew * L::OUT_WARP);   // 2 x 1 KB
+    const uint32_t s_scale_u32 = smem_u32(s_scale), s_bias0_u32 = smem_u32(s_bias0),
+                   s_bias_u32 = smem_u32(s_bias), s_table_u32 = smem_u32(s_table);
     const int row = quarter * 32 + lane;
-    constexpr int LPR = CH / 8;            // lanes (16-byte chunks) per row of a chunk
-    constexpr int RPI = 32 / LPR;          // rows per copy-out instruction
+    const int sw = (lane >> 2) & 1;        // SWIZZLE_32B: 16-byte half ^= bit 7 of the address
+    const bool d_tma = p.d_tma != 0;
     int cur_n = -1;
     float mn = 0.f, mx = 0.f;              // GEGLU: running min / max of this CTA's outputs
-    uint32_t tl = 0;
-    for (int g = cid; g < total_groups; g += nclusters, ++tl) {
+    uint32_t tl = 0, nstore = 0;           // nstore: chunks staged so far (staging tile = parity)
+    for (int g = g_begin; g < g_end; ++g, ++tl) {
       const Tile t = tile_of(g);
       const uint32_t slot = tl & 1u;
       // ---- per-column operands of this n-tile (reloaded only when the n-tile changes) ----
@@ -409,19 +479,29 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         cur_n = t.n_tile0;
       }
       const RowInfo ri = row_info<KIND>(p, row, t.m0, t.tn0, t.tp0, t.tq0);
-      const int c_lo = ehalf ? (NCH + 1) / 2 : 0;
-      const int c_hi = ehalf ? NCH : (NCH + 1) / 2;
+      // first output row of this warp's 32-row slab (TMA stores: rows of a tile are contiguous)
+      const RowInfo r0 = row_info<KIND>(p, quarter * 32, t.m0, t.tn0, t.tp0, t.tq0);
+      const int c_lo = (NCH * epart) / TP_EPI_PARTS;
+      const int c_hi = (NCH * (epart + 1)) / TP_EPI_PARTS;
       const uint32_t t_base = tmem_base + slot * TP_SLOT_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
+      // per-row operand pointers of the fused tails
+      const bool has_ca = (KIND != KIND_GEGLU) && p.chan_add != nullptr;
+      const bool has_rs = (KIND != KIND_GEGLU) && p.residual != nullptr;
+      const __half* ca_row = has_ca && ri.ok ? p.chan_add + (ri.out_row / p.rows_per_img) * p.ldca : nullptr;
+      const __half* rs_row = has_rs && ri.ok ? p.residual + ri.out_row * p.ldr : nullptr;
+      const uint32_t b0_u32 = (KIND == KIND_CONV && p.has_table)
+                                  ? s_table_u32 + static_cast<uint32_t>(ri.cls * L::TAB_PITCH) * 4u
+                                  : s_bias0_u32;
 
-      auto dequant8 = [&](int cls, int col, const int32_t* a, __half* h) {
+      // 8 accumulators -> 8 halves: three separately rounded fp32 operations, then RN to fp16
+      auto dequant8 = [&](int col, const int32_t* a, __half* h) {
 #pragma unroll
         for (int j0 = 0; j0 < 8; j0 += 4) {
-          const float4 sc = *reinterpret_cast<const float4*>(s_scale + col + j0);
-          const float* b0src = (KIND == KIND_CONV && p.has_table)
-                                   ? (s_table + cls * L::TAB_PITCH + col + j0) : (s_bias0 + col + j0);
-          const float4 b0 = *reinterpret_cast<const float4*>(b0src);
+          const uint32_t off = static_cast<uint32_t>(col + j0) * 4u;
+          const float4 sc = lds_f4(s_scale_u32 + off);
+          const float4 b0 = lds_f4(b0_u32 + off);
           float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_bias) bs = *reinterpret_cast<const float4*>(s_bias + col + j0);
+          if (has_bias) bs = lds_f4(s_bias_u32 + off);
           const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
           const float b0v[4] = {b0.x, b0.y, b0.z, b0.w};
           const float bsv[4] = {bs.x, bs.y, bs.z, bs.w};
@@ -433,14 +513,47 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
         }
       };
+      // stage 16 halves of this lane's row and send the 32 x 16 tile out
+      auto store_chunk = [&](const __half* y, int out_col) {
+        const uint32_t buf = stage_u32 + (nstore & 1u) * 1024u;
+        if (d_tma) {
+          // the store that last read this staging tile (two chunks ago) must be done reading
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          sts_v4(buf + lane * 32 + (sw << 4), reinterpret_cast<const uint4*>(y)[0]);
+          sts_v4(buf + lane * 32 + ((sw ^ 1) << 4), reinterpret_cast<const uint4*>(y)[1]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmD, buf, out_col, static_cast<int>(r0.out_row));
+            bulk_commit();
+          }
+        } else {
+          __syncwarp();                                // previous copy-out has read this tile
+          if (ri.ok) {
+            sts_v4(buf + lane * 32 + (sw << 4), reinterpret_cast<const uint4*>(y)[0]);
+            sts_v4(buf + lane * 32 + ((sw ^ 1) << 4), reinterpret_cast<const uint4*>(y)[1]);
+          }
+          __syncwarp();
+          // two lanes per row, 16 rows per instruction
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int r = i * 16 + (lane >> 1);
+            const RowInfo ro = row_info<KIND>(p, quarter * 32 + r, t.m0, t.tn0, t.tp0, t.tq0);
+            const int col = out_col + (lane & 1) * 8;
+            if (ro.ok && col + 8 <= p.d_cols)
+              *reinterpret_cast<uint4*>(p.D + ro.out_row * p.ldd + col) =
+                  lds_v4(buf + r * 32 + ((((lane & 1) ^ (r >> 2)) & 1) << 4));
+          }
+        }
+        ++nstore;
+      };
 
+      TP_DBG(threadIdx.x == 64 && tl == 2, 0);       // epilogue of tile 2 starts waiting
       if (KIND == KIND_GEGLU) {
         // 32 accumulator columns = 16 value + 16 gate columns of the same 16 outputs
-        RowInfo ro[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-          ro[i] = row_info<KIND>(p, quarter * 32 + i * 16 + (lane >> 1), t.m0, t.tn0, t.tp0, t.tq0);
         mbar_wait(&tmem_full[slot], (tl >> 1) & 1u);
+        TP_DBG(threadIdx.x == 64 && tl == 2, 1);
         tc_fence_after();
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; ++c) {
@@ -456,68 +569,48 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = static_cast<uint32_t>(static_cast<int32_t>(v[j]) >> 4);
           }
-          const bool cols_ok = t.n_tile0 + c * 32 + 32 <= p.N;
-          if (ri.ok && cols_ok) {
+          __align__(16) __half y[16];
+          {
             __align__(16) __half h[32];
 #pragma unroll
             for (int j8 = 0; j8 < 32; j8 += 8)
-              dequant8(0, c * 32 + j8, reinterpret_cast<const int32_t*>(v) + j8, h + j8);
-            __align__(16) __half y[16];
+              dequant8(c * 32 + j8, reinterpret_cast<const int32_t*>(v) + j8, h + j8);
+            const bool live = ri.ok && (t.n_tile0 + c * 32 + 32 <= p.N);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               y[j] = geglu_half(h[j], h[16 + j]);
-              const float f = __half2float(y[j]);
+              const float f = live ? __half2float(y[j]) : 0.f;
               mn = fminf(mn, f);
               mx = fmaxf(mx, f);
             }
-            uint4* dst = reinterpret_cast<uint4*>(stage_out + lane * L::OUT_PITCH);
-            dst[0] = reinterpret_cast<const uint4*>(y)[0];
-            dst[1] = reinterpret_cast<const uint4*>(y)[1];
           }
-          __syncwarp();
-          if (cols_ok) {
-            const int64_t ocol = ((t.n_tile0 + c * 32) >> 1) + (lane & 1) * 8;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              if (!ro[i].ok) continue;
-              const int r = i * 16 + (lane >> 1);
-              *reinterpret_cast<uint4*>(p.D + ro[i].out_row * p.ldd + ocol) =
-                  *reinterpret_cast<const uint4*>(stage_out + r * L::OUT_PITCH + (lane & 1) * 16);
-            }
-          }
-          __syncwarp();
+          store_chunk(y, (t.n_tile0 + c * 32) >> 1);
         }
       } else {
-        RowInfo ro[LPR];
-        int64_t ca_off[LPR];
-#pragma unroll
-        for (int i = 0; i < LPR; ++i) {
-          ro[i] = row_info<KIND>(p, quarter * 32 + i * RPI + lane / LPR, t.m0, t.tn0, t.tp0, t.tq0);
-          ca_off[i] = (p.chan_add != nullptr && ro[i].ok) ? (ro[i].out_row / p.rows_per_img) * p.ldca : 0;
-        }
-        const bool has_tail = (p.chan_add != nullptr) || (p.residual != nullptr);
-        uint4 t_ca[LPR], t_rs[LPR];
+        // operands of the fused tails, fetched one chunk ahead (the first chunk's while the MMAs
+        // of this tile are still running)
+        uint4 t_ca[2], t_rs[2];
         auto fetch_tail = [&](int c) {
-          const int ccol = t.n_tile0 + c * CH + (lane % LPR) * 8;
-          if (c < c_hi && ccol + 8 <= p.N) {
+          const int col = t.n_tile0 + c * CH;
+          if (c < c_hi) {
 #pragma unroll
-            for (int i = 0; i < LPR; ++i) {
-              if (!ro[i].ok) continue;
-              if (p.chan_add != nullptr)
-                t_ca[i] = __ldcg(reinterpret_cast<const uint4*>(p.chan_add + ca_off[i] + ccol));
-              if (p.residual != nullptr)
-                t_rs[i] = __ldcg(reinterpret_cast<const uint4*>(p.residual + ro[i].out_row * p.ldr + ccol));
+            for (int i = 0; i < 2; ++i) {
+              if (col + i * 8 + 8 > p.N) continue;
+              if (ca_row != nullptr) t_ca[i] = __ldcg(reinterpret_cast<const uint4*>(ca_row + col + i * 8));
+              if (rs_row != nullptr) t_rs[i] = __ldcg(reinterpret_cast<const uint4*>(rs_row + col + i * 8));
             }
           }
         };
-        if (has_tail) fetch_tail(c_lo);
+        if (has_ca || has_rs) fetch_tail(c_lo);
         mbar_wait(&tmem_full[slot], (tl >> 1) & 1u);
+        TP_DBG(threadIdx.x == 64 && tl == 2, 1);       // accumulator ready
         tc_fence_after();
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; ++c) {
-          uint32_t v[CH];
-          tmem_ld_32x32(t_base + c * CH, reinterpret_cast<uint32_t(&)[32]>(v));
+          uint32_t v[16];
+          tmem_ld_32x16(t_base + c * CH, v);
           tmem_ld_wait();
+          TP_DBG(threadIdx.x == 64 && tl == 2 && c == c_lo, 2);   // first chunk in registers
           if (c == c_hi - 1) {                         // this warp has read its part of the slot
             tc_fence_before();
             __syncwarp();
@@ -527,47 +620,39 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
             for (int j = 0; j < CH; ++j) v[j] = static_cast<uint32_t>(static_cast<int32_t>(v[j]) >> 4);
           }
-          if (ri.ok) {
+          if (p.acc_out != nullptr && ri.ok) {         // raw accumulators (parity tests)
 #pragma unroll
-            for (int j8 = 0; j8 < CH; j8 += 8) {
-              const int col = c * CH + j8;
-              if (p.acc_out != nullptr && t.n_tile0 + col + 8 <= p.N) {
-                int32_t* arow = p.acc_out + ri.out_row * p.N + t.n_tile0 + col;
-                *reinterpret_cast<int4*>(arow) = make_int4(v[j8], v[j8 + 1], v[j8 + 2], v[j8 + 3]);
-                *reinterpret_cast<int4*>(arow + 4) = make_int4(v[j8 + 4], v[j8 + 5], v[j8 + 6], v[j8 + 7]);
-              }
-              __align__(16) __half h[8];
-              dequant8(ri.cls, col, reinterpret_cast<const int32_t*>(v) + j8, h);
-              *reinterpret_cast<uint4*>(stage_out + lane * L::OUT_PITCH + j8 * 2) =
-                  *reinterpret_cast<const uint4*>(h);
+            for (int j4 = 0; j4 < CH; j4 += 4) {
+              const int col = t.n_tile0 + c * CH + j4;
+              if (col + 4 <= p.N)
+                *reinterpret_cast<int4*>(p.acc_out + ri.out_row * p.N + col) =
+                    make_int4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
             }
           }
-          __syncwarp();
-          const int ccol = c * CH + (lane % LPR) * 8;
-          uint4 o[LPR];
-          const bool col_ok = t.n_tile0 + ccol + 8 <= p.N;
-          if (col_ok) {
+          __align__(16) __half y[16];
 #pragma unroll
-            for (int i = 0; i < LPR; ++i) {
-              if (!ro[i].ok) continue;
-              const int r = i * RPI + lane / LPR;
-              o[i] = *reinterpret_cast<const uint4*>(stage_out + r * L::OUT_PITCH + (lane % LPR) * 16);
-              if (p.chan_add != nullptr) o[i] = add_half8(o[i], t_ca[i]);
-              if (p.residual != nullptr) o[i] = add_half8(o[i], t_rs[i]);
-            }
-          }
-          if (has_tail) fetch_tail(c + 1);
-          if (col_ok) {
+          for (int j8 = 0; j8 < CH; j8 += 8)
+            dequant8(c * CH + j8, reinterpret_cast<const int32_t*>(v) + j8, y + j8);
+          if (has_ca || has_rs) {
 #pragma unroll
-            for (int i = 0; i < LPR; ++i) {
-              if (!ro[i].ok) continue;
-              *reinterpret_cast<uint4*>(p.D + ro[i].out_row * p.ldd + t.n_tile0 + ccol) = o[i];
+            for (int i = 0; i < 2; ++i) {
+              if (t.n_tile0 + c * CH + i * 8 + 8 > p.N) continue;
+              uint4 o = reinterpret_cast<const uint4*>(y)[i];
+              if (ca_row != nullptr) o = add_half8(o, t_ca[i]);
+              if (rs_row != nullptr) o = add_half8(o, t_rs[i]);
+              reinterpret_cast<uint4*>(y)[i] = o;
             }
+            fetch_tail(c + 1);
           }
-          __syncwarp();                                // staging is reused by the next chunk
+          TP_DBG(threadIdx.x == 64 && tl == 2 && c == c_lo, 3);   // first chunk dequantised
+          store_chunk(y, t.n_tile0 + c * CH);
+          TP_DBG(threadIdx.x == 64 && tl == 2 && c == c_lo, 4);   // first chunk staged / sent
         }
       }
+      TP_DBG(threadIdx.x == 64 && (tl == 2 || tl == 3), tl == 2 ? 5 : 6);   // tile drained
     }
+    if (d_tma && lane == 0) bulk_wait_all();           // every store has completed
+    __syncwarp();
     tc_fence_before();
     if (KIND == KIND_GEGLU) {
       // one min / max partial per CTA (consumed by quant_rows_premm_kernel, quant2.cu)
@@ -593,7 +678,7 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       constexpr int CPS = L::W_ROWS * 4;                           // 16-byte packed chunks per k-block
       constexpr int PT = (CPS + NT - 1) / NT;
       uint32_t it = 0;
-      for (int g = cid; g < total_groups; g += nclusters) {
+      for (int g = g_begin; g < g_end; ++g) {
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int stage = it % STAGES;
           mbar_wait(&raw_full[stage], (it / STAGES) & 1u);
