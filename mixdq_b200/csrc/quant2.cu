@@ -416,7 +416,7 @@ static int launch_pass2(const __half* x, int64_t ldx, unsigned int nchunks, unsi
   const int shift = n_bits == 4 ? 0 : 128;
   cudaError_t e;
   if (n > 148u * 5u * kQ2Threads / 2u) {               // > 2.5 waves of the one-vector form
-    const int g2 = grid_for2(n, kQ2Threads * 4, 148 * 2);
+    const int g2 = 148 * 2;                              // the whole resident grid: balanced SMs
     e = launch_pdl(quant_rows_premm_kernel<4>, g2, kQ2Threads, 0, st, x, ldx, nchunks, n, q,
                    static_cast<DynWs*>(ws), nparts, scale_out, zp_out, zero_words, zero_n, qmax,
                    shift);

@@ -282,3 +282,103 @@ def test_node_mappings_match_reference_workflow():
     import mixdq_extension.op.qlinear as ql
     import mixdq_extension.op.quant as qq
     assert callable(qc.qconv2d) and callable(ql.qlinear) and callable(qq.quantize_per_tensor)
+
+
+def test_quantized_unet_file_round_trip(tmp_path):
+    """N2: the quantised model (int8 / packed-int4 codes, scales, sums, BOS rows, stored layout) is
+    written to disk and rebuilt on a META skeleton without any float weight; every buffer,
+    attribute and the reference-format state_dict survive the round trip."""
+    from mixdq_b200 import serialize
+    from mixdq_b200.unet import UNet2DConditionModel, tiny_config
+    unet, names, args = _tiny_quantized()
+    # mixed precision: a few W4 layers, one 4-bit-activation layer, BOS rows on the K/V layers
+    for i, n in enumerate(names):
+        if "ff.net" in n or "attn1.to_q" in n:
+            args.w_config["model." + n] = 4
+        if n.endswith("attn2.to_out.0"):
+            args.a_config["model." + n] = 4
+    ehs = torch.randn(1, 77, unet.cfg.cross_attention_dim)
+    bos_dict = mixdq.compute_bos_dict(unet, ehs)
+    mixdq.quantize_unet(unet, args, ckpt=None, bos=True, bos_dict=bos_dict)
+    path = tmp_path / "tiny_quantized.pt"
+    info = serialize.save_quantized_unet(unet, path, meta={"model": "tiny", "w": "mixed"})
+    assert info["leaves"] == len(names) and info["quantized_bytes"] > 0
+    with torch.device("meta"):
+        skel = UNet2DConditionModel(tiny_config())
+    loaded = serialize.load_quantized_unet(skel, path, "cpu")
+    a, b = dict(unet.named_modules()), dict(loaded.named_modules())
+    kinds = set()
+    for n in names:
+        assert type(a[n]) is type(b[n]) and a[n]._get_name() == b[n]._get_name(), n
+        kinds.add(a[n]._get_name())
+        assert set(a[n]._buffers) == set(b[n]._buffers), n
+        for k, t in a[n]._buffers.items():
+            if t is not None:
+                assert torch.equal(t, b[n]._buffers[k]) and t.dtype == b[n]._buffers[k].dtype, (n, k)
+        for k in ("dynamic", "a_bits", "w_kind", "w_bits", "split", "bos", "valid_for_acceleration",
+                  "in_features", "out_features", "kernel_size", "stride", "padding"):
+            assert getattr(a[n], k, None) == getattr(b[n], k, None), (n, k)
+    assert {"QuantizedLinearW4A8", "QuantizedLinearW8A4", "QuantizedLinearW8A8",
+            "QuantizedConv2dW8A8"} <= kinds
+    sa, sb = unet.state_dict(), loaded.state_dict()
+    assert set(sa) == set(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+    assert not any(p.is_meta for p in loaded.parameters()) and not any(x.is_meta for x in loaded.buffers())
+    # a file of another format / version is refused
+    with pytest.raises(ValueError):
+        serialize.load_quantized_unet(skel, {"format": "something else"}, "cpu")
+
+
+def test_repo_root_is_a_comfyui_plugin():
+    """repo-root __init__.py re-exports the node mappings like the reference's (__init__.py:1-3)"""
+    import importlib.util
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    spec = importlib.util.spec_from_file_location("mixdq_plugin_root", root / "__init__.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert set(mod.NODE_CLASS_MAPPINGS) == {"Mixdq", "LoadPipe", "OrgGen", "MixdqIntegral"}
+    assert mod.__all__ == ["NODE_CLASS_MAPPINGS", "NODE_DISPLAY_NAME_MAPPINGS"]
+
+
+def test_shipping_config_on_the_sdxl_skeleton():
+    """weight_8.00.yaml + act_8.00.yaml (the ComfyUI node's default, kernels/mixdq.py:560-570) on the
+    SDXL-Turbo skeleton: 794 weight entries of which 4 are 4-bit, 785 activation entries — the 9
+    layers missing from the act config keep fp16 activations and therefore run as FP fallbacks
+    (conv_in, conv_out, down_blocks.0.resnets.0.conv2, up_blocks.2.resnets.2
+    .conv_shortcut and five ff.net.2 layers)."""
+    from mixdq_b200.unet import UNet2DConditionModel, sdxl_turbo_config
+    with torch.device("meta"):
+        unet = UNet2DConditionModel(sdxl_turbo_config())
+    args = SimpleNamespace(w_config="weight/weight_8.00.yaml", a_config="act/act_8.00.yaml")
+    mixdq.register_qconfig_from_input_files(unet, args, bos=False, bos_dict=None)
+    leaves = dict(unet.quantizable_layers())
+    assert len(leaves) == 794
+    w4 = sorted(n for n, m in leaves.items() if m.qconfig.weight().dtype == torch.quint4x2)
+    fp_act = sorted(n for n, m in leaves.items() if m.qconfig.activation().dtype == torch.float16)
+    assert len(w4) == 4 and all(leaves[n].w_bit == 4 for n in w4)
+    assert len(fp_act) == 9 and not any(hasattr(leaves[n], "a_bit") for n in fp_act)
+    expect = {"conv_in", "conv_out", "down_blocks.0.resnets.0.conv2",
+              "up_blocks.2.resnets.2.conv_shortcut",
+              "up_blocks.0.attentions.0.transformer_blocks.0.ff.net.2"}
+    assert expect <= set(fp_act)
+    assert sum(1 for n in fp_act if n.startswith("down_blocks.2.attentions.1.transformer_blocks")
+               and n.endswith("ff.net.2")) == 4
+    # the 9 up-block shortcuts carry their channel split (kernels/quantize.py:61)
+    splits = [leaves[n].split for n in leaves if "up_blocks" in n and n.endswith("conv_shortcut")]
+    assert splits == [1280, 1280, 1280, 1280, 640, 640, 640, 320, 320]
+    # from_float gates: a protected layer becomes an FP fallback, a 4-bit layer W4A8 (checked on
+    # one small layer of each kind, materialised on the CPU)
+    for name, want in ((fp_act[0], "FPFallback"), (w4[0], "W4A8")):
+        src = leaves[name]
+        if isinstance(src, nn.Linear):
+            real = nn.Linear(src.in_features, src.out_features, bias=src.bias is not None).half()
+            qcls = QuantizedLinear
+        else:
+            real = nn.Conv2d(src.in_channels, src.out_channels, src.kernel_size, src.stride,
+                             src.padding, bias=src.bias is not None).half()
+            qcls = QuantizedConv2d
+        for k in ("qconfig", "module_name", "w_bit", "a_bit", "split"):
+            if hasattr(src, k):
+                setattr(real, k, getattr(src, k))
+        q = qcls.from_float(real, split=getattr(src, "split", 0) or 0, ckpt=None)
+        assert q._get_name().endswith(want), (name, q._get_name())
