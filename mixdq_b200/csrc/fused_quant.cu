@@ -679,7 +679,13 @@ extern "C" int mixdq_gn_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int
       return MIXDQ_ERR_CUDA;
     attr = true;
   }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool three_kernels = y_out && mixdq_two_pass_enabled() &&
+                             static_cast<int64_t>(NB) * HW * (C >> 3) < (1ll << 31);
   int cpi = kNumSm / NB;                       // CTAs per image, all co-resident
+  // (three CTAs per SM in the barrier-free form were tried for batch > 1: the apply kernel got 25 %
+  // faster at batch 32 but both kernels got slower inside the batch-8 graph, 1.05 -> 1.38 ms per
+  // step, and the statistics then depend on the row split; kept at one CTA per SM)
   const int max_useful = (HW + 3) / 4;         // >= 4 rows per CTA
   if (cpi > max_useful) cpi = max_useful;
   if (cpi < 1) cpi = 1;
@@ -690,8 +696,7 @@ extern "C" int mixdq_gn_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int
   int smem = static_cast<int>(srows * C * 2);
   const int scratch = kFqWarps * (C / 8) * 16;   // phase-0 partials [warps][chunks] float4
   if (smem < scratch) smem = scratch;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (y_out && mixdq_two_pass_enabled() && static_cast<int64_t>(NB) * HW * (C >> 3) < (1ll << 31)) {
+  if (three_kernels) {
     // statistics kernel -> apply kernel (fp16 y + min/max) -> single-pass quantiser. No CTA waits
     // for another one, so the grids need not be co-resident: the same row split is kept because
     // the statistics kernel's deterministic in-CTA reduction is written for it.

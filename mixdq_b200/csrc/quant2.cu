@@ -39,54 +39,60 @@ __device__ __forceinline__ uint32_t pack_sat_s8(int a, int b, uint32_t c) {
   return d;
 }
 
-// 8 halves -> 8 codes, ~8 instructions per element (it was 21: FRND / F2I / clamp / shift / mask per
-// element made the quantise pass issue-bound at batch 8, ncu: 250 warp instructions per vector):
-//   t = x * (1/delta); r = rint(t) by the 1.5 * 2^23 trick (two FADDs, exact for |t| < 2^22; here
-//   |t| <= 255 by construction of delta); the exact division only when some element of the vector
-//   sits within 1e-4 of a rounding boundary (see qdiff_round_quot in quant_ws.cuh; ~6 % of the
-//   warps); code - shift = clamp(r + (z - shift), lo, hi) where for 8 bit [lo, hi] = [-128, 127] is
-//   exactly the s8 saturation of cvt.pack (r + z - shift is an integer, exact in fp32).
+// 8 halves -> 8 codes in ~7 instructions per element (it was 21: FRND / F2I / clamp / shift / mask
+// per element made the quantise pass issue-bound at batch >= 8, ncu: 250 warp instructions per
+// vector against 126 MB of traffic per launch):
+//   u = fma(x, 1/delta, 1.5 * 2^23)        -> the low mantissa bits of u hold k = rint(x / delta)
+//                                             (exact product, ONE rounding; |x / delta| <= 255)
+//   d = fma(x, 1/delta, -(u - 1.5 * 2^23)) -> distance of the exact product to k
+//   the exact IEEE division only when some |d| of the vector exceeds 0.4999: the reference rounds
+//   the correctly rounded fp32 QUOTIENT (torch.round(x / delta), base_quantizer.py:186), which can
+//   differ from rint(x * (1/delta)) only that close to a rounding boundary (see qdiff_round_quot
+//   in quant_ws.cuh; ~6 % of the warps take the out-of-line path);
+//   code - shift = sat_s8(k + z - shift): integer add on the bit pattern of u, clamped by the
+//   saturating cvt.pack (8 bit: [lo, hi] = [-128, 127] IS the s8 range; 4 bit: explicit min / max).
 __device__ __forceinline__ uint2 quant8_compact(const int4& raw, float delta, float inv, float z,
                                                 float qmax = 255.0f, int shift = 128) {
   const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-  constexpr float kMagic = 12582912.0f;    // 1.5 * 2^23
-  float x[8], r[8];
+  constexpr float kMagic = 12582912.0f;    // 1.5 * 2^23, bit pattern 0x4B400000
+  float x[8];
+  int k[8];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float2 f = __half22float2(h2[i]);
     x[2 * i] = f.x;
     x[2 * i + 1] = f.y;
   }
-  float worst = 0.0f;                      // max |t - rint(t)| over the vector
+  float worst = 0.0f;                      // max |x / delta - rint| over the vector
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float t = __fmul_rn(x[i], inv);
-    r[i] = __fsub_rn(__fadd_rn(t, kMagic), kMagic);
-    worst = fmaxf(worst, fabsf(__fsub_rn(t, r[i])));
+    const float u = __fmaf_rn(x[i], inv, kMagic);
+    k[i] = __float_as_int(u) - 0x4B400000;
+    worst = fmaxf(worst, fabsf(__fmaf_rn(x[i], inv, -__fsub_rn(u, kMagic))));
   }
-  if (worst > 0.4999f) {                   // |t - x/delta| < 5e-5: some element needs the quotient
+  if (worst > 0.4999f) {                   // some element needs the correctly rounded quotient
     // the arrays are ROTATED so that the loop body only touches element 0 (static register
     // indexing, one call site); only flagged elements pay for the division
 #pragma unroll 1
     for (int i = 0; i < 8; ++i) {
-      float e = r[0];
-      if (fabsf(__fsub_rn(__fmul_rn(x[0], inv), e)) > 0.4999f) e = exact_round_quot(x[0], delta);
+      int e = k[0];
+      if (fabsf(__fmaf_rn(x[0], inv, -static_cast<float>(e))) > 0.4999f)
+        e = static_cast<int>(exact_round_quot(x[0], delta));
       const float x0 = x[0];
 #pragma unroll
-      for (int j = 0; j < 7; ++j) { x[j] = x[j + 1]; r[j] = r[j + 1]; }
+      for (int j = 0; j < 7; ++j) { x[j] = x[j + 1]; k[j] = k[j + 1]; }
       x[7] = x0;
-      r[7] = e;
+      k[7] = e;
     }
   }
-  const float zs = __fsub_rn(z, static_cast<float>(shift));     // exact
+  const int zs = static_cast<int>(z) - shift;                   // z is integer-valued
   int c[8];
-  if (shift == 128 && qmax == 255.0f) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) c[i] = __float2int_rn(__fadd_rn(r[i], zs));   // saturated by the pack
-  } else {
-    const float lo = -static_cast<float>(shift), hi = qmax - static_cast<float>(shift);
+  for (int i = 0; i < 8; ++i) c[i] = k[i] + zs;
+  if (!(shift == 128 && qmax == 255.0f)) {
+    const int lo = -shift, hi = static_cast<int>(qmax) - shift;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) c[i] = __float2int_rn(fminf(fmaxf(__fadd_rn(r[i], zs), lo), hi));
+    for (int i = 0; i < 8; ++i) c[i] = min(max(c[i], lo), hi);
   }
   uint2 out;
   out.x = pack_sat_s8(c[1], c[0], pack_sat_s8(c[3], c[2], 0u));
@@ -252,19 +258,15 @@ quant_rows_premm_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int 
     }
   } else {
     // batches of U vectors per thread, all U loads in flight together; two CTAs per SM (64
-    // registers) overlap one CTA's conversion with the other's loads. The conversion loop is NOT
-    // unrolled (one inlined copy of the quantiser, registers rotated).
+    // registers) overlap one CTA's conversion with the other's loads.
     const unsigned long long step = static_cast<unsigned long long>(U) * stride;
     unsigned long long base = it;
 #pragma unroll 1
     while (base < items) {
-      unsigned long long i = base;
-#pragma unroll 1
-      for (int u = 0; u < U; ++u) {
-        if (i < items) qv[i] = quant8_compact(v[0], delta, inv, z, qmax, shift);
 #pragma unroll
-        for (int j = 0; j + 1 < U; ++j) v[j] = v[j + 1];
-        i += stride;
+      for (int u = 0; u < U; ++u) {
+        const unsigned long long i = base + static_cast<unsigned long long>(u) * stride;
+        if (i < items) qv[i] = quant8_compact(v[u], delta, inv, z, qmax, shift);
       }
       base += step;
 #pragma unroll
