@@ -338,6 +338,10 @@ int mixdq_quant_i8_dynamic_bits(const mixdq_half_t* x, int64_t ldx, int64_t M, i
 int mixdq_quant_i8_static_range(const mixdq_half_t* x, int64_t numel, const float* scale_inv,
                                 const float* zp, int lo, int hi, int8_t* q,
                                 mixdq_stream_t stream);
+/* mixdq_ln_quant_i8_dynamic / mixdq_gn_quant_i8_dynamic with q == NULL (y_out required): normalise
+   only — y_out receives the fp16 LayerNorm / GroupNorm[+SiLU] output and nothing is quantised
+   (static-scale callers quantise y_out with mixdq_quant_i8_static and the layer's checkpoint
+   parameters; scale_out / zp_out may then be NULL). */
 int mixdq_ln_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int M, int C,
                               const mixdq_half_t* gamma, const mixdq_half_t* beta, float eps,
                               int8_t* q, mixdq_half_t* y_out, float* scale_out, float* zp_out,

@@ -312,8 +312,14 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = C >> 3;
   const int cpg = C / G;
-  const int n = blockIdx.x / ctas_per_image;
-  const int row0 = (blockIdx.x - n * ctas_per_image) * rows_per_cta;
+  // MODE 1 (statistics kernel of the barrier-free form): the launch covers NB x ctas_per_image
+  // VIRTUAL blocks — every image is cut into the same row ranges whatever the batch is, so its
+  // statistics (fixed-order fp32 partial per block, then order-independent fixed-point
+  // accumulation) do not depend on the other images of the batch — walked by a resident grid.
+  const int vtotal = (MODE == 1) ? NB * ctas_per_image : static_cast<int>(gridDim.x);
+  for (int vb = blockIdx.x; vb < vtotal; vb += gridDim.x) {
+  const int n = vb / ctas_per_image;
+  const int row0 = (vb - n * ctas_per_image) * rows_per_cta;
   const int row1 = min(HW, row0 + rows_per_cta);
   const __half* ximg = x + static_cast<int64_t>(n) * HW * ldx;
 
@@ -373,7 +379,7 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
     const long long fixed = __double2ll_rn(static_cast<double>(t) * (k ? kFixSq : kFixSum));
     atomicAdd(&ws->gsum[(n * G) * 2 + threadIdx.x], static_cast<unsigned long long>(fixed));
   }
-  if (MODE == 1) return;     // statistics kernel: the kernel boundary is the barrier
+  if (MODE == 1) { __syncthreads(); continue; }   // statistics kernel: the kernel boundary is the barrier
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -474,6 +480,7 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
       qrow[c] = qdiff_vec8(y, delta, z);
     }
   }
+  }  // virtual blocks (one iteration except for MODE 1)
 }
 
 template <typename K>
@@ -543,12 +550,20 @@ extern "C" int mixdq_ln_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int
                                          float eps, int8_t* q, mixdq_half_t* y_out,
                                          float* scale_out, float* zp_out, void* ws,
                                          mixdq_stream_t stream) {
-  if (M <= 0 || C <= 0 || !x || !gamma || !beta || !q || !scale_out || !zp_out || !ws || ldx < C)
+  // q == nullptr (with y_out): LayerNorm only, the caller quantises y with static parameters
+  if (M <= 0 || C <= 0 || !x || !gamma || !beta || !ws || ldx < C ||
+      (q ? (!scale_out || !zp_out) : !y_out))
     return MIXDQ_ERR_INVALID_ARG;
-  if ((C & 7) || (ldx & 7) || !al16(x) || !al16(gamma) || !al16(beta) || !al16(q) ||
+  if ((C & 7) || (ldx & 7) || !al16(x) || !al16(gamma) || !al16(beta) || (q && !al16(q)) ||
       (y_out && !al16(y_out)))
     return MIXDQ_ERR_ALIGNMENT;
   if (C > kLnMaxChunks * 256) return MIXDQ_ERR_UNSUPPORTED;
+  if (q == nullptr)
+    return mixdq_q2_ln(reinterpret_cast<const __half*>(x), ldx, M, C,
+                       reinterpret_cast<const __half*>(gamma),
+                       reinterpret_cast<const __half*>(beta), eps, nullptr,
+                       reinterpret_cast<__half*>(y_out), nullptr, nullptr, ws,
+                       static_cast<cudaStream_t>(stream));
   static bool attr = false;
   if (!attr) {
     if (set_smem(ln_quant_kernel<5, false>, kFqMaxSmem) ||
@@ -659,10 +674,11 @@ extern "C" int mixdq_gn_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int
                                          const mixdq_half_t* beta, float eps, int silu, int8_t* q,
                                          mixdq_half_t* y_out, float* scale_out, float* zp_out,
                                          void* ws, mixdq_stream_t stream) {
-  if (NB <= 0 || HW <= 0 || C <= 0 || G <= 0 || !x || !gamma || !beta || !q || !scale_out ||
-      !zp_out || !ws || ldx < C)
+  // q == nullptr (with y_out): normalise only, the caller quantises y with static parameters
+  if (NB <= 0 || HW <= 0 || C <= 0 || G <= 0 || !x || !gamma || !beta || !ws || ldx < C ||
+      (q ? (!scale_out || !zp_out) : !y_out))
     return MIXDQ_ERR_INVALID_ARG;
-  if ((C & 7) || (ldx & 7) || !al16(x) || !al16(gamma) || !al16(beta) || !al16(q) ||
+  if ((C & 7) || (ldx & 7) || !al16(x) || !al16(gamma) || !al16(beta) || (q && !al16(q)) ||
       (y_out && !al16(y_out)))
     return MIXDQ_ERR_ALIGNMENT;
   const int cpg = C / G;
@@ -683,9 +699,6 @@ extern "C" int mixdq_gn_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int
   const bool three_kernels = y_out && mixdq_two_pass_enabled() &&
                              static_cast<int64_t>(NB) * HW * (C >> 3) < (1ll << 31);
   int cpi = kNumSm / NB;                       // CTAs per image, all co-resident
-  // (three CTAs per SM in the barrier-free form were tried for batch > 1: the apply kernel got 25 %
-  // faster at batch 32 but both kernels got slower inside the batch-8 graph, 1.05 -> 1.38 ms per
-  // step, and the statistics then depend on the row split; kept at one CTA per SM)
   const int max_useful = (HW + 3) / 4;         // >= 4 rows per CTA
   if (cpi > max_useful) cpi = max_useful;
   if (cpi < 1) cpi = 1;
@@ -707,15 +720,30 @@ extern "C" int mixdq_gn_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int
     const __half* bh = reinterpret_cast<const __half*>(beta);
     __half* yh = reinterpret_cast<__half*>(y_out);
     DynWs* w = static_cast<DynWs*>(ws);
-    if (launch_pdl(k1, NB * cpi, kFqThreads, scratch, st, xh, ldx, NB, HW, C, G, gh, bh, eps, q, yh,
-                   w, scale_out, zp_out, cpi, rpc, 0) != cudaSuccess)
+    // statistics: every image is cut into the SAME row ranges whatever the batch is (the batch-1
+    // split: one block per SM), walked as virtual blocks by a resident grid — an image's
+    // statistics, hence the whole static-scale UNet, are invariant under batch sharding
+    // (mixdq_b200/dp.py; a per-batch split changed the fp32 partial sums in the last bits)
+    int cpi1 = kNumSm < max_useful ? kNumSm : max_useful;
+    const int rpc1 = (HW + cpi1 - 1) / cpi1;
+    cpi1 = (HW + rpc1 - 1) / rpc1;
+    const int g1 = NB * cpi1 < NB * cpi ? NB * cpi1 : NB * cpi;
+    if (launch_pdl(k1, g1, kFqThreads, scratch, st, xh, ldx, NB, HW, C, G, gh, bh, eps, q, yh,
+                   w, scale_out, zp_out, cpi1, rpc1, 0) != cudaSuccess)
       return MIXDQ_ERR_CUDA;
     if (launch_pdl(k2, NB * cpi, kFqThreads, 0, st, xh, ldx, NB, HW, C, G, gh, bh, eps, q, yh, w,
                    scale_out, zp_out, cpi, rpc, 0) != cudaSuccess)
       return MIXDQ_ERR_CUDA;
+    if (q == nullptr) {
+      // GroupNorm only (static-scale callers): the quantise pass that normally re-zeroes the
+      // statistics accumulators does not run, so clear them here (a memset node under capture)
+      return cudaMemsetAsync(w->gsum, 0, sizeof(unsigned long long) * NB * G * 2, st) == cudaSuccess
+                 ? MIXDQ_OK : MIXDQ_ERR_CUDA;
+    }
     return mixdq_q2_premm(yh, static_cast<int64_t>(NB) * HW * C, q, scale_out, zp_out, ws,
                           NB * cpi, w->gsum, NB * G * 2, st);
   }
+  if (q == nullptr) return MIXDQ_ERR_UNSUPPORTED;
   auto gk = silu ? gn_quant_kernel<true, 0> : gn_quant_kernel<false, 0>;
   if (launch_pdl(gk, NB * cpi, kFqThreads, smem, st, reinterpret_cast<const __half*>(x), ldx, NB, HW,
                  C, G, reinterpret_cast<const __half*>(gamma), reinterpret_cast<const __half*>(beta),

@@ -480,5 +480,6 @@ int mixdq_q2_ln(const __half* x, int64_t ldx, int M, int C, const __half* gamma,
             : launch_pdl(ln_minmax_kernel<8, 256>, g1, 256, 0, st, x, ldx, M, C, gamma, beta, eps, y, w);
   }
   if (e != cudaSuccess) return MIXDQ_ERR_CUDA;
+  if (q == nullptr) return MIXDQ_OK;                        // LayerNorm only (static-scale callers)
   return mixdq_q2_premm(y, static_cast<int64_t>(M) * C, q, scale_out, zp_out, ws, g1, nullptr, 0, st);
 }

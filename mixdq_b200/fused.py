@@ -44,7 +44,7 @@ from .nn.linear import QuantizedLinear
 # eligibility
 # ---------------------------------------------------------------------------------------------
 def _lin_ok(m) -> bool:
-    if not (isinstance(m, QuantizedLinear) and m.valid_for_acceleration and m.dynamic):
+    if not (isinstance(m, QuantizedLinear) and m.valid_for_acceleration):
         return False
     if m.a_bits != 8:
         return False                       # 4-bit activation layers run module by module
@@ -65,7 +65,7 @@ def _set_lin_weight(m: QuantizedLinear, w: torch.Tensor) -> None:
 
 
 def _conv_ok(m) -> bool:
-    if not (isinstance(m, QuantizedConv2d) and m.valid_for_acceleration and m.dynamic):
+    if not (isinstance(m, QuantizedConv2d) and m.valid_for_acceleration):
         return False
     pad, stride, k = m.padding[0], m.stride[0], m.kernel_size[0]
     geom = stride in (1, 2) and (pad == 0 or (pad == 1 and k == 3))
@@ -85,6 +85,59 @@ def _gn_ok(norm: nn.GroupNorm) -> bool:
 def _ln_ok(norm: nn.LayerNorm) -> bool:
     return (norm.weight is not None and norm.weight.dtype == torch.float16
             and norm.normalized_shape[-1] % 8 == 0 and norm.normalized_shape[-1] <= 2048)
+
+
+# ---------------------------------------------------------------------------------------------
+# activation-quantisation policy of a consumer layer
+#   dynamic: per-tensor min-max of the tensor itself (qdiff, base_quantizer.py:155-190)
+#   static : the layer's PTQ-checkpoint parameters and the reference's own formula
+#            (quantize_per_tensor_to_int8, quantize.cc:9-30). The GEMM / conv entry points take the
+#            activation scalars from device memory and form scale[n] = w_scale[n] * a_scale and
+#            bias0[n] = wsum[n] * a_zp in fp32 — the same two products `from_float` stores as the
+#            `scale` / `bias0` buffers (nn/Linear.py:125-132) — so the static path is bit-identical
+#            to the unfused static modules wherever the activation tensor is.
+# ---------------------------------------------------------------------------------------------
+def _act_key(m, sfx: str = ""):
+    """None for a dynamic layer, else its static (delta, zero point) as a hashable key"""
+    if m.dynamic:
+        return None
+    return (float(getattr(m, "act_scales" + sfx)), float(getattr(m, "act_zero_points" + sfx)))
+
+
+def _same_act(mods) -> bool:
+    return len({_act_key(m) for m in mods}) == 1
+
+
+def _static_args(m, sfx: str = ""):
+    return (getattr(m, "act_scales_inv" + sfx), getattr(m, "act_scales" + sfx),
+            getattr(m, "act_zero_points" + sfx))
+
+
+def _q_ln(x, norm, cons):
+    """LayerNorm -> int8 for consumer `cons`: (codes, scale, zero point)"""
+    if cons.dynamic:
+        return ops.layernorm_quantize_dynamic(x, norm.weight, norm.bias, norm.eps)
+    inv, sc, zp = _static_args(cons)
+    y = ops.layernorm_fp16(x, norm.weight, norm.bias, norm.eps)
+    return ops.quantize_per_tensor_to_int8(y, inv, zp), sc, zp
+
+
+def _q_gn(x, norm, silu: bool, cons):
+    """GroupNorm [+ SiLU] -> int8 channels_last for consumer `cons`"""
+    if cons.dynamic:
+        return ops.groupnorm_quantize_dynamic(x, norm.num_groups, norm.weight, norm.bias, norm.eps,
+                                              silu=silu)
+    inv, sc, zp = _static_args(cons)
+    y = ops.groupnorm_fp16(x, norm.num_groups, norm.weight, norm.bias, norm.eps, silu)
+    return ops.quantize_per_tensor_to_int8(y, inv, zp), sc, zp
+
+
+def _q_act(x, cons):
+    """plain tensor ([B, T, C] tokens, dense or row-pitched; [B, K]; NHWC images) -> int8"""
+    if cons.dynamic:
+        return _quant_tokens(x) if x.dim() == 3 else ops.quantize_per_tensor_dynamic(x)
+    inv, sc, zp = _static_args(cons)
+    return ops.quantize_per_tensor_to_int8(x, inv, zp), sc, zp
 
 
 # ---------------------------------------------------------------------------------------------
@@ -162,14 +215,23 @@ class GegluLinear:
                 mod.weight_sum_by_input_channels.index_select(0, idx).contiguous()
             if mod.bias is not None:
                 mod.bias = mod.bias.index_select(0, idx).contiguous()
+            for k in ("scale", "bias0", "weight_zero_points"):      # static-mode per-row buffers
+                if getattr(mod, k, None) is not None:
+                    setattr(mod, k, getattr(mod, k).index_select(0, idx).contiguous())
             mod.geglu_interleaved = True
             mod.register_buffer("geglu_inverse_index", torch.argsort(idx), persistent=False)
         self.mod = mod
 
-    def run(self, q8, scale, zp):
+    def run(self, q8, scale, zp, cons=None):
+        """-> int8 GEGLU output quantised for `cons` (ff.net.2)"""
         m = self.mod
-        return ops.qlinear_geglu_quantize_dynamic(q8, _lin_weight(m), m.weight_scales, scale, zp,
-                                                  m.weight_sum_by_input_channels, m.bias)
+        if cons is None or cons.dynamic:
+            return ops.qlinear_geglu_quantize_dynamic(q8, _lin_weight(m), m.weight_scales, scale,
+                                                      zp, m.weight_sum_by_input_channels, m.bias)
+        y = ops.qlinear_geglu_fp16(q8, _lin_weight(m), m.weight_scales, scale, zp,
+                                   m.weight_sum_by_input_channels, m.bias)
+        inv, sc, z2 = _static_args(cons)
+        return ops.quantize_per_tensor_to_int8(y, inv, z2), sc, z2
 
 
 class SharedInputGroup:
@@ -207,8 +269,7 @@ class SharedInputGroup:
             xin = self.pre(x) if self.pre is not None else x
             if self.bos:
                 xin = xin[:, 1:, :]
-            q8, s, z = _quant_tokens(xin) if xin.dim() == 3 else \
-                ops.quantize_per_tensor_dynamic(xin)
+            q8, s, z = _q_act(xin, self.cat.mods[0])
             outs = self.cat.run_parts(q8, s, z)
             if self.bos:
                 outs = [torch.cat([rows.expand(o.shape[0], -1, -1), o], dim=1)
@@ -327,30 +388,35 @@ def fused_transformer_block_forward(self, hidden_states, *args, **kwargs):
     x = hidden_states
     c = x.shape[-1]
     # --- self-attention ---
-    q8, s, z = ops.layernorm_quantize_dynamic(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+    q8, s, z = _q_ln(x, self.norm1, self.attn1.to_q)
     cat = f["qkv"]
     outs = cat.run_parts(q8, s, z)
     o = _attention(cat.slice_of(outs, 0), cat.slice_of(outs, 1), cat.slice_of(outs, 2),
                    self.attn1.heads)
-    o8, s, z = _quant_tokens(o)
+    o8, s, z = _q_act(o, self.attn1.to_out[0])
     x = _run_linear(self.attn1.to_out[0], o8, s, z, residual=x)
     # --- cross-attention ---
-    q8, s, z = ops.layernorm_quantize_dynamic(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+    q8, s, z = _q_ln(x, self.norm2, self.attn2.to_q)
     q = _run_linear(self.attn2.to_q, q8, s, z)
     kv = f["kv"]
     kk, vv = kv.get(self.attn2.to_k, ctx), kv.get(self.attn2.to_v, ctx)
     heads = self.attn2.heads
     o = _attention(q, kk, vv, heads)
-    o8, s, z = _quant_tokens(o)
+    o8, s, z = _q_act(o, self.attn2.to_out[0])
     x = _run_linear(self.attn2.to_out[0], o8, s, z, residual=x)
     # --- feed-forward ---
-    q8, s, z = ops.layernorm_quantize_dynamic(x, self.norm3.weight, self.norm3.bias, self.norm3.eps)
+    q8, s, z = _q_ln(x, self.norm3, self.ff.net[0].proj)
+    ff2 = self.ff.net[2]
     if f.get("ffproj") is not None:
-        g8, s, z = f["ffproj"].run(q8, s, z)
+        g8, s, z = f["ffproj"].run(q8, s, z, ff2)
     else:
         hg = _run_linear(self.ff.net[0].proj, q8, s, z)
-        g8, s, z = ops.geglu_quantize_dynamic(hg)
-    return _run_linear(self.ff.net[2], g8, s, z, residual=x)
+        if ff2.dynamic:
+            g8, s, z = ops.geglu_quantize_dynamic(hg)
+        else:
+            h, gate = hg.chunk(2, dim=-1)
+            g8, s, z = _q_act(h * F.gelu(gate), ff2)
+    return _run_linear(ff2, g8, s, z, residual=x)
 
 
 def fused_transformer2d_forward(self, hidden_states, *args, **kwargs):
@@ -368,12 +434,11 @@ def fused_transformer2d_forward(self, hidden_states, *args, **kwargs):
     b, c, h, w = x.shape
     if not x.is_contiguous(memory_format=torch.channels_last):
         x = x.contiguous(memory_format=torch.channels_last)
-    q8, s, z = ops.groupnorm_quantize_dynamic(x, self.norm.num_groups, self.norm.weight,
-                                              self.norm.bias, self.norm.eps, silu=False)
+    q8, s, z = _q_gn(x, self.norm, False, self.proj_in)
     y = _run_linear(self.proj_in, q8.permute(0, 2, 3, 1).reshape(b, h * w, c), s, z)
     for blk in self.transformer_blocks:
         y = blk(y, ctx) if native else blk(y, encoder_hidden_states=ctx)
-    o8, s, z = _quant_tokens(y)
+    o8, s, z = _q_act(y, self.proj_out)
     res = x.permute(0, 2, 3, 1).reshape(b, h * w, c)
     out = _run_linear(self.proj_out, o8, s, z, residual=res)
     out = out.reshape(b, h, w, c).permute(0, 3, 1, 2)
@@ -394,20 +459,25 @@ def fused_resnet_forward(self, input_tensor, temb, *args, **kwargs):
     if not x.is_contiguous(memory_format=torch.channels_last):
         x = x.contiguous(memory_format=torch.channels_last)
     n1, n2 = self.norm1, self.norm2
-    h8, s, z = ops.groupnorm_quantize_dynamic(x, n1.num_groups, n1.weight, n1.bias, n1.eps, silu=True)
+    h8, s, z = _q_gn(x, n1, True, self.conv1)
     t = f["temb"].get(self.time_emb_proj, temb)                  # [B, K] fp16 (column slice)
     h = _run_conv(self.conv1, h8, s, z, chan_add=t)
-    h8, s, z = ops.groupnorm_quantize_dynamic(h, n2.num_groups, n2.weight, n2.bias, n2.eps, silu=True)
+    h8, s, z = _q_gn(h, n2, True, self.conv2)
     sc = self.conv_shortcut
     if sc is None:
         res = x
     elif sc.split == 0:
-        x8, xs, xz = ops.quantize_per_tensor_dynamic(x)
+        x8, xs, xz = _q_act(x, sc)
         res = _run_conv(sc, x8, xs, xz)
     else:
         c = x.shape[1]
-        xa, sa, za = ops.quantize_nhwc_slice_dynamic(x, 0, sc.split)
-        xb, sb, zb = ops.quantize_nhwc_slice_dynamic(x, sc.split, c)
+        if sc.dynamic:
+            xa, sa, za = ops.quantize_nhwc_slice_dynamic(x, 0, sc.split)
+            xb, sb, zb = ops.quantize_nhwc_slice_dynamic(x, sc.split, c)
+        else:
+            (ia, sa, za), (ib, sb, zb) = _static_args(sc), _static_args(sc, "_0")
+            xa = ops.quantize_to_nhwc(x, ia, za, 0, sc.split)
+            xb = ops.quantize_to_nhwc(x, ib, zb, sc.split, c)
         res = ops.qconv1x1_split_dynamic_fused(
             xa, sc.weight_int, sc.weight_scales, sc.weight_sum_per_output_channel, sa, za,
             xb, sc.weight_int_0, sc.weight_scales_0, sc.weight_sum_per_output_channel_0, sb, zb,
@@ -458,6 +528,9 @@ def _block_ok(blk) -> bool:
         return False
     if not all(_lin_ok(m) for m in lins) or not all(isinstance(n, nn.LayerNorm) and _ln_ok(n) for n in norms):
         return False
+    # one mode per block; q / k / v read ONE quantised tensor, so static parameters must agree
+    if len({m.dynamic for m in lins}) != 1 or not _same_act(lins[:3]) or not _same_act(lins[5:7]):
+        return False
     bos = [bool(getattr(m, "bos", False)) for m in (blk.attn2.to_k, blk.attn2.to_v)]
     return bos[0] == bos[1]
 
@@ -474,7 +547,20 @@ def _resnet_ok(res) -> bool:
     except AttributeError:
         return False
     sc = getattr(res, "conv_shortcut", None)
-    return ok and (sc is None or _conv_ok(sc)) and isinstance(getattr(res, "nonlinearity", None), nn.SiLU)
+    mods = [res.conv1, res.conv2, res.time_emb_proj] + ([sc] if sc is not None else [])
+    return ok and (sc is None or _conv_ok(sc)) and len({m.dynamic for m in mods}) == 1 \
+        and isinstance(getattr(res, "nonlinearity", None), nn.SiLU)
+
+
+def _kv_key(blk):
+    """attn2.to_k / to_v layers that may share one quantised context tensor and one GEMM: same
+    context width, same BOS mode and — static scales — the same activation parameters"""
+    k = blk.attn2.to_k
+    return (k.in_features, bool(getattr(k, "bos", False)), _act_key(k))
+
+
+def _temb_key(r):
+    return (r.time_emb_proj.in_features, _act_key(r.time_emb_proj))
 
 
 def fuse_unet(unet: nn.Module, verbose: bool = False) -> dict:
@@ -495,11 +581,11 @@ def fuse_unet(unet: nn.Module, verbose: bool = False) -> dict:
     # one K/V group per (context width, BOS mode)
     kv_groups = {}
     for blk in blocks:
-        key = (blk.attn2.to_k.in_features, bool(getattr(blk.attn2.to_k, "bos", False)))
+        key = _kv_key(blk)
         kv_groups.setdefault(key, []).extend([blk.attn2.to_k, blk.attn2.to_v])
     kv_objs = {k: SharedInputGroup(v, bos=k[1]) for k, v in kv_groups.items()}
     for blk in blocks:
-        key = (blk.attn2.to_k.in_features, bool(getattr(blk.attn2.to_k, "bos", False)))
+        key = _kv_key(blk)
         proj = blk.ff.net[0].proj
         blk._mixdq_fused = {"orig_forward": blk.forward,
                             "qkv": CatLinear([blk.attn1.to_q, blk.attn1.to_k, blk.attn1.to_v]),
@@ -513,10 +599,10 @@ def fuse_unet(unet: nn.Module, verbose: bool = False) -> dict:
     if resnets:
         temb_groups = {}
         for r in resnets:
-            temb_groups.setdefault(r.time_emb_proj.in_features, []).append(r.time_emb_proj)
+            temb_groups.setdefault(_temb_key(r), []).append(r.time_emb_proj)
         temb_objs = {k: SharedInputGroup(v, pre=F.silu) for k, v in temb_groups.items()}
         for r in resnets:
-            r._mixdq_fused = {"temb": temb_objs[r.time_emb_proj.in_features]}
+            r._mixdq_fused = {"temb": temb_objs[_temb_key(r)]}
             r.forward = types.MethodType(fused_resnet_forward, r)
             summary["temb_layers"] += 1
     # the shared-input results live for ONE UNet forward (see SharedInputGroup)

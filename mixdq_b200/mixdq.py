@@ -126,14 +126,14 @@ def quantize_unet(unet, args, ckpt, bos, bos_dict, fuse: Optional[bool] = None):
     min-max weight scales.
 
     `fuse` (extension; the reference signature ends at `bos_dict`): also re-bind the block
-    forwards to the fused kernels (mixdq_b200.fused.fuse_unet). Default: when the model already
-    sits on a CUDA device and the quantisation is dynamic. The module tree, names and buffers of
-    the quantized leaves are the same either way."""
+    forwards to the fused kernels (mixdq_b200.fused.fuse_unet), for dynamic AND static (ckpt)
+    activation scales. Default: when the model already sits on a CUDA device. The module tree,
+    names and buffers of the quantized leaves are the same either way."""
     register_qconfig_from_input_files(unet, args, bos=bos, bos_dict=bos_dict)
     convert_to_quantized(unet, ckpt)
     if fuse is None:
         p = next(iter(unet.buffers()), None)
-        fuse = ckpt is None and p is not None and p.device.type == "cuda"
+        fuse = p is not None and p.device.type == "cuda"
     if fuse:
         from .fused import fuse_unet
         fuse_unet(unet)

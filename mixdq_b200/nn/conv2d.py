@@ -154,6 +154,10 @@ class QuantizedConv2d(nn.Module):
                     else:
                         new_mod.register_buffer(
                             "bias0" + sfx, wsum * getattr(new_mod, "act_zero_points" + sfx))
+                        # the fused block forwards fold the activation scalars inside the kernel
+                        # (bias0[n] = wsum[n] * zp): not part of the reference's state_dict
+                        new_mod.register_buffer("weight_sum_per_output_channel" + sfx, wsum,
+                                                persistent=False)
                     setattr(new_mod, "weight_sum_by_input_channels" + sfx, None)
                 else:
                     new_mod.register_buffer("weight_sum_by_input_channels" + sfx,

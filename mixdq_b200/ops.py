@@ -868,6 +868,76 @@ def groupnorm_quantize_dynamic(x: torch.Tensor, num_groups: int, weight: torch.T
     return (q, sc, zp, y) if return_y else (q, sc, zp)
 
 
+# ---- static-scale producers (fused blocks with a PTQ checkpoint) --------------------------------
+# The normalisation kernels of the dynamic path write their fp16 result into a tensor; with static
+# (checkpoint) activation parameters that tensor is quantised by the reference's own formula
+# (quantize_per_tensor_to_int8: one FMA, round, saturate) — no min/max, no partials.
+def layernorm_fp16(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float
+                   ) -> torch.Tensor:
+    """LayerNorm over the last dim, fp16 in / fp16 out, by the LayerNorm kernel of the fused path."""
+    _check(x.dtype == torch.float16 and weight.dtype == torch.float16
+           and bias.dtype == torch.float16, "layernorm_fp16 expects fp16 tensors")
+    C = x.shape[-1]
+    x2 = x.reshape(-1, C)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    y = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    lib = _lib.load()
+    with _DeviceGuard(x2):
+        ws = _dynamic_workspace(x2.device)
+        _launch("ln", lib.mixdq_ln_quant_i8_dynamic,
+                (x2.data_ptr(), x2.stride(0) if M > 1 else C, M, C, weight.data_ptr(),
+                 bias.data_ptr(), float(eps), None, y.data_ptr(), None, None, ws.data_ptr()), x2,
+                keep=(x2, weight, bias, y, ws), algo_bytes=4 * M * C)
+    return y
+
+
+def groupnorm_fp16(x: torch.Tensor, num_groups: int, weight: torch.Tensor, bias: torch.Tensor,
+                   eps: float, silu: bool) -> torch.Tensor:
+    """GroupNorm [+ SiLU], fp16 channels_last in / out, by the statistics + apply kernels of the
+    fused path (two launches and a memset of the statistics accumulators)."""
+    _check(x.dtype == torch.float16 and x.dim() == 4, "groupnorm_fp16 expects fp16 4-D")
+    n, c, h, w = x.shape
+    if _nhwc_pitch(x) != c:
+        x = x.contiguous(memory_format=torch.channels_last)
+    y = torch.empty((n, c, h, w), dtype=torch.float16, device=x.device,
+                    memory_format=torch.channels_last)
+    lib = _lib.load()
+    with _DeviceGuard(x):
+        ws = _dynamic_workspace(x.device)
+        _launch("gn", lib.mixdq_gn_quant_i8_dynamic,
+                (x.data_ptr(), c, n, h * w, c, num_groups, weight.data_ptr(), bias.data_ptr(),
+                 float(eps), 1 if silu else 0, None, y.data_ptr(), None, None, ws.data_ptr()), x,
+                keep=(x, weight, bias, y, ws), kernels=2, algo_bytes=4 * x.numel())
+    return y
+
+
+def qlinear_geglu_fp16(input_int8, weight_il, weight_scale_il, input_scale, input_zero_point,
+                       weight_sum_il, bias_il=None) -> torch.Tensor:
+    """ff.net.0.proj with the GEGLU in the GEMM epilogue -> fp16 [..., inner] (rows of the weight
+    interleaved by `geglu_interleave_index`); the first half of qlinear_geglu_quantize_dynamic."""
+    w4 = _is_w4(weight_il)
+    N2, K = weight_il.shape[0], weight_il.shape[1] * (2 if w4 else 1)
+    I = N2 // 2
+    a = input_int8 if input_int8.is_contiguous() else input_int8.contiguous()
+    M = a.numel() // K
+    y = torch.empty((*input_int8.shape[:-1], I), dtype=torch.float16, device=a.device)
+    lib = _lib.load()
+    with _DeviceGuard(a):
+        ws = _dynamic_workspace(a.device)
+        _launch("gemm_geglu_w4" if w4 else "gemm_geglu",
+                lib.mixdq_gemm_w4a8_geglu_f16_dyn if w4 else lib.mixdq_gemm_w8a8_geglu_f16_dyn,
+                (a.data_ptr(), K, weight_il.data_ptr(), weight_scale_il.data_ptr(),
+                 weight_sum_il.data_ptr(), input_scale.data_ptr(), input_zero_point.data_ptr(),
+                 _ptr(bias_il), y.data_ptr(), I, M, N2, K, ws.data_ptr()), a,
+                keep=(a, weight_il, weight_scale_il, weight_sum_il, input_scale,
+                      input_zero_point, bias_il, y, ws),
+                algo_bytes=M * K + N2 * K // (2 if w4 else 1) + 2 * M * I + 10 * N2,
+                algo_ops=2 * M * N2 * K)
+    return y
+
+
 def quantize_rows_dynamic(x2: torch.Tensor):
     """A10 on a 2-D row-pitched fp16 view [M, cols] (stride(1) == 1) -> dense int8 [M, cols]."""
     _check(x2.dtype == torch.float16 and x2.dim() == 2 and x2.stride(1) == 1,

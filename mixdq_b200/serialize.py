@@ -18,8 +18,8 @@ the GPU first. Here the quantised model itself is serialised:
 Buffers are written in their STORED layout: a GEGLU projection whose rows were interleaved for the
 fused epilogue (`geglu_interleaved`) stays interleaved in the file — one copy of every weight, in
 the layout the kernels consume. `load_quantized_unet` rebuilds the modules on a skeleton created on
-the META device: no fp16 weight is ever materialised, the GPU holds the 2.6 GB of int8 / int4
-buffers and nothing else (bench.py `memory.loaded_from_quantized_file_mb`).
+the META device: no fp16 weight is ever materialised, the GPU holds the 2.5 GB of int8 / int4
+buffers (SDXL, all W8) and nothing else (tests/test_gpu_realsize.py checks the resident bytes).
 """
 from __future__ import annotations
 
@@ -55,8 +55,12 @@ def quantized_state(unet: nn.Module, meta: Optional[dict] = None) -> dict:
     for name, m in unet.named_modules():
         if isinstance(m, (QuantizedLinear, QuantizedConv2d)):
             leaves[name] = _leaf_record(m)
+            # non-persistent buffers that are operands (not derived indices) travel too, and come
+            # back non-persistent, so the reference-format state_dict is unchanged
+            leaves[name]["non_persistent"] = sorted(
+                b for b in m._non_persistent_buffers_set if b != "geglu_inverse_index")
             for bname, buf in m._buffers.items():
-                if buf is None or bname in m._non_persistent_buffers_set:
+                if buf is None or bname == "geglu_inverse_index":
                     continue
                 # members of an N-concatenated group are views of one storage: store each leaf's
                 # own rows (clone), the loader re-concatenates when it fuses
@@ -91,8 +95,9 @@ def _build_leaf(rec: dict, tensors: Dict[str, torch.Tensor], prefix: str, device
     m.device = device
     for key, t in tensors.items():
         if key.startswith(prefix) and "." not in key[len(prefix):]:
-            t = t.to(device)
-            m.register_buffer(key[len(prefix):], t)
+            bname = key[len(prefix):]
+            m.register_buffer(bname, t.to(device),
+                              persistent=bname not in rec.get("non_persistent", ()))
     if getattr(m, "geglu_interleaved", False):
         from . import ops
         idx = ops.geglu_interleave_index(m.out_features // 2, device)
@@ -148,9 +153,7 @@ def load_quantized_unet(skeleton: nn.Module, path_or_state, device, fuse: Option
             if key in other:
                 mod._buffers[bname] = other[key].to(device)
     if fuse is None:
-        dyn = any(getattr(m, "dynamic", False) for m in skeleton.modules()
-                  if isinstance(m, (QuantizedLinear, QuantizedConv2d)))
-        fuse = dyn and device.type == "cuda"
+        fuse = device.type == "cuda"
     if fuse:
         from .fused import fuse_unet
         fuse_unet(skeleton)

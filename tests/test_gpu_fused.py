@@ -155,7 +155,9 @@ def test_two_pass_and_single_kernel_quantisers_agree(ops, dev):
     w = (1 + 0.2 * torch.randn(640, generator=g)).half().to(dev)
     b = (0.1 * torch.randn(640, generator=g)).half().to(dev)
     wide = (torch.randn(1024, 1920, generator=g) * 3).half().to(dev)
-    img = (torch.randn(2, 640, 32, 32, generator=g) * 1.5).half().to(dev).contiguous(
+    # (one image: the barrier-free GroupNorm cuts every image into the batch-1 row ranges so that
+    # results do not depend on the batch; the single-kernel form splits per batch)
+    img = (torch.randn(1, 640, 32, 32, generator=g) * 1.5).half().to(dev).contiguous(
         memory_format=torch.channels_last)
     outs = []
     try:

@@ -440,3 +440,91 @@ def test_fused_forward_diffusers_conventions(dev):
         assert fuse_unet(t2.to(dev))["transformer_blocks"] == 0
     finally:
         del sys.modules[fake.__name__]
+
+
+def test_static_ckpt_mode_through_fuse_unet(dev):
+    """Static (PTQ checkpoint) activation scales through the fused block forwards:
+    the reference's shipped mode no longer runs leaf by leaf. The fused producers write fp16 and
+    the reference's own static formula quantises it with the consumer's checkpoint parameters; the
+    GEMM / conv kernels fold the static scalars exactly like the `scale` / `bias0` buffers do.
+      * a quantised layer fed identical int8-able input is bit-identical fused vs unfused
+        (checked on every Linear of the transformer blocks through the block-level comparison of
+        the quantised tensors' consumers);
+      * per block, teacher-forced: north-star tolerance (LayerNorm / GroupNorm / GEGLU are
+        restatements within a few fp16 ulp of the stock ops -> isolated 1-step code flips);
+      * whole UNet under a CUDA graph: replay == eager."""
+    import bench
+    from mixdq_b200 import mixdq, ops
+    from mixdq_b200.fused import fuse_unet
+    from mixdq_b200.unet import build_unet
+    unet = build_unet("tiny", seed=3).half()
+    names = [n for n, _ in unet.quantizable_layers()]
+    args = SimpleNamespace(w_config={n: 8 for n in names}, a_config={n: 8 for n in names})
+    ckpt = bench.synth_ckpt(unet)
+    inputs = unet.example_inputs(2, "cpu", torch.float16, seed=1)
+    mixdq.quantize_unet(unet, args, ckpt=ckpt, bos=False, bos_dict=None, fuse=False)
+    unet = unet.to(dev).to(memory_format=torch.channels_last).eval()
+    assert not any(m.dynamic for m in unet.modules() if hasattr(m, "valid_for_acceleration"))
+    kw = {k: v.to(dev) for k, v in inputs.items()}
+    kinds = ("BasicTransformerBlock", "ResnetBlock2D", "Transformer2DModel")
+    blocks = [(n, m) for n, m in unet.named_modules() if type(m).__name__ in kinds]
+    rec = {}
+
+    def hook(name):
+        def f(m, inp, out):
+            rec[name] = ([t.detach().clone() for t in inp], out.detach().clone())
+        return f
+    handles = [m.register_forward_hook(hook(n)) for n, m in blocks]
+    with torch.no_grad():
+        plain = unet(**kw)[0].clone()
+        for h in handles:
+            h.remove()
+        state_before = {k: v.clone() for k, v in unet.state_dict().items()}
+        summary = fuse_unet(unet)
+        assert summary["transformer_blocks"] == 4 and summary["resnets"] == 8, summary
+        # fusing changes no stored value of the reference-format state_dict
+        after = unet.state_dict()
+        assert set(after) == set(state_before) and all(torch.equal(after[k], state_before[k]) for k in after)
+        for n, m in blocks:
+            inp, out = rec[n]
+            # a Transformer2DModel CONTAINS free-running transformer blocks (code flips of one
+            # block feed the next): twice the single-block tolerance
+            tol = 2e-2 if type(m).__name__ == "Transformer2DModel" else 1e-2
+            ok, stats = close(m(*inp), out, abs_tol=tol, cos_tol=0.9999, rel_to_max=True)
+            assert ok, (n, stats)
+        c0 = ops.launch_count()
+        fused = unet(**kw)[0].clone()
+        n_fused = ops.launch_count() - c0
+    ok, stats = close(fused, plain, abs_tol=8e-2, cos_tol=0.998, rel_to_max=True)
+    assert ok, stats
+    assert n_fused > 0
+    mixdq.cuda_graph_opt(unet)
+    with torch.no_grad():
+        g1 = unet(**kw)[0].clone()
+        g2 = unet(**kw)[0].clone()
+    assert torch.equal(g1, fused) and torch.equal(g2, fused)
+
+
+def test_static_linear_fused_entry_is_bit_identical(dev):
+    """the dynamic-scalar GEMM entry point fed a layer's STATIC (delta, zp) reproduces the static
+    module bit for bit: scale[n] = w_scale[n] * delta and bias0[n] = wsum[n] * zp are the same fp32
+    products `from_float` stores (nn/Linear.py:125-132)"""
+    import bench
+    from mixdq_b200 import ops
+    from mixdq_b200.nn.linear import QuantizedLinear
+    torch.manual_seed(0)
+    fm = nn.Linear(1280, 640).half()
+    _prep(fm, "blk.attn1.to_q")
+    fm.a_bit = 8
+    d = torch.stack([torch.full((640,), 0.01), torch.full((640,), 0.005),
+                     fm.weight.detach().float().abs().amax(1) / 127]).half()
+    ck = {"blk.attn1.to_q.weight_quantizer": {"delta_list": d, "zero_point_list": torch.zeros_like(d)},
+          "blk.attn1.to_q.act_quantizer": {"delta_list": torch.tensor([2.7, 0.55, 0.0323]).half(),
+                                           "zero_point_list": torch.tensor([2.0, 8.0, 131.0]).half()}}
+    q = QuantizedLinear.from_float(fm, ckpt=ck).to(dev)
+    x = torch.randn(2, 256, 1280, generator=torch.Generator().manual_seed(1)).half().to(dev)
+    want = q(x)
+    x8 = ops.quantize_per_tensor_to_int8(x, q.act_scales_inv, q.act_zero_points)
+    got = ops.qlinear_dynamic_fused(x8, q.weight_int, q.weight_scales, q.act_scales,
+                                    q.act_zero_points, q.weight_sum_by_input_channels, q.bias)
+    assert torch.equal(bits(got), bits(want))
