@@ -333,6 +333,11 @@ int mixdq_quant_i8_dynamic_rows(const mixdq_half_t* x, int64_t ldx, int M, int c
 int mixdq_quant_i8_dynamic_bits(const mixdq_half_t* x, int64_t ldx, int64_t M, int64_t cols,
                                 int n_bits, float* scale_out, float* zp_out, int8_t* q, void* ws,
                                 mixdq_stream_t stream);
+/* out[0] = min(0, min x), out[1] = max(0, max x) of a dense fp16 tensor (numel % 8 == 0): the
+   clamped range the qdiff quantizers start from (base_quantizer.py:155-158), used by the PTQ
+   calibration (mixdq_b200/ptq.py; reference scripts/ptq.py:126-155). */
+int mixdq_minmax_f16(const mixdq_half_t* x, int64_t numel, float* out, void* ws,
+                     mixdq_stream_t stream);
 /* A1 with an explicit code range: q = clamp(lrintf(x * scale_inv + zp), lo, hi), flat dense.
    [lo, hi] = [0, 15] with the unshifted zero point for static 4-bit activations. */
 int mixdq_quant_i8_static_range(const mixdq_half_t* x, int64_t numel, const float* scale_inv,

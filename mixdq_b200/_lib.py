@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "mixdq_quant_i8_dynamic_rows", "mixdq_ln_quant_i8_dynamic", "mixdq_geglu_quant_i8_dynamic", "mixdq_gn_quant_i8_dynamic",
     "mixdq_gemm_w8a8_geglu_f16_dyn", "mixdq_quant_i8_premm",
     "mixdq_gemm_w4a8_f16_dyn_res", "mixdq_gemm_w4a8_geglu_f16_dyn", "mixdq_conv_w4a8_f16",
-    "mixdq_conv_w4a8_f16_dyn", "mixdq_quant_i8_dynamic_bits", "mixdq_quant_i8_static_range",
+    "mixdq_conv_w4a8_f16_dyn", "mixdq_quant_i8_dynamic_bits", "mixdq_quant_i8_static_range", "mixdq_minmax_f16",
 ]
 
 
@@ -60,6 +60,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mixdq_debug_set_persist_bn.argtypes = [c_int]
     lib.mixdq_quant_i8_dynamic_bits.restype = c_int
     lib.mixdq_quant_i8_dynamic_bits.argtypes = [P, c_int64, c_int64, c_int64, c_int, P, P, P, P, P]
+    lib.mixdq_minmax_f16.restype = c_int
+    lib.mixdq_minmax_f16.argtypes = [P, c_int64, P, P, P]
     lib.mixdq_quant_i8_static_range.restype = c_int
     lib.mixdq_quant_i8_static_range.argtypes = [P, c_int64, P, P, c_int, c_int, P, P]
     lib.mixdq_debug_force_splits.restype = None

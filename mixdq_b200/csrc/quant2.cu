@@ -389,6 +389,32 @@ ln_minmax_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
   dbg.end(ws);
 }
 
+// one CTA: (min, max) of the `nparts` partials a min/max pass left in the workspace
+__global__ void __launch_bounds__(256)
+minmax_finish_kernel(const DynWs* __restrict__ ws, int nparts, float* __restrict__ out) {
+  __shared__ float s_mn[8], s_mx[8];
+  pdl_wait();
+  float mn = 0.0f, mx = 0.0f;
+  for (int i = threadIdx.x; i < nparts; i += 256) {
+    const float2 p = __ldcg(&ws->partial[i]);
+    mn = fminf(mn, p.x);
+    mx = fmaxf(mx, p.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+    out[0] = mn;
+    out[1] = mx;
+  }
+}
+
 static inline int grid_for2(int64_t items, int per_block, int max_blocks) {
   int64_t g = (items + per_block - 1) / per_block;
   if (g < 1) g = 1;
@@ -482,4 +508,24 @@ int mixdq_q2_ln(const __half* x, int64_t ldx, int M, int C, const __half* gamma,
   if (e != cudaSuccess) return MIXDQ_ERR_CUDA;
   if (q == nullptr) return MIXDQ_OK;                        // LayerNorm only (static-scale callers)
   return mixdq_q2_premm(y, static_cast<int64_t>(M) * C, q, scale_out, zp_out, ws, g1, nullptr, 0, st);
+}
+
+// (min(0, min x), max(0, max x)) of a dense fp16 tensor -> out[2] (PTQ calibration: the clamped
+// range of base_quantizer.py:155-158). numel % 8 == 0.
+extern "C" int mixdq_minmax_f16(const mixdq_half_t* x, int64_t numel, float* out, void* ws,
+                                mixdq_stream_t stream) {
+  if (numel <= 0 || !x || !out || !ws) return MIXDQ_ERR_INVALID_ARG;
+  if ((numel & 7) || (reinterpret_cast<uintptr_t>(x) & 15)) return MIXDQ_ERR_ALIGNMENT;
+  const int64_t items = numel >> 3;
+  if (items > kMaxItems) return MIXDQ_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned int n = static_cast<unsigned int>(items);
+  const int g1 = grid_for2(items, kQ2Threads, 148 * 4);
+  if (launch_pdl(minmax_rows_kernel, g1, kQ2Threads, 0, st, reinterpret_cast<const __half*>(x),
+                 static_cast<int64_t>(0), n, n, static_cast<DynWs*>(ws)) != cudaSuccess)
+    return MIXDQ_ERR_CUDA;
+  if (launch_pdl(minmax_finish_kernel, 1, 256, 0, st, static_cast<const DynWs*>(ws), g1, out) !=
+      cudaSuccess)
+    return MIXDQ_ERR_CUDA;
+  return MIXDQ_OK;
 }

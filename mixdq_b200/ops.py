@@ -938,6 +938,23 @@ def qlinear_geglu_fp16(input_int8, weight_il, weight_scale_il, input_scale, inpu
     return y
 
 
+def tensor_minmax(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [2] = (min(0, min x), max(0, max x)) of a dense fp16 tensor (numel % 8 == 0), by the
+    min/max pass of the dynamic quantiser + a one-CTA reduction of its partials (PTQ calibration,
+    mixdq_b200.ptq)."""
+    _check(x.dtype == torch.float16 and x.device.type == "cuda", "tensor_minmax expects CUDA fp16")
+    xd = x if _is_dense(x) else x.contiguous()
+    _check(xd.numel() % 8 == 0 and xd.numel() > 0, "tensor_minmax needs numel % 8 == 0")
+    out = torch.empty(2, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    with _DeviceGuard(xd):
+        ws = _dynamic_workspace(xd.device)
+        _launch("minmax", lib.mixdq_minmax_f16,
+                (xd.data_ptr(), xd.numel(), out.data_ptr(), ws.data_ptr()), xd, kernels=2,
+                keep=(xd, out, ws), algo_bytes=2 * xd.numel())
+    return out
+
+
 def quantize_rows_dynamic(x2: torch.Tensor):
     """A10 on a 2-D row-pitched fp16 view [M, cols] (stride(1) == 1) -> dense int8 [M, cols]."""
     _check(x2.dtype == torch.float16 and x2.dim() == 2 and x2.stride(1) == 1,

@@ -231,6 +231,57 @@ def golden_configs(ref: Path, out: Path):
     print("configs:", list(cfg), "bos entries:", len(bos))
 
 
+def golden_ptq(QuantLayer, out: Path):
+    """The calibration flow of scripts/ptq.py:126-155 on single layers: weight quantizers
+    initialised from the weights (one forward with weight_quant only), then the activation
+    quantizers' running statistics over several calibration batches (momentum 0.95,
+    base_quantizer.py:41,160-171 — updated once per bit width of `mixed_precision` per forward)."""
+    g = torch.Generator().manual_seed(4321)
+    flat = {}
+
+    def calibrate(name, mod, batches, split=0):
+        layer = QuantLayer(mod, wq_cfg(8), aq_cfg(8))
+        qs = [layer.weight_quantizer, layer.act_quantizer]
+        if split:
+            # the '_0' twins are created by the first split forward
+            pass
+        for q in qs:
+            q.module_name = "golden"
+        kw = dict(split=split) if split else {}
+        with torch.no_grad():
+            layer.set_quant_state(True, False)
+            layer(batches[0], **kw)
+            layer.weight_quantizer.init_done = True
+            if split:
+                layer.weight_quantizer_0.init_done = True
+            layer.set_quant_state(True, True)
+            for xb in batches:
+                layer(xb, **kw)
+        flat[f"{name}.weight"] = mod.weight.detach().numpy()
+        for i, xb in enumerate(batches):
+            flat[f"{name}.x{i}"] = xb.numpy()
+        flat[f"{name}.n_batches"] = np.array(len(batches))
+        flat[f"{name}.w_delta_list"] = layer.weight_quantizer.delta_list.reshape(3, -1).numpy()
+        flat[f"{name}.a_delta_list"] = layer.act_quantizer.delta_list.reshape(3).numpy()
+        flat[f"{name}.a_zp_list"] = layer.act_quantizer.zero_point_list.reshape(3).numpy()
+        if split:
+            flat[f"{name}.w_delta_list_0"] = layer.weight_quantizer_0.delta_list.reshape(3, -1).numpy()
+            flat[f"{name}.a_delta_list_0"] = layer.act_quantizer_0.delta_list.reshape(3).numpy()
+            flat[f"{name}.a_zp_list_0"] = layer.act_quantizer_0.zero_point_list.reshape(3).numpy()
+
+    lin = nn.Linear(64, 48)
+    calibrate("linear", lin, [torch.randn(2, 7, 64, generator=g) * (1.0 + 0.3 * i) + 0.1 * i
+                              for i in range(4)])
+    conv = nn.Conv2d(16, 24, 3, padding=1)
+    calibrate("conv", conv, [torch.randn(2, 16, 9, 9, generator=g) * (0.8 + 0.2 * i) for i in range(3)])
+    sc = nn.Conv2d(24, 16, 1)
+    calibrate("split", sc, [torch.cat([torch.randn(2, 8, 6, 6, generator=g) * (2.0 + i),
+                                       torch.randn(2, 16, 6, 6, generator=g) * 0.5 + 1.0], dim=1)
+                            for i in range(3)], split=8)
+    np.savez_compressed(out / "ptq_running_stat.npz", **flat)
+    print("ptq cases: linear, conv, split")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -241,6 +292,7 @@ def main():
     torch.manual_seed(0)
     QuantLayer = import_qdiff(ref)
     golden_qdiff(QuantLayer, out)
+    golden_ptq(QuantLayer, out)
     golden_known_answer(out)
     golden_configs(ref, out)
     golden_from_float(ref, out)

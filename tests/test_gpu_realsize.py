@@ -206,3 +206,36 @@ def test_quantized_file_loads_without_a_float_model(dev, tmp_path):
     with torch.no_grad():
         got = loaded(**inputs)[0]
     assert torch.equal(got, want)
+
+
+def test_ptq_calibration_on_the_gpu(dev):
+    """N4: calibrate the fp16 UNet on the GPU (min / max of every layer input by the library's
+    reduction kernel), quantise with the resulting checkpoint (static scales, fused blocks) and
+    stay close to the fp16 UNet; the min/max kernel agrees with torch exactly."""
+    import bench
+    from mixdq_b200 import mixdq, ops, ptq
+    g = torch.Generator().manual_seed(0)
+    for shape in ((8,), (256, 1280), (2, 320, 64, 64), (77 * 2048,)):
+        x = (torch.randn(*shape, generator=g) * 3 - 0.5).half().to(dev)
+        mm = ops.tensor_minmax(x).cpu()
+        assert float(mm[0]) == min(float(x.min()), 0.0) and float(mm[1]) == max(float(x.max()), 0.0)
+    pos = torch.rand(4096, generator=g).half().to(dev) + 1
+    assert float(ops.tensor_minmax(pos)[0]) == 0.0              # range always contains zero
+    fp16 = bench.build_fp16_unet("tiny", dev, seed=6)
+    batches = [fp16.example_inputs(2, dev, torch.float16, seed=s) for s in (11, 12, 13)]
+    ck = ptq.calibrate(fp16, batches)
+    # same statistics as the torch path on the CPU copy of the inputs (fp16 min/max is exact)
+    name = "mid_block.attentions.0.transformer_blocks.0.attn1.to_q"
+    assert ck[name + ".act_quantizer"]["delta_list"].shape == (3,)
+    names = [n for n, _ in fp16.quantizable_layers()]
+    args = SimpleNamespace(w_config={n: 8 for n in names}, a_config={n: 8 for n in names})
+    q = copy.deepcopy(fp16)
+    mixdq.quantize_unet(q, args, ckpt=ck, bos=False, bos_dict=None)
+    q = q.to(memory_format=torch.channels_last).eval()
+    assert getattr(q, "_mixdq_fused_summary", None) is not None
+    test_in = fp16.example_inputs(2, dev, torch.float16, seed=14)
+    with torch.no_grad():
+        want = fp16(**test_in)[0]
+        got = q(**test_in)[0]
+    err, cos = _stats(got, want)
+    assert cos >= 0.99 and err <= 0.15, (err, cos)

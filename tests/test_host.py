@@ -382,3 +382,58 @@ def test_shipping_config_on_the_sdxl_skeleton():
                 setattr(real, k, getattr(src, k))
         q = qcls.from_float(real, split=getattr(src, "split", 0) or 0, ckpt=None)
         assert q._get_name().endswith(want), (name, q._get_name())
+
+
+def test_ptq_running_statistics_match_reference_quantizers(golden_dir):
+    """N4: mixdq_b200.ptq restates the calibration arithmetic of the reference's BaseQuantizer
+    (running min / max with momentum 0.95 updated once per bit width per forward, delta, zero
+    point; per-channel symmetric weight scales) — pinned on vectors produced by the reference's own
+    quantizers driven like scripts/ptq.py:126-155 (oracle/make_golden.py::golden_ptq)."""
+    import numpy as np
+    from mixdq_b200 import ptq
+    z = np.load(golden_dir / "ptq_running_stat.npz")
+    g = {k: torch.from_numpy(z[k]) for k in z.files}
+    for name, split in (("linear", 0), ("conv", 0), ("split", 8)):
+        w = g[f"{name}.weight"]
+        n = int(g[f"{name}.n_batches"])
+        stats = [ptq.ActRunningStat(), ptq.ActRunningStat()]
+        for i in range(n):
+            x = g[f"{name}.x{i}"]
+            parts = (x[:, :split], x[:, split:]) if split else (x,)
+            for st, part in zip(stats, parts):
+                st.observe(*ptq.tensor_minmax(part))
+        sfxs = ("", "_0") if split else ("",)
+        wparts = (w[:, :split], w[:, split:]) if split else (w,)
+        for st, sfx, wp in zip(stats, sfxs, wparts):
+            assert torch.equal(st.delta_list, g[f"{name}.a_delta_list{sfx}"]), (name, sfx)
+            assert torch.equal(st.zero_point_list, g[f"{name}.a_zp_list{sfx}"]), (name, sfx)
+            assert torch.equal(ptq.weight_delta_list(wp), g[f"{name}.w_delta_list{sfx}"]), (name, sfx)
+
+
+def test_ptq_calibrate_produces_a_kernel_format_checkpoint():
+    """calibrate() on the tiny UNet (CPU, float): every layer gets the entries `from_float` looks
+    up (incl. the `_0` twins of the split shortcuts), in the dtype / shapes of new_ckpt.pth
+    (kernels/convert_ckpt.py:22-46), and the static quantisation it drives runs."""
+    from mixdq_b200 import ptq
+    unet = build_unet("tiny", seed=5)
+    names = [n for n, _ in unet.quantizable_layers()]
+    batches = [unet.example_inputs(2, "cpu", torch.float32, seed=s) for s in (1, 2, 3)]
+    ck = ptq.calibrate(unet, batches)
+    splits = quantize.derive_up_block_splits(unet)
+    for n in names:
+        cout = dict(unet.named_modules())[n].weight.shape[0]
+        for key in [n + ".weight_quantizer", n + ".act_quantizer"] + \
+                ([n + ".weight_quantizer_0", n + ".act_quantizer_0"] if n in splits else []):
+            e = ck[key]
+            assert e["delta_list"].dtype == torch.float16 and e["zero_point_list"].dtype == torch.float16
+            want = (3, cout) if "weight" in key else (3,)
+            assert tuple(e["delta_list"].shape) == want and tuple(e["zero_point_list"].shape) == want
+        a = ck[n + ".act_quantizer"]
+        assert (a["delta_list"] > 0).all() and (a["zero_point_list"][2] >= 0) and (a["zero_point_list"][2] <= 255)
+    assert len(ck) == 2 * len(names) + 2 * len(splits)
+    args = SimpleNamespace(w_config={"model." + n: 8 for n in names},
+                           a_config={"model." + n: 8 for n in names})
+    mixdq.quantize_unet(unet.half(), args, ckpt=ck, bos=False, bos_dict=None)
+    q = dict(unet.named_modules())["mid_block.attentions.0.transformer_blocks.0.attn1.to_q"]
+    assert q.valid_for_acceleration and not q.dynamic
+    assert float(q.act_scales) == float(ck[q.module_name + ".act_quantizer"]["delta_list"][2])
