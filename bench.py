@@ -547,7 +547,7 @@ def main():
         "unit": "TFLOP/s" if tensor_bound else "GB/s",
         "frac": tops / (2 * bf16_peak) if tensor_bound else achieved / hbm_peak,
         "traffic": traffic,
-        "kernel": "tc_i8_kernel (tcgen05 int8 GEMM / implicit-GEMM conv family)",
+        "kernel": "tc_i8_kernel / tc_i8_persist_kernel (tcgen05 int8 GEMM / implicit-GEMM conv family)",
         "launches_per_step": tc_launch, "avg_launch_us": tc_ms * 1e3 / max(tc_launch, 1),
         "algorithmic_bytes_per_launch": tc_bytes / max(tc_launch, 1),
         "algorithmic_ops_per_byte": ai,

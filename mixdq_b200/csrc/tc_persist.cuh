@@ -178,7 +178,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-// profiling stamps (p.dbg != nullptr): 16 slots of %globaltimer per CTA, steady-state tile 2 / 3
+// profiling stamps (p.dbg != nullptr): 16 slots of %globaltimer per CTA; tile dbg_tl = dbg_mode >> 4
+// of every CTA (and the one after it)
 #define TP_DBG(cond, slot)                                                        \
   do {                                                                            \
     if (p.dbg != nullptr && (cond)) p.dbg[blockIdx.x * 16 + (slot)] = gtime_ns(); \
@@ -217,6 +218,8 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t dbg_tl = static_cast<uint32_t>(p.dbg_mode) >> 4;   // which tile of a CTA is stamped
+  TP_DBG(threadIdx.x == 0, 11);                                      // kernel entry
   pdl_launch_dependents();
 
   // ---- tile schedule: groups of CS vertically adjacent tiles, m fastest; every cluster takes a
@@ -328,7 +331,7 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t it = 0;                                     // k-block iterations issued so far
     int pre = 0;
     // profiling only (results are garbage): bit1 = no TMA loads, bit0 = no MMA issue
-    const bool skip_tma = !W4 && (p.dbg_mode & 2) != 0;
+    const bool skip_tma = !W4 && (p.dbg_mode & 2) != 0;   // (bits 4.. select the stamped tile)
     if (g_begin < g_end && !skip_tma) {
       const Tile t0 = tile_of(g_begin);
       pre = num_kb < STAGES ? num_kb : STAGES;
@@ -341,7 +344,9 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       __syncwarp();
     }
+    TP_DBG(lane == 0, 12);                               // setup done, first weights in flight
     pdl_wait();
+    TP_DBG(lane == 0, 13);                               // dependency wait passed
     for (int g = g_begin; g < g_end; ++g) {
       const Tile t = tile_of(g);
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -378,9 +383,9 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t d_tmem = tmem_base + slot * TP_SLOT_COLS;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int stage = it % STAGES;
-        TP_DBG(lane == 0 && kb == 0 && (tl == 2 || tl == 3), tl == 2 ? 7 : 9);   // tile's first wait
+        TP_DBG(lane == 0 && kb == 0 && (tl == dbg_tl || tl == dbg_tl + 1), tl == dbg_tl ? 7 : 9);   // tile's first wait
         mbar_wait(&full_bar[stage], (it / STAGES) & 1u);
-        TP_DBG(lane == 0 && kb == 0 && tl == 2, 10);                             // first stage landed
+        TP_DBG(lane == 0 && kb == 0 && tl == dbg_tl, 10);                             // first stage landed
         tc_fence_after();
         if (elect_one()) {
           const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(stage * (L::A_BYTES >> 4));
@@ -403,7 +408,7 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
         }
         __syncwarp();
-        TP_DBG(lane == 0 && kb == num_kb - 1 && tl == 2, 8);                     // last MMA issued
+        TP_DBG(lane == 0 && kb == num_kb - 1 && tl == dbg_tl, 8);                     // last MMA issued
       }
     }
     }
@@ -549,11 +554,11 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         ++nstore;
       };
 
-      TP_DBG(threadIdx.x == 64 && tl == 2, 0);       // epilogue of tile 2 starts waiting
+      TP_DBG(threadIdx.x == 64 && tl == dbg_tl, 0);       // epilogue of tile 2 starts waiting
       if (KIND == KIND_GEGLU) {
         // 32 accumulator columns = 16 value + 16 gate columns of the same 16 outputs
         mbar_wait(&tmem_full[slot], (tl >> 1) & 1u);
-        TP_DBG(threadIdx.x == 64 && tl == 2, 1);
+        TP_DBG(threadIdx.x == 64 && tl == dbg_tl, 1);
         tc_fence_after();
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; ++c) {
@@ -603,14 +608,14 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         };
         if (has_ca || has_rs) fetch_tail(c_lo);
         mbar_wait(&tmem_full[slot], (tl >> 1) & 1u);
-        TP_DBG(threadIdx.x == 64 && tl == 2, 1);       // accumulator ready
+        TP_DBG(threadIdx.x == 64 && tl == dbg_tl, 1);       // accumulator ready
         tc_fence_after();
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; ++c) {
           uint32_t v[16];
           tmem_ld_32x16(t_base + c * CH, v);
           tmem_ld_wait();
-          TP_DBG(threadIdx.x == 64 && tl == 2 && c == c_lo, 2);   // first chunk in registers
+          TP_DBG(threadIdx.x == 64 && tl == dbg_tl && c == c_lo, 2);   // first chunk in registers
           if (c == c_hi - 1) {                         // this warp has read its part of the slot
             tc_fence_before();
             __syncwarp();
@@ -644,12 +649,12 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
             fetch_tail(c + 1);
           }
-          TP_DBG(threadIdx.x == 64 && tl == 2 && c == c_lo, 3);   // first chunk dequantised
+          TP_DBG(threadIdx.x == 64 && tl == dbg_tl && c == c_lo, 3);   // first chunk dequantised
           store_chunk(y, t.n_tile0 + c * CH);
-          TP_DBG(threadIdx.x == 64 && tl == 2 && c == c_lo, 4);   // first chunk staged / sent
+          TP_DBG(threadIdx.x == 64 && tl == dbg_tl && c == c_lo, 4);   // first chunk staged / sent
         }
       }
-      TP_DBG(threadIdx.x == 64 && (tl == 2 || tl == 3), tl == 2 ? 5 : 6);   // tile drained
+      TP_DBG(threadIdx.x == 64 && (tl == dbg_tl || tl == dbg_tl + 1), tl == dbg_tl ? 5 : 6);   // tile drained
     }
     if (d_tma && lane == 0) bulk_wait_all();           // every store has completed
     __syncwarp();
@@ -720,6 +725,7 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   __syncwarp();
   __syncthreads();
+  TP_DBG(threadIdx.x == 0, 14);                          // all roles done
   if (PAIR) cluster_sync_all();        // no CTA exits (or frees TMEM) while the pair still runs
   if (warp == 1) {
     tc_fence_after();
