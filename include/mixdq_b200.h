@@ -359,6 +359,34 @@ int mixdq_gn_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int NB, int HW
                               int silu, int8_t* q, mixdq_half_t* y_out, float* scale_out,
                               float* zp_out, void* ws, mixdq_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Producers with STATIC (PTQ-checkpoint) scales of the consumer: the reference quantises the
+ * fp16 output of the producing op with the layer's stored parameters
+ * (mixdq_extension.op.quantize_per_tensor_to_int8 at nn/Linear.py:154-176, nn/Conv2d.py:282-347;
+ * formula csrc/quant_dequant/quantize_kernel.cu:20-24). Here the producer applies that formula to
+ * its own fp16-rounded values before they leave the SM: q = sat8(rint(fma(y, *scale_inv, *zp))),
+ * bit-identical to the dynamic-path producer followed by mixdq_quant_i8_static on its y_out.
+ *   ln    : one kernel                     (LayerNorm -> to_q/k/v, attn2.to_q, ff.net.0.proj)
+ *   gn    : statistics kernel + apply kernel (GroupNorm[+SiLU] -> resnet convs, proj_in)
+ *   geglu : the GEGLU GEMM (rows interleaved as for mixdq_gemm_w8a8_geglu_f16_dyn; w_bits = 8:
+ *           int8 codes, 4: packed nibbles) writes Q [M][N2/2] int8 (row pitch ldq, % 16) -> ff.net.2
+ * Same shape restrictions as the dynamic entry points; q dense.
+ * ---------------------------------------------------------------------------------------- */
+int mixdq_ln_quant_i8_static(const mixdq_half_t* x, int64_t ldx, int M, int C,
+                             const mixdq_half_t* gamma, const mixdq_half_t* beta, float eps,
+                             const float* scale_inv, const float* zp, int8_t* q, void* ws,
+                             mixdq_stream_t stream);
+int mixdq_gn_quant_i8_static(const mixdq_half_t* x, int64_t ldx, int NB, int HW, int C, int G,
+                             const mixdq_half_t* gamma, const mixdq_half_t* beta, float eps,
+                             int silu, const float* scale_inv, const float* zp, int8_t* q,
+                             void* ws, mixdq_stream_t stream);
+int mixdq_gemm_geglu_i8_static(const int8_t* A, int64_t lda, const void* W_il, int w_bits,
+                               const float* w_scale_il, const float* wsum_il,
+                               const float* a_scale, const float* a_zp,
+                               const mixdq_half_t* bias_il, const float* q_scale_inv,
+                               const float* q_zp, int8_t* Q, int64_t ldq, int M, int N2, int K,
+                               void* ws, mixdq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,7 @@ ABI_SYMBOLS = [
     "mixdq_gemm_w8a8_geglu_f16_dyn", "mixdq_quant_i8_premm",
     "mixdq_gemm_w4a8_f16_dyn_res", "mixdq_gemm_w4a8_geglu_f16_dyn", "mixdq_conv_w4a8_f16",
     "mixdq_conv_w4a8_f16_dyn", "mixdq_quant_i8_dynamic_bits", "mixdq_quant_i8_static_range", "mixdq_minmax_f16",
+    "mixdq_ln_quant_i8_static", "mixdq_gn_quant_i8_static", "mixdq_gemm_geglu_i8_static",
 ]
 
 
@@ -142,6 +143,14 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mixdq_gn_quant_i8_dynamic.restype = c_int
     lib.mixdq_gn_quant_i8_dynamic.argtypes = [P, c_int64, c_int, c_int, c_int, c_int, P, P,
                                               c_float, c_int, P, P, P, P, P, P]
+    lib.mixdq_ln_quant_i8_static.restype = c_int
+    lib.mixdq_ln_quant_i8_static.argtypes = [P, c_int64, c_int, c_int, P, P, c_float, P, P, P, P, P]
+    lib.mixdq_gn_quant_i8_static.restype = c_int
+    lib.mixdq_gn_quant_i8_static.argtypes = [P, c_int64, c_int, c_int, c_int, c_int, P, P,
+                                             c_float, c_int, P, P, P, P, P]
+    lib.mixdq_gemm_geglu_i8_static.restype = c_int
+    lib.mixdq_gemm_geglu_i8_static.argtypes = [P, c_int64, P, c_int, P, P, P, P, P, P, P, P,
+                                               c_int64, c_int, c_int, c_int, P, P]
 
 
 def load() -> ctypes.CDLL:

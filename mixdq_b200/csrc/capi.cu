@@ -405,10 +405,19 @@ static int geglu_common(const int8_t* A, int64_t lda, const int8_t* W_il,
                         const float* w_scale_il, const float* wsum_il, const float* a_scale,
                         const float* a_zp, const mixdq_half_t* bias_il, mixdq_half_t* Y,
                         int64_t ldy, int M, int N2, int K, void* ws, mixdq_stream_t stream,
-                        bool w4) {
+                        bool w4, int8_t* Q = nullptr, int64_t ldq = 0,
+                        const float* q_inv = nullptr, const float* q_zp = nullptr) {
+  // Q != nullptr: static scales of the consumer — int8 codes [M][N2/2] (row pitch ldq) instead of
+  // the fp16 Y + min/max partials
   if (M < 0 || N2 <= 0 || K <= 0 || !W_il || !w_scale_il || !wsum_il || !a_scale || !a_zp || !ws)
     return MIXDQ_ERR_INVALID_ARG;
   if (M == 0) return MIXDQ_OK;
+  if (Q) {
+    if (!A || lda < K || ldq < N2 / 2 || !q_inv || !q_zp) return MIXDQ_ERR_INVALID_ARG;
+    if ((ldq % 16) || !al16(Q)) return MIXDQ_ERR_ALIGNMENT;
+    Y = reinterpret_cast<mixdq_half_t*>(Q);   // never written; keeps the pointer checks below simple
+    ldy = ldq;
+  }
   if (!A || !Y || lda < K || ldy < N2 / 2) return MIXDQ_ERR_INVALID_ARG;
   if ((K % (w4 ? 32 : 16)) || (N2 % 32) || (lda % 16) || (ldy % 8) || !al16(A) || !al16(W_il) ||
       !al16(Y))
@@ -453,6 +462,7 @@ static int geglu_common(const int8_t* A, int64_t lda, const int8_t* W_il,
   p.bias = reinterpret_cast<const __half*>(bias_il);
   p.D = reinterpret_cast<__half*>(Y); p.ldd = ldy;
   p.mm_partial = static_cast<DynWs*>(ws)->partial;   // address arithmetic only (device pointer)
+  p.q_out = Q; p.ldq = ldq; p.q_inv = q_inv; p.q_zp = q_zp;
   if (pbn) {
     // one min / max partial per persistent CTA
     p.tiles_m = m_tiles; p.tiles_n = (N2 + pbn - 1) / pbn;
@@ -463,8 +473,13 @@ static int geglu_common(const int8_t* A, int64_t lda, const int8_t* W_il,
     if (groups < clusters) clusters = groups;
     partial_count_slot(ws) = static_cast<int>(clusters * pcs);
     CUtensorMap tmD;
-    if (!make_tmap_out(&tmD, Y, N2 / 2, M, ldy)) return MIXDQ_ERR_CUDA;
-    p.d_tma = 1; p.d_cols = N2 / 2;
+    if (Q) {
+      tmD = tmA;                               // unused: the codes leave through plain stores
+      p.d_tma = 0; p.d_cols = N2 / 2;
+    } else {
+      if (!make_tmap_out(&tmD, Y, N2 / 2, M, ldy)) return MIXDQ_ERR_CUDA;
+      p.d_tma = 1; p.d_cols = N2 / 2;
+    }
     g_last_path = w4 ? "tcgen05-w4-geglu-persist" : "tcgen05-geglu-persist";
     return persist_launch(KIND_GEGLU, pbn, w4, pcs, tmA, tmW, tmD, p, static_cast<cudaStream_t>(stream));
   }
@@ -510,6 +525,19 @@ extern "C" int mixdq_gemm_w4a8_geglu_f16_dyn(const int8_t* A, int64_t lda,
                                              void* ws, mixdq_stream_t stream) {
   return geglu_common(A, lda, reinterpret_cast<const int8_t*>(W_il_packed), w_scale_il, wsum_il,
                       a_scale, a_zp, bias_il, Y, ldy, M, N2, K, ws, stream, true);
+}
+
+extern "C" int mixdq_gemm_geglu_i8_static(const int8_t* A, int64_t lda, const void* W_il,
+                                          int w_bits, const float* w_scale_il,
+                                          const float* wsum_il, const float* a_scale,
+                                          const float* a_zp, const mixdq_half_t* bias_il,
+                                          const float* q_scale_inv, const float* q_zp, int8_t* Q,
+                                          int64_t ldq, int M, int N2, int K, void* ws,
+                                          mixdq_stream_t stream) {
+  if (!Q || (w_bits != 8 && w_bits != 4)) return MIXDQ_ERR_INVALID_ARG;
+  return geglu_common(A, lda, static_cast<const int8_t*>(W_il), w_scale_il, wsum_il, a_scale, a_zp,
+                      bias_il, nullptr, 0, M, N2, K, ws, stream, w_bits == 4, Q, ldq, q_scale_inv,
+                      q_zp);
 }
 
 extern "C" int mixdq_gemm_w8a8_f16_dyn_res(const int8_t* A, int64_t lda, const int8_t* W,

@@ -277,4 +277,28 @@ __device__ __forceinline__ __half geglu_half(__half h, __half g) {
   return __float2half_rn(geglu_f32(__half2float(h), __half2float(g)));
 }
 
+// two saturated s8 from two s32, merged above the low half of c: d = (c << 16) | (sat8(a) << 8) | sat8(b)
+__device__ __forceinline__ uint32_t pack_sat_s8(int a, int b, uint32_t c) {
+  uint32_t d;
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// the reference's STATIC quantiser on 8 halves (quantize_kernel.cu:20-24: one FMA, round to
+// nearest even, saturate to int8), packed by the saturating cvt.pack
+__device__ __forceinline__ uint2 static_quant8(const int4& raw, float inv, float zp) {
+  const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+  int c[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h2[i]);
+    c[2 * i] = __float2int_rn(__fmaf_rn(f.x, inv, zp));
+    c[2 * i + 1] = __float2int_rn(__fmaf_rn(f.y, inv, zp));
+  }
+  uint2 out;
+  out.x = pack_sat_s8(c[1], c[0], pack_sat_s8(c[3], c[2], 0u));
+  out.y = pack_sat_s8(c[5], c[4], pack_sat_s8(c[7], c[6], 0u));
+  return out;
+}
+
 }  // namespace mixdq

@@ -303,7 +303,10 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
                 const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps,
                 int8_t* __restrict__ q, __half* __restrict__ y_out, DynWs* __restrict__ ws,
                 float* __restrict__ scale_out, float* __restrict__ zp_out, int ctas_per_image,
-                int rows_per_cta, int stash_rows) {
+                int rows_per_cta, int stash_rows, int8_t* __restrict__ qs,
+                const float* __restrict__ s_inv, const float* __restrict__ s_zp) {
+  // qs != nullptr (MODE 2 only): STATIC activation scales — the apply pass quantises with the
+  // consumer's checkpoint parameters instead of writing fp16 + min/max for a quantise pass
   extern __shared__ int4 stash[];   // [stash_rows][C/8]
   __shared__ float s_mean[32], s_rstd[32];
   __shared__ int s_last;
@@ -403,12 +406,13 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
     s_rstd[threadIdx.x] = rsqrtf(static_cast<float>(var) + eps);
   }
   __syncthreads();
-  // the last CTA to have read the statistics re-zeroes them for the next call (MODE 2: the
-  // quantise pass that follows clears them instead — nobody waits here)
-  if (MODE == 2) s_last = 0;
-  if (MODE != 2 && threadIdx.x == 0) s_last = (atomicAdd(&ws->done2, 1u) == gridDim.x - 1) ? 1 : 0;
+  // the last CTA to have read the statistics re-zeroes them for the next call (MODE 2 with
+  // dynamic scales: the quantise pass that follows clears them instead — nobody waits here)
+  const bool rezero = (MODE != 2) || (qs != nullptr);   // static apply pass: no quantise pass follows
+  if (!rezero) s_last = 0;
+  if (rezero && threadIdx.x == 0) s_last = (atomicAdd(&ws->done2, 1u) == gridDim.x - 1) ? 1 : 0;
   __syncthreads();
-  if (MODE != 2 && s_last) {
+  if (rezero && s_last) {
     for (int i = threadIdx.x; i < NB * G * 2; i += kFqThreads) ws->gsum[i] = 0ull;
     __threadfence();
     __syncthreads();
@@ -421,6 +425,7 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
 
   // ---- phase 1: normalise (+SiLU) -> fp16 -> stash, min/max ----
   float mn = 0.f, mx = 0.f;
+  const float q_inv = (MODE == 2 && qs) ? __ldg(s_inv) : 0.f, q_zp = (MODE == 2 && qs) ? __ldg(s_zp) : 0.f;
   {
     // flat (row, chunk) items of this CTA, four 16-byte loads in flight per thread (a warp-per-row
     // loop left each lane with one or two dependent load -> compute -> store chains per row)
@@ -442,6 +447,11 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
         const int it = it0 + u * kFqThreads;
         if (it >= items) break;
         const int4 y = gn_vec8<SILU>(raw[u], 8 * c[u], cpg, s_mean, s_rstd, gamma, beta);
+        if (MODE == 2 && qs != nullptr) {
+          reinterpret_cast<uint2*>(qs + (static_cast<int64_t>(n) * HW + row0 + lr[u]) * C)[c[u]] =
+              static_quant8(y, q_inv, q_zp);
+          continue;
+        }
         minmax_vec8(y, mn, mx);
         if (MODE == 0 && lr[u] < stash_rows) stash[it] = y;
         if (y_out)
@@ -449,6 +459,7 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
       }
     }
   }
+  if (MODE == 2 && qs != nullptr) return;
   if (MODE == 2) {
     // store this CTA's min / max partial (quant2.cu protocol) and stop: quantisation is the next
     // kernel's job
@@ -503,7 +514,8 @@ int mixdq_q2_premm(const __half* x, int64_t numel, int8_t* q, float* scale_out, 
                    cudaStream_t st);
 int mixdq_q2_ln(const __half* x, int64_t ldx, int M, int C, const __half* gamma,
                 const __half* beta, float eps, int8_t* q, __half* y, float* scale_out,
-                float* zp_out, void* ws, cudaStream_t st);
+                float* zp_out, void* ws, cudaStream_t st, int8_t* qs = nullptr,
+                const float* s_inv = nullptr, const float* s_zp = nullptr);
 bool mixdq_two_pass_enabled();
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -669,17 +681,18 @@ extern "C" int mixdq_quant_i8_dynamic_rows(const mixdq_half_t* x, int64_t ldx, i
   return MIXDQ_OK;
 }
 
-extern "C" int mixdq_gn_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int NB, int HW, int C,
-                                         int G, const mixdq_half_t* gamma,
-                                         const mixdq_half_t* beta, float eps, int silu, int8_t* q,
-                                         mixdq_half_t* y_out, float* scale_out, float* zp_out,
-                                         void* ws, mixdq_stream_t stream) {
+// qs != nullptr: STATIC scales — statistics kernel, then an apply kernel that quantises with
+// (*s_inv, *s_zp) straight from its registers (q, y_out, scale_out, zp_out unused)
+static int gn_entry(const mixdq_half_t* x, int64_t ldx, int NB, int HW, int C, int G,
+                    const mixdq_half_t* gamma, const mixdq_half_t* beta, float eps, int silu,
+                    int8_t* q, mixdq_half_t* y_out, float* scale_out, float* zp_out, void* ws,
+                    mixdq_stream_t stream, int8_t* qs, const float* s_inv, const float* s_zp) {
   // q == nullptr (with y_out): normalise only, the caller quantises y with static parameters
   if (NB <= 0 || HW <= 0 || C <= 0 || G <= 0 || !x || !gamma || !beta || !ws || ldx < C ||
-      (q ? (!scale_out || !zp_out) : !y_out))
+      (qs ? (!s_inv || !s_zp) : (q ? (!scale_out || !zp_out) : !y_out)))
     return MIXDQ_ERR_INVALID_ARG;
   if ((C & 7) || (ldx & 7) || !al16(x) || !al16(gamma) || !al16(beta) || (q && !al16(q)) ||
-      (y_out && !al16(y_out)))
+      (y_out && !al16(y_out)) || (qs && !al16(qs)))
     return MIXDQ_ERR_ALIGNMENT;
   const int cpg = C / G;
   // a 16-byte chunk of 8 channels must touch at most two groups
@@ -696,7 +709,7 @@ extern "C" int mixdq_gn_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int
     attr = true;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool three_kernels = y_out && mixdq_two_pass_enabled() &&
+  const bool three_kernels = (qs || (y_out && mixdq_two_pass_enabled())) &&
                              static_cast<int64_t>(NB) * HW * (C >> 3) < (1ll << 31);
   int cpi = kNumSm / NB;                       // CTAs per image, all co-resident
   const int max_useful = (HW + 3) / 4;         // >= 4 rows per CTA
@@ -729,11 +742,13 @@ extern "C" int mixdq_gn_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int
     cpi1 = (HW + rpc1 - 1) / rpc1;
     const int g1 = NB * cpi1 < NB * cpi ? NB * cpi1 : NB * cpi;
     if (launch_pdl(k1, g1, kFqThreads, scratch, st, xh, ldx, NB, HW, C, G, gh, bh, eps, q, yh,
-                   w, scale_out, zp_out, cpi1, rpc1, 0) != cudaSuccess)
+                   w, scale_out, zp_out, cpi1, rpc1, 0, static_cast<int8_t*>(nullptr), static_cast<const float*>(nullptr),
+                   static_cast<const float*>(nullptr)) != cudaSuccess)
       return MIXDQ_ERR_CUDA;
     if (launch_pdl(k2, NB * cpi, kFqThreads, 0, st, xh, ldx, NB, HW, C, G, gh, bh, eps, q, yh, w,
-                   scale_out, zp_out, cpi, rpc, 0) != cudaSuccess)
+                   scale_out, zp_out, cpi, rpc, 0, qs, s_inv, s_zp) != cudaSuccess)
       return MIXDQ_ERR_CUDA;
+    if (qs != nullptr) return MIXDQ_OK;   // the apply kernel's last CTA cleared the accumulators
     if (q == nullptr) {
       // GroupNorm only (static-scale callers): the quantise pass that normally re-zeroes the
       // statistics accumulators does not run, so clear them here (a memset node under capture)
@@ -743,12 +758,47 @@ extern "C" int mixdq_gn_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int
     return mixdq_q2_premm(yh, static_cast<int64_t>(NB) * HW * C, q, scale_out, zp_out, ws,
                           NB * cpi, w->gsum, NB * G * 2, st);
   }
-  if (q == nullptr) return MIXDQ_ERR_UNSUPPORTED;
+  if (q == nullptr || qs != nullptr) return MIXDQ_ERR_UNSUPPORTED;
   auto gk = silu ? gn_quant_kernel<true, 0> : gn_quant_kernel<false, 0>;
   if (launch_pdl(gk, NB * cpi, kFqThreads, smem, st, reinterpret_cast<const __half*>(x), ldx, NB, HW,
                  C, G, reinterpret_cast<const __half*>(gamma), reinterpret_cast<const __half*>(beta),
                  eps, q, reinterpret_cast<__half*>(y_out), static_cast<DynWs*>(ws), scale_out,
-                 zp_out, cpi, rpc, static_cast<int>(srows)) != cudaSuccess)
+                 zp_out, cpi, rpc, static_cast<int>(srows), static_cast<int8_t*>(nullptr), static_cast<const float*>(nullptr),
+                   static_cast<const float*>(nullptr)) != cudaSuccess)
     return MIXDQ_ERR_CUDA;
   return MIXDQ_OK;
+}
+
+extern "C" int mixdq_gn_quant_i8_dynamic(const mixdq_half_t* x, int64_t ldx, int NB, int HW, int C,
+                                         int G, const mixdq_half_t* gamma,
+                                         const mixdq_half_t* beta, float eps, int silu, int8_t* q,
+                                         mixdq_half_t* y_out, float* scale_out, float* zp_out,
+                                         void* ws, mixdq_stream_t stream) {
+  return gn_entry(x, ldx, NB, HW, C, G, gamma, beta, eps, silu, q, y_out, scale_out, zp_out, ws,
+                  stream, nullptr, nullptr, nullptr);
+}
+
+extern "C" int mixdq_gn_quant_i8_static(const mixdq_half_t* x, int64_t ldx, int NB, int HW, int C,
+                                        int G, const mixdq_half_t* gamma, const mixdq_half_t* beta,
+                                        float eps, int silu, const float* scale_inv,
+                                        const float* zp, int8_t* q, void* ws,
+                                        mixdq_stream_t stream) {
+  if (!q) return MIXDQ_ERR_INVALID_ARG;
+  return gn_entry(x, ldx, NB, HW, C, G, gamma, beta, eps, silu, nullptr, nullptr, nullptr, nullptr,
+                  ws, stream, q, scale_inv, zp);
+}
+
+extern "C" int mixdq_ln_quant_i8_static(const mixdq_half_t* x, int64_t ldx, int M, int C,
+                                        const mixdq_half_t* gamma, const mixdq_half_t* beta,
+                                        float eps, const float* scale_inv, const float* zp,
+                                        int8_t* q, void* ws, mixdq_stream_t stream) {
+  if (M <= 0 || C <= 0 || !x || !gamma || !beta || !ws || ldx < C || !q || !scale_inv || !zp)
+    return MIXDQ_ERR_INVALID_ARG;
+  if ((C & 7) || (ldx & 7) || !al16(x) || !al16(gamma) || !al16(beta) || !al16(q))
+    return MIXDQ_ERR_ALIGNMENT;
+  if (C > kLnMaxChunks * 256) return MIXDQ_ERR_UNSUPPORTED;
+  return mixdq_q2_ln(reinterpret_cast<const __half*>(x), ldx, M, C,
+                     reinterpret_cast<const __half*>(gamma), reinterpret_cast<const __half*>(beta),
+                     eps, nullptr, nullptr, nullptr, nullptr, ws, static_cast<cudaStream_t>(stream),
+                     q, scale_inv, zp);
 }

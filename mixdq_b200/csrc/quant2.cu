@@ -32,13 +32,6 @@ __device__ __noinline__ float exact_round_quot(float x, float delta) {
   return rintf(__fdiv_rn(x, delta));
 }
 
-// two saturated s8 from two s32, merged above the low half of c: d = (c << 16) | (sat8(a) << 8) | sat8(b)
-__device__ __forceinline__ uint32_t pack_sat_s8(int a, int b, uint32_t c) {
-  uint32_t d;
-  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
-
 // 8 halves -> 8 codes in ~7 instructions per element (it was 21: FRND / F2I / clamp / shift / mask
 // per element made the quantise pass issue-bound at batch >= 8, ncu: 250 warp instructions per
 // vector against 126 MB of traffic per launch):
@@ -290,7 +283,10 @@ template <int MAXCH, int NT>
 __global__ void __launch_bounds__(NT)
 ln_minmax_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
                  const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps,
-                 __half* __restrict__ y, DynWs* __restrict__ ws) {
+                 __half* __restrict__ y, DynWs* __restrict__ ws, int8_t* __restrict__ qs,
+                 const float* __restrict__ s_inv, const float* __restrict__ s_zp) {
+  // qs != nullptr: STATIC activation scales — the normalised fp16 values are quantised right here
+  // with the consumer's checkpoint parameters (no fp16 round trip, no min/max, no second kernel)
   QDbg dbg;
   dbg.begin(ws);
   pdl_launch_dependents();
@@ -315,6 +311,7 @@ ln_minmax_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
           warm(reinterpret_cast<const int4*>(x + static_cast<int64_t>(r0) * ldx) + lane + 32 * i);
     }
   }
+  const float q_inv = qs ? __ldg(s_inv) : 0.0f, q_zp = qs ? __ldg(s_zp) : 0.0f;   // checkpoint constants
   pdl_wait();
   dbg.waited(ws);
   __half2 mn = __float2half2_rn(0.0f), mx = mn;
@@ -378,13 +375,17 @@ ln_minmax_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
           o2[j] = __floats2half2_rn(fmaf(g.x, rstd * (f.x - mean), b.x),
                                     fmaf(g.y, rstd * (f.y - mean), b.y));
         }
-        hminmax8(out, mn, mx);
-        yrow[c] = out;
+        if (qs != nullptr) {
+          reinterpret_cast<uint2*>(qs + static_cast<int64_t>(r) * C)[c] = static_quant8(out, q_inv, q_zp);
+        } else {
+          hminmax8(out, mn, mx);
+          yrow[c] = out;
+        }
       }
     }
   }
   dbg.stamp(2);
-  publish_partial<NT>(ws, mn, mx);
+  if (qs == nullptr) publish_partial<NT>(ws, mn, mx);
   dbg.stamp(3);
   dbg.end(ws);
 }
@@ -487,26 +488,27 @@ int mixdq_q2_premm(const __half* x, int64_t numel, int8_t* q, float* scale_out, 
 // LayerNorm -> fp16 y (caller's buffer) + per-CTA min/max, then pass 2 on y
 int mixdq_q2_ln(const __half* x, int64_t ldx, int M, int C, const __half* gamma,
                 const __half* beta, float eps, int8_t* q, __half* y, float* scale_out,
-                float* zp_out, void* ws, cudaStream_t st) {
+                float* zp_out, void* ws, cudaStream_t st, int8_t* qs, const float* s_inv,
+                const float* s_zp) {
   if (static_cast<int64_t>(M) * (C >> 3) > kMaxItems) return MIXDQ_ERR_UNSUPPORTED;
   DynWs* w = static_cast<DynWs*>(ws);
   cudaError_t e;
   int g1;
-  if (y == nullptr) return MIXDQ_ERR_UNSUPPORTED;          // the two-pass form needs the scratch
+  if (y == nullptr && qs == nullptr) return MIXDQ_ERR_UNSUPPORTED;   // the two-pass form needs the scratch
   if (M <= 512) {
     g1 = (M + 1) / 2;
     e = (C <= 5 * 256)
-            ? launch_pdl(ln_minmax_kernel<5, 64>, g1, 64, 0, st, x, ldx, M, C, gamma, beta, eps, y, w)
-            : launch_pdl(ln_minmax_kernel<8, 64>, g1, 64, 0, st, x, ldx, M, C, gamma, beta, eps, y, w);
+            ? launch_pdl(ln_minmax_kernel<5, 64>, g1, 64, 0, st, x, ldx, M, C, gamma, beta, eps, y, w, qs, s_inv, s_zp)
+            : launch_pdl(ln_minmax_kernel<8, 64>, g1, 64, 0, st, x, ldx, M, C, gamma, beta, eps, y, w, qs, s_inv, s_zp);
   } else {
     g1 = (M + 7) / 8;
     if (g1 > 512) g1 = 512;
     e = (C <= 5 * 256)
-            ? launch_pdl(ln_minmax_kernel<5, 256>, g1, 256, 0, st, x, ldx, M, C, gamma, beta, eps, y, w)
-            : launch_pdl(ln_minmax_kernel<8, 256>, g1, 256, 0, st, x, ldx, M, C, gamma, beta, eps, y, w);
+            ? launch_pdl(ln_minmax_kernel<5, 256>, g1, 256, 0, st, x, ldx, M, C, gamma, beta, eps, y, w, qs, s_inv, s_zp)
+            : launch_pdl(ln_minmax_kernel<8, 256>, g1, 256, 0, st, x, ldx, M, C, gamma, beta, eps, y, w, qs, s_inv, s_zp);
   }
   if (e != cudaSuccess) return MIXDQ_ERR_CUDA;
-  if (q == nullptr) return MIXDQ_OK;                        // LayerNorm only (static-scale callers)
+  if (q == nullptr) return MIXDQ_OK;       // LayerNorm only / LayerNorm + static quantisation
   return mixdq_q2_premm(y, static_cast<int64_t>(M) * C, q, scale_out, zp_out, ws, g1, nullptr, 0, st);
 }
 

@@ -101,6 +101,12 @@ struct TcParams {
   int64_t ldd;
   int32_t* acc_out;       // optional raw accumulator dump [rows][N]
   float2* mm_partial;     // KIND_GEGLU: per-CTA {min(0, min), max(0, max)} of the fp16 output
+  // KIND_GEGLU with STATIC scales of the consumer (ff.net.2): the fp16 GEGLU values are quantised
+  // in the epilogue, q_out[row][col] = sat8(rint(fma(y, *q_inv, *q_zp))), and D / mm_partial unused
+  int8_t* q_out;
+  int64_t ldq;
+  const float* q_inv;
+  const float* q_zp;
   int32_t* ws;            // split-K exchange workspace: [CTA][BN/4][128][4] int32 (splits > 1)
   unsigned long long* dbg; // optional phase timestamps (globaltimer ns), 8 slots per CTA
   int dbg_mode;            // profiling only: bit0 = skip MMA issue, bit1 = skip TMA loads
@@ -626,6 +632,8 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int i = 0; i < 2; ++i)
         ro[i] = row_info<KIND>(p, quarter * 32 + i * 16 + (lane >> 1), m0, tn0, tp0, tq0);
       float mn = 0.f, mx = 0.f;
+      const bool to_q = p.q_out != nullptr;
+      const float q_inv = to_q ? __ldg(p.q_inv) : 0.f, q_zp = to_q ? __ldg(p.q_zp) : 0.f;
       wait_accumulators();
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; ++c) {
@@ -660,12 +668,20 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             mn = fminf(mn, f);
             mx = fmaxf(mx, f);
           }
-          uint4* dst = reinterpret_cast<uint4*>(stage_out + row * L::OUT_PITCH + c * 32);
-          dst[0] = reinterpret_cast<const uint4*>(y)[0];
-          dst[1] = reinterpret_cast<const uint4*>(y)[1];
+          if (to_q) {
+            // 16 codes = 16 bytes of this lane's row, straight to global memory
+            const uint2 lo = static_quant8(reinterpret_cast<const int4*>(y)[0], q_inv, q_zp);
+            const uint2 hi = static_quant8(reinterpret_cast<const int4*>(y)[1], q_inv, q_zp);
+            *reinterpret_cast<uint4*>(p.q_out + ri.out_row * p.ldq + ((n_tile0 + c * 32) >> 1)) =
+                make_uint4(lo.x, lo.y, hi.x, hi.y);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(stage_out + row * L::OUT_PITCH + c * 32);
+            dst[0] = reinterpret_cast<const uint4*>(y)[0];
+            dst[1] = reinterpret_cast<const uint4*>(y)[1];
+          }
         }
         __syncwarp();
-        if (cols_ok) {
+        if (cols_ok && !to_q) {
           const int64_t ocol = ((n_tile0 + c * 32) >> 1) + (lane & 1) * 8;
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
@@ -687,7 +703,7 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       float* s_mm = reinterpret_cast<float*>(smem + ((L::OUT_BYTES + 15) & ~15));
       if (lane == 0) { s_mm[(warp - 2) * 2] = mn; s_mm[(warp - 2) * 2 + 1] = mx; }
       epi_bar_sync();
-      if (threadIdx.x == 64) {
+      if (threadIdx.x == 64 && !to_q) {
 #pragma unroll
         for (int w = 0; w < 8; ++w) { mn = fminf(mn, s_mm[2 * w]); mx = fmaxf(mx, s_mm[2 * w + 1]); }
         p.mm_partial[blockIdx.y * gridDim.x + blockIdx.x] = make_float2(mn, mx);

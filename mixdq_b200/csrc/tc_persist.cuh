@@ -436,6 +436,8 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const bool d_tma = p.d_tma != 0;
     int cur_n = -1;
     float mn = 0.f, mx = 0.f;              // GEGLU: running min / max of this CTA's outputs
+    const bool to_q = (KIND == KIND_GEGLU) && p.q_out != nullptr;   // GEGLU -> int8, static scales
+    const float q_inv = to_q ? __ldg(p.q_inv) : 0.f, q_zp = to_q ? __ldg(p.q_zp) : 0.f;
     uint32_t tl = 0, nstore = 0;           // nstore: chunks staged so far (staging tile = parity)
     for (int g = g_begin; g < g_end; ++g, ++tl) {
       const Tile t = tile_of(g);
@@ -589,7 +591,17 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               mx = fmaxf(mx, f);
             }
           }
-          store_chunk(y, (t.n_tile0 + c * 32) >> 1);
+          if (to_q) {
+            // static scales of the consumer: 16 codes of this lane's row straight to global memory
+            if (ri.ok && (t.n_tile0 + c * 32 + 32 <= p.N)) {
+              const uint2 lo = static_quant8(reinterpret_cast<const int4*>(y)[0], q_inv, q_zp);
+              const uint2 hi = static_quant8(reinterpret_cast<const int4*>(y)[1], q_inv, q_zp);
+              *reinterpret_cast<uint4*>(p.q_out + ri.out_row * p.ldq + ((t.n_tile0 + c * 32) >> 1)) =
+                  make_uint4(lo.x, lo.y, hi.x, hi.y);
+            }
+          } else {
+            store_chunk(y, (t.n_tile0 + c * 32) >> 1);
+          }
         }
       } else {
         // operands of the fused tails, fetched one chunk ahead (the first chunk's while the MMAs
@@ -669,7 +681,7 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       float* s_mm = reinterpret_cast<float*>(smem + L::OFF_MM);
       if (lane == 0) { s_mm[ew * 2] = mn; s_mm[ew * 2 + 1] = mx; }
       named_bar_sync(1, 32 * TP_EPI_WARPS);
-      if (threadIdx.x == 64) {
+      if (threadIdx.x == 64 && p.q_out == nullptr) {
 #pragma unroll
         for (int w = 0; w < TP_EPI_WARPS; ++w) { mn = fminf(mn, s_mm[2 * w]); mx = fmaxf(mx, s_mm[2 * w + 1]); }
         p.mm_partial[blockIdx.x] = make_float2(mn, mx);

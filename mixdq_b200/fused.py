@@ -118,8 +118,7 @@ def _q_ln(x, norm, cons):
     if cons.dynamic:
         return ops.layernorm_quantize_dynamic(x, norm.weight, norm.bias, norm.eps)
     inv, sc, zp = _static_args(cons)
-    y = ops.layernorm_fp16(x, norm.weight, norm.bias, norm.eps)
-    return ops.quantize_per_tensor_to_int8(y, inv, zp), sc, zp
+    return ops.layernorm_quantize_static(x, norm.weight, norm.bias, norm.eps, inv, zp), sc, zp
 
 
 def _q_gn(x, norm, silu: bool, cons):
@@ -128,8 +127,8 @@ def _q_gn(x, norm, silu: bool, cons):
         return ops.groupnorm_quantize_dynamic(x, norm.num_groups, norm.weight, norm.bias, norm.eps,
                                               silu=silu)
     inv, sc, zp = _static_args(cons)
-    y = ops.groupnorm_fp16(x, norm.num_groups, norm.weight, norm.bias, norm.eps, silu)
-    return ops.quantize_per_tensor_to_int8(y, inv, zp), sc, zp
+    return ops.groupnorm_quantize_static(x, norm.num_groups, norm.weight, norm.bias, norm.eps,
+                                         silu, inv, zp), sc, zp
 
 
 def _q_act(x, cons):
@@ -228,10 +227,10 @@ class GegluLinear:
         if cons is None or cons.dynamic:
             return ops.qlinear_geglu_quantize_dynamic(q8, _lin_weight(m), m.weight_scales, scale,
                                                       zp, m.weight_sum_by_input_channels, m.bias)
-        y = ops.qlinear_geglu_fp16(q8, _lin_weight(m), m.weight_scales, scale, zp,
-                                   m.weight_sum_by_input_channels, m.bias)
         inv, sc, z2 = _static_args(cons)
-        return ops.quantize_per_tensor_to_int8(y, inv, z2), sc, z2
+        return ops.qlinear_geglu_quantize_static(q8, _lin_weight(m), m.weight_scales, scale, zp,
+                                                 m.weight_sum_by_input_channels, m.bias,
+                                                 inv, z2), sc, z2
 
 
 class SharedInputGroup:

@@ -938,6 +938,81 @@ def qlinear_geglu_fp16(input_int8, weight_il, weight_scale_il, input_scale, inpu
     return y
 
 
+def layernorm_quantize_static(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
+                              eps: float, scale_inv: torch.Tensor, zero_point: torch.Tensor
+                              ) -> torch.Tensor:
+    """LayerNorm + the reference's static quantiser in ONE kernel: int8 [..., C], bit-identical to
+    quantize_per_tensor_to_int8(layernorm_fp16(x, ...), scale_inv, zero_point)."""
+    _check(x.dtype == torch.float16 and weight.dtype == torch.float16
+           and bias.dtype == torch.float16, "layernorm_quantize_static expects fp16 tensors")
+    C = x.shape[-1]
+    x2 = x.reshape(-1, C)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    q = torch.empty(x.shape, dtype=torch.int8, device=x.device)
+    lib = _lib.load()
+    with _DeviceGuard(x2):
+        ws = _dynamic_workspace(x2.device)
+        _launch("ln_quant", lib.mixdq_ln_quant_i8_static,
+                (x2.data_ptr(), x2.stride(0) if M > 1 else C, M, C, weight.data_ptr(),
+                 bias.data_ptr(), float(eps), scale_inv.data_ptr(), zero_point.data_ptr(),
+                 q.data_ptr(), ws.data_ptr()), x2,
+                keep=(x2, weight, bias, scale_inv, zero_point, q, ws), algo_bytes=3 * M * C)
+    return q
+
+
+def groupnorm_quantize_static(x: torch.Tensor, num_groups: int, weight: torch.Tensor,
+                              bias: torch.Tensor, eps: float, silu: bool, scale_inv: torch.Tensor,
+                              zero_point: torch.Tensor) -> torch.Tensor:
+    """GroupNorm [+ SiLU] + the reference's static quantiser (statistics kernel, then an apply
+    kernel that emits the codes): int8 [N,C,H,W] channels_last, bit-identical to
+    quantize_per_tensor_to_int8(groupnorm_fp16(x, ...), scale_inv, zero_point)."""
+    _check(x.dtype == torch.float16 and x.dim() == 4, "groupnorm_quantize_static expects fp16 4-D")
+    n, c, h, w = x.shape
+    if _nhwc_pitch(x) != c:
+        x = x.contiguous(memory_format=torch.channels_last)
+    q = torch.empty((n, c, h, w), dtype=torch.int8, device=x.device,
+                    memory_format=torch.channels_last)
+    lib = _lib.load()
+    with _DeviceGuard(x):
+        ws = _dynamic_workspace(x.device)
+        _launch("gn_quant", lib.mixdq_gn_quant_i8_static,
+                (x.data_ptr(), c, n, h * w, c, num_groups, weight.data_ptr(), bias.data_ptr(),
+                 float(eps), 1 if silu else 0, scale_inv.data_ptr(), zero_point.data_ptr(),
+                 q.data_ptr(), ws.data_ptr()), x,
+                keep=(x, weight, bias, scale_inv, zero_point, q, ws), kernels=2,
+                algo_bytes=5 * x.numel())
+    return q
+
+
+def qlinear_geglu_quantize_static(input_int8, weight_il, weight_scale_il, input_scale,
+                                  input_zero_point, weight_sum_il, bias_il, scale_inv: torch.Tensor,
+                                  zero_point: torch.Tensor) -> torch.Tensor:
+    """ff.net.0.proj with GEGLU AND the static quantisation of its result (for ff.net.2) in the
+    GEMM epilogue: one kernel, int8 [..., inner]; bit-identical to
+    quantize_per_tensor_to_int8(qlinear_geglu_fp16(...), scale_inv, zero_point)."""
+    w4 = _is_w4(weight_il)
+    N2, K = weight_il.shape[0], weight_il.shape[1] * (2 if w4 else 1)
+    I = N2 // 2
+    a = input_int8 if input_int8.is_contiguous() else input_int8.contiguous()
+    M = a.numel() // K
+    q = torch.empty((*input_int8.shape[:-1], I), dtype=torch.int8, device=a.device)
+    lib = _lib.load()
+    with _DeviceGuard(a):
+        ws = _dynamic_workspace(a.device)
+        _launch("gemm_geglu_w4" if w4 else "gemm_geglu", lib.mixdq_gemm_geglu_i8_static,
+                (a.data_ptr(), K, weight_il.data_ptr(), 4 if w4 else 8,
+                 weight_scale_il.data_ptr(), weight_sum_il.data_ptr(), input_scale.data_ptr(),
+                 input_zero_point.data_ptr(), _ptr(bias_il), scale_inv.data_ptr(),
+                 zero_point.data_ptr(), q.data_ptr(), I, M, N2, K, ws.data_ptr()), a,
+                keep=(a, weight_il, weight_scale_il, weight_sum_il, input_scale,
+                      input_zero_point, bias_il, scale_inv, zero_point, q, ws),
+                algo_bytes=M * K + N2 * K // (2 if w4 else 1) + M * I + 10 * N2,
+                algo_ops=2 * M * N2 * K)
+    return q
+
+
 def tensor_minmax(x: torch.Tensor) -> torch.Tensor:
     """fp32 [2] = (min(0, min x), max(0, max x)) of a dense fp16 tensor (numel % 8 == 0), by the
     min/max pass of the dynamic quantiser + a one-CTA reduction of its partials (PTQ calibration,

@@ -296,3 +296,83 @@ def test_split_shortcut_dynamic(ops, dev):
     o1, _ = O.qconv2d_kernel(qbr, wb, wsb * sbr, None, wb.float().sum(dim=[1, 2, 3]) * zbr, 0.0, None, 1, 0)
     ref = O.add_fp16(O.split_shortcut_kernel(o0, o1), res)
     assert torch.equal(bits(y.contiguous()), bits(ref))
+
+
+# ---- producers with STATIC (checkpoint) scales: one pass, bit-identical to producer -> A1 ----
+def _static_params(dev, delta, zp):
+    d = torch.tensor(delta, dtype=torch.float32)
+    return (1.0 / d).to(dev), torch.tensor(float(zp), dtype=torch.float32).to(dev)
+
+
+@pytest.mark.parametrize("M,C", [(256, 1280), (1024, 640), (77, 64), (8192, 640), (300, 2048),
+                                 (4, 1280)])
+def test_layernorm_quant_static(ops, dev, M, C):
+    g = torch.Generator().manual_seed(M + C)
+    x = (torch.randn(M, C, generator=g) * 2 + 0.3).half().to(dev)
+    w = (1 + 0.2 * torch.randn(C, generator=g)).half().to(dev)
+    b = (0.1 * torch.randn(C, generator=g)).half().to(dev)
+    for delta, zp in ((0.031, -9.0), (0.004, 20.0)):        # the second one saturates
+        inv, z = _static_params(dev, delta, zp)
+        y = ops.layernorm_fp16(x, w, b, 1e-5)
+        want = ops.quantize_per_tensor_to_int8(y, inv, z)
+        got = ops.layernorm_quantize_static(x, w, b, 1e-5, inv, z)
+        assert torch.equal(got, want)
+        # and against the oracle's A1 formula on the kernel's own fp16 values
+        assert torch.equal(got.cpu(), O.quantize_static_kernel(y.cpu(), inv.item(), z.item()))
+    # the dynamic path still works on the same workspace afterwards
+    q, s, zz, yy = ops.layernorm_quantize_dynamic(x, w, b, 1e-5, return_y=True)
+    assert torch.equal(bits(yy), bits(y))
+
+
+@pytest.mark.parametrize("N,C,H,W,G,silu", [
+    (1, 320, 64, 64, 32, True), (1, 1280, 16, 16, 32, True), (1, 2560, 16, 16, 32, True),
+    (2, 1280, 16, 16, 32, False), (8, 640, 32, 32, 32, False), (3, 64, 8, 8, 16, True)])
+def test_groupnorm_quant_static(ops, dev, N, C, H, W, G, silu):
+    g = torch.Generator().manual_seed(N * C + H)
+    x = (torch.randn(N, C, H, W, generator=g) * torch.linspace(0.5, 3.0, C).view(1, C, 1, 1)
+         + torch.linspace(-1, 1, C).view(1, C, 1, 1)).half()
+    w = (1 + 0.2 * torch.randn(C, generator=g)).half().to(dev)
+    b = (0.1 * torch.randn(C, generator=g)).half().to(dev)
+    xd = x.to(dev).contiguous(memory_format=torch.channels_last)
+    inv, z = _static_params(dev, 0.023, -31.0)
+    for _ in range(3):     # repeated calls: the apply kernel's last CTA re-zeroes the statistics
+        y = ops.groupnorm_fp16(xd, G, w, b, 1e-5, silu)
+        want = ops.quantize_per_tensor_to_int8(y, inv, z)
+        got = ops.groupnorm_quantize_static(xd, G, w, b, 1e-5, silu, inv, z)
+        assert got.is_contiguous(memory_format=torch.channels_last) and got.shape == x.shape
+        assert torch.equal(got, want)
+    # the dynamic three-kernel form finds the accumulators clean
+    q, s, zz, yy = ops.groupnorm_quantize_dynamic(xd, G, w, b, 1e-5, silu, return_y=True)
+    assert torch.equal(bits(yy.contiguous()), bits(y.contiguous()))
+
+
+@pytest.mark.parametrize("M,I,K,w4", [(256, 5120, 1280, False), (1024, 2560, 640, False),
+                                      (77, 64, 128, False), (300, 80, 64, False),
+                                      (2048, 5120, 1280, False), (8192, 2560, 640, False),
+                                      (256, 5120, 1280, True), (2048, 5120, 1280, True)])
+def test_geglu_static_quant_in_gemm_epilogue(ops, dev, M, I, K, w4):
+    """ff.net.0.proj + GEGLU + the static quantiser of ff.net.2 in ONE tcgen05 kernel (one-tile and
+    persistent forms, W8 and packed W4) == GEGLU GEMM -> fp16 -> quantize_per_tensor_to_int8."""
+    from mixdq_b200.nn.utils import pack_int4
+    g = torch.Generator().manual_seed(M + I + K)
+    x8 = torch.randint(-128, 128, (M, K), dtype=torch.int8, generator=g).to(dev)
+    lim = 8 if w4 else 128
+    w = torch.randint(-lim + 1, lim, (2 * I, K), dtype=torch.int8, generator=g)
+    ws_ = (0.001 + 0.01 * torch.rand(2 * I, generator=g)).to(dev) * (16 if w4 else 1)
+    wsum = w.float().sum(1).to(dev)
+    bias = torch.randn(2 * I, generator=g).half().to(dev)
+    a_s = torch.tensor(0.04, device=dev); a_z = torch.tensor(-7.0, device=dev)
+    idx = ops.geglu_interleave_index(I, dev)
+    w_il = w.to(dev)[idx].contiguous()
+    if w4:
+        w_il = pack_int4(w_il)
+    args = (x8, w_il, ws_[idx].contiguous(), a_s, a_z, wsum[idx].contiguous(),
+            bias[idx].contiguous())
+    y = ops.qlinear_geglu_fp16(*args)
+    rng = y.float().abs().max().item()
+    inv, z = _static_params(dev, max(rng, 1e-3) / 200.0, -40.0)     # some saturation
+    want = ops.quantize_per_tensor_to_int8(y, inv, z)
+    for _ in range(2):
+        got = ops.qlinear_geglu_quantize_static(*args, inv, z)
+        assert got.shape == (M, I) and torch.equal(got, want)
+    assert torch.equal(got.cpu(), O.quantize_static_kernel(y.cpu(), inv.item(), z.item()))
