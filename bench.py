@@ -381,6 +381,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp16", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="leaf-by-leaf module swap only")
+    ap.add_argument("--no-static", action="store_true",
+                    help="config 2: skip the extra static-scale (PTQ checkpoint) timing")
     ap.add_argument("--sweep-out", default=None, help="config 5: also write the table to this file")
     ap.add_argument("--profile-fp16", action="store_true",
                     help="with --profile-step: profile the FP16 baseline UNet instead")
@@ -454,7 +456,9 @@ def main():
 
     # ---- quantized UNet ----
     qunet = quantize_copy(unet16, cfg["mode"], cfg["w_config"], cfg["a_config"], fuse)
-    del unet16
+    want_static = (args.config == 2 and cfg["mode"] == "dynamic" and not args.no_static)
+    if not want_static:
+        del unet16
     torch.cuda.empty_cache()
     kinds = {}
     for m in qunet.modules():
@@ -559,6 +563,35 @@ def main():
     }
     del g_tc
 
+    # ---- the same UNet with STATIC (PTQ-checkpoint) activation scales: the mode the reference's
+    #      own kernels ship with (nn/Linear.py:154-176); reported beside the dynamic headline ----
+    static_scales = None
+    if want_static:
+        sunet = quantize_copy(unet16, "static", cfg["w_config"], cfg["a_config"], fuse)
+        del unet16
+        with torch.no_grad():
+            sunet(**inputs)
+            c0 = ops.launch_count()
+            sunet(**inputs)
+            s_launches = ops.launch_count() - c0
+        g_s, out_s = capture(sunet, inputs)
+
+        def step_static():
+            g_s.replay()
+            if world > 1:
+                dp.gather_latents(out_s[0], total, world)
+        ms_s = time_region(step_static, args.steps, args.warmup, world, device)
+        static_scales = {
+            "ms_per_step": ms_s, "img_per_s": total / (ms_s * 1e-3),
+            "gpu_launches_per_step": s_launches,
+            "speedup_over_fp16": None if fp16_ms is None else fp16_ms / ms_s,
+            "what": "same UNet, same kernels, static per-tensor activation scales from a synthetic "
+                    "PTQ checkpoint in the reference's kernel format (the reference extension's own "
+                    "mode): LayerNorm / GroupNorm / GEGLU producers emit int8 directly, no min/max "
+                    "and no quantise pass behind them"}
+        del g_s, out_s, sunet
+        torch.cuda.empty_cache()
+
     # ---- CPU baseline (rank 0, N = 1 only): whole UNet, batch 1, 1 warm-up + 3 timed ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -606,6 +639,7 @@ def main():
                     "fp16": {"static": 4998.0, "dynamic": 240.88, "peak": 5239.0},
                     "w8a8": {"static": 2575.32, "dynamic": 55.77, "peak": 2631.10}},
             },
+            "static_scales": static_scales,
             "fp16_baseline": None if fp16_ms is None else {
                 "ms_per_step": fp16_ms, "img_per_s": total / (fp16_ms * 1e-3),
                 "speedup_w8a8_over_fp16": fp16_ms / ms,
