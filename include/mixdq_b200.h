@@ -64,6 +64,9 @@ void        mixdq_debug_set_persist(int mode, int cluster);
 /* Tuning hook: restrict the persistent kernel's tile-width choice to `bn` (128 / 160 / 256; 0 =
    cost model). */
 void        mixdq_debug_set_persist_bn(int bn);
+/* 3x3 convolutions on the persistent kernel: one haloed A box for the three vertical taps
+   (default on; 0 = plain per-tap boxes, for A/B timing and the parity tests of both forms) */
+void        mixdq_debug_set_conv_halo(int on);
 /* Force the split-K factor (cluster size) of the tcgen05 kernels (1/2/4/8; 0 = heuristic). */
 void        mixdq_debug_force_splits(int splits);
 /* Give the tcgen05 kernels a device buffer of 8 uint64 PER CTA of the largest grid launched:

@@ -18,7 +18,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libmixdq_b200.so"
 # every symbol include/mixdq_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "mixdq_abi_version", "mixdq_set_workspace", "mixdq_stream_capture_id", "mixdq_debug_set_pdl", "mixdq_strerror", "mixdq_last_path", "mixdq_force_simt",
-    "mixdq_debug_force_bn", "mixdq_debug_force_splits", "mixdq_debug_set_persist", "mixdq_debug_set_persist_bn", "mixdq_debug_set_timing_buffer",
+    "mixdq_debug_force_bn", "mixdq_debug_force_splits", "mixdq_debug_set_persist", "mixdq_debug_set_persist_bn", "mixdq_debug_set_conv_halo", "mixdq_debug_set_timing_buffer",
     "mixdq_debug_set_mode", "mixdq_debug_set_cluster", "mixdq_debug_set_two_pass", "mixdq_debug_set_quant_timing_buffer",
     "mixdq_quant_i8_static", "mixdq_quant_i8_static_strided", "mixdq_quant_i8_nchw2nhwc",
     "mixdq_quant_dynamic_ws_bytes", "mixdq_quant_i8_dynamic",
@@ -59,6 +59,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mixdq_debug_set_persist.argtypes = [c_int, c_int]
     lib.mixdq_debug_set_persist_bn.restype = None
     lib.mixdq_debug_set_persist_bn.argtypes = [c_int]
+    lib.mixdq_debug_set_conv_halo.restype = None
+    lib.mixdq_debug_set_conv_halo.argtypes = [c_int]
     lib.mixdq_quant_i8_dynamic_bits.restype = c_int
     lib.mixdq_quant_i8_dynamic_bits.argtypes = [P, c_int64, c_int64, c_int64, c_int, P, P, P, P, P]
     lib.mixdq_minmax_f16.restype = c_int

@@ -218,6 +218,7 @@ extern "C" int mixdq_stream_capture_id(mixdq_stream_t stream, unsigned long long
 }
 extern "C" void mixdq_debug_set_persist(int mode, int cluster) { persist_set_mode(mode, cluster); }
 extern "C" void mixdq_debug_set_persist_bn(int bn) { persist_force_bn(bn); }
+extern "C" void mixdq_debug_set_conv_halo(int on) { persist_set_halo(on); }
 extern "C" void mixdq_debug_force_bn(int bn) { g_force_bn = bn; }
 extern "C" void mixdq_debug_force_splits(int s) { g_force_splits = s; }
 // MIXDQ_A_PREFETCH=1 enables an L2 prefetch of the first A tile before the dependency wait.
@@ -628,8 +629,13 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
             tilesN = (N + boxN - 1) / boxN;
   const int m_tiles = tilesQ * tilesP * tilesN;
   const int kb_per_tap = (C + BLOCK_K - 1) / BLOCK_K;
-  const int pbn = persist_bn(m_tiles, K, R * S * kb_per_tap, KIND_CONV);
+  int pbn = persist_bn(m_tiles, K, R * S * kb_per_tap, KIND_CONV);
   const int pcs = pbn ? persist_cluster_size(m_tiles) : 1;
+  // 3x3 convolutions on the persistent CTA-pair kernel: 160-wide tiles with one haloed A box for
+  // the three vertical taps (fewer operand bytes per MMA than any plain tile width)
+  const bool halo = pbn &&
+                    persist_halo_ok(160, w4, pcs, R, S, pad, stride, boxW, boxH, boxN);
+  if (halo) pbn = 160;
   int bn = pbn, splits = 1;
   if (!pbn) pick_tile(m_tiles, K, R * S * kb_per_tap, true, st, &bn, &splits);
 
@@ -640,7 +646,8 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
     uint64_t strides[3] = {static_cast<uint64_t>(x_cpitch), static_cast<uint64_t>(x_cpitch) * W,
                            static_cast<uint64_t>(x_cpitch) * W * H};
     uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(boxW * stride),
-                       static_cast<uint32_t>(boxH * stride), static_cast<uint32_t>(boxN)};
+                       static_cast<uint32_t>((halo ? boxH + 2 : boxH) * stride),
+                       static_cast<uint32_t>(boxN)};
     uint32_t estr[4] = {1, static_cast<uint32_t>(stride), static_cast<uint32_t>(stride), 1};
     if (!make_tmap(&tmA, x, 4, dims, strides, box, estr)) return MIXDQ_ERR_CUDA;
   }
@@ -664,7 +671,7 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
   p.num_kb = R * S * p.kb_per_tap;
   p.S = S; p.pad = pad; p.stride = stride; p.NB = N; p.H = H; p.W = W; p.P = P; p.Q = Q;
   p.boxW = boxW; p.boxH = boxH; p.boxN = boxN; p.tilesQ = tilesQ; p.tilesP = tilesP;
-  p.a_tx_bytes = static_cast<uint32_t>(boxW) * boxH * boxN * BLOCK_K;
+  p.a_tx_bytes = static_cast<uint32_t>(boxW) * (halo ? boxH + 2 : boxH) * boxN * BLOCK_K;
   p.has_table = pad > 0 ? 1 : 0;
   p.scale = scale; p.bias0 = pad > 0 ? wsum_krs : bias0_k; p.a_zp = zp; p.a_scale = a_scale;
   p.bias = reinterpret_cast<const __half*>(bias);
@@ -681,6 +688,10 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
     CUtensorMap tmD;
     if (!make_tmap_out(&tmD, y, K, static_cast<uint64_t>(N) * P * Q, K)) return MIXDQ_ERR_CUDA;
     p.d_tma = rows_contig ? 1 : 0; p.d_cols = K;
+    if (halo) {
+      g_last_path = "tcgen05-persist-halo";
+      return persist_launch_conv_halo(tmA, tmW, tmD, p, st);
+    }
     g_last_path = w4 ? "tcgen05-w4-persist" : "tcgen05-persist";
     return persist_launch(KIND_CONV, pbn, w4, pcs, tmA, tmW, tmD, p, st);
   }

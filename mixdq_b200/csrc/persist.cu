@@ -70,6 +70,8 @@ int persist_pick_bn(int m_tiles, int N, int num_kb, int kind) {
 }
 
 void persist_force_bn(int bn) { g_persist_bn = bn; }
+static int g_halo = -1;             // env MIXDQ_CONV_HALO / mixdq_debug_set_conv_halo: 0 = off
+void persist_set_halo(int on) { g_halo = on ? 1 : 0; }
 
 void persist_set_mode(int mode, int cs) {
   read_env();
@@ -82,11 +84,11 @@ int persist_cluster_size(int m_tiles) {
   return (g_persist_cs == 2 && m_tiles >= 2) ? 2 : 1;
 }
 
-template <int BN, int STAGES, int KIND, bool W4, int CS>
+template <int BN, int STAGES, int KIND, bool W4, int CS, bool HALO = false>
 static int launch(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& d, const TcParams& p,
                   cudaStream_t st) {
-  using L = TpSmem<BN, STAGES, KIND, W4, CS>;
-  auto kern = tc_i8_persist_kernel<BN, STAGES, KIND, W4, CS>;
+  using L = TpSmem<BN, STAGES, KIND, W4, CS, HALO>;
+  auto kern = tc_i8_persist_kernel<BN, STAGES, KIND, W4, CS, HALO>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) !=
@@ -143,6 +145,22 @@ static int by_flags(int bn, bool w4, int cs, const CUtensorMap& a, const CUtenso
                     const CUtensorMap& d, const TcParams& p, cudaStream_t st) {
   if (w4) return cs == 2 ? by_bn<KIND, true, 2>(bn, a, w, d, p, st) : by_bn<KIND, true, 1>(bn, a, w, d, p, st);
   return cs == 2 ? by_bn<KIND, false, 2>(bn, a, w, d, p, st) : by_bn<KIND, false, 1>(bn, a, w, d, p, st);
+}
+
+// 3x3 / pad 1 / stride 1 convolutions on CTA pairs with 160-wide tiles: one haloed A box per
+// (s, channel block) serves the three vertical taps (tc_persist.cuh, TpSmem::HALO). Env
+// MIXDQ_CONV_HALO=0 switches it off (A/B timing).
+bool persist_halo_ok(int bn, bool w4, int cs, int R, int S, int pad, int stride, int boxW, int boxH,
+                     int boxN) {
+  if (g_halo < 0) { const char* e = getenv("MIXDQ_CONV_HALO"); g_halo = e ? atoi(e) : 1; }
+  if (g_persist_bn > 0 && g_persist_bn != 160) return false;      // another width is being forced
+  return g_halo && bn == 160 && !w4 && cs == 2 && R == 3 && S == 3 && pad == 1 && stride == 1 &&
+         boxN == 1 && (boxW % 8) == 0 && (boxH + 2) * boxW <= 2 * BLOCK_M;
+}
+
+int persist_launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmD,
+                             TcParams p, cudaStream_t st) {
+  return launch<160, 3, KIND_CONV, false, 2, true>(tmA, tmW, tmD, p, st);
 }
 
 int persist_launch(int kind, int bn, bool w4, int cs, const CUtensorMap& tmA,

@@ -21,5 +21,12 @@ int persist_cluster_size(int m_tiles);
 // MIXDQ_ERR_* code.
 int persist_launch(int kind, int bn, bool w4, int cs, const CUtensorMap& tmA,
                    const CUtensorMap& tmW, const CUtensorMap& tmD, TcParams p, cudaStream_t st);
+// HALO form of the 3x3 convolution (see persist.cu): applicable? / launch. tmA must then have been
+// encoded with a {128, boxW, boxH + 2, 1} box and p.a_tx_bytes = (boxH + 2) * boxW * 128.
+void persist_set_halo(int on);      // test / tuning hook
+bool persist_halo_ok(int bn, bool w4, int cs, int R, int S, int pad, int stride, int boxW, int boxH,
+                     int boxN);
+int persist_launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmD,
+                             TcParams p, cudaStream_t st);
 
 }  // namespace mixdq

@@ -49,23 +49,33 @@ constexpr int TP_CONV_WARPS = 4;
 constexpr int TP_THREADS_W4 = TP_THREADS + 32 * TP_CONV_WARPS;   // 448
 constexpr int TP_SLOT_COLS = 256;                           // TMEM columns per accumulator slot
 
-template <int BN, int STAGES, int KIND, bool W4, int CS = 1>
+template <int BN, int STAGES, int KIND, bool W4, int CS = 1, bool HALO = false>
 struct TpSmem {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K;
   static constexpr int W_ROWS = BN / CS;                     // W rows staged by this CTA
   static constexpr int W_BYTES = W_ROWS * BLOCK_K;
+  // HALO (3x3 / pad 1 / stride 1 convolutions): a ring stage holds ONE A box with a one-row halo
+  // above and below — (boxH + 2) x boxW pixels <= 2 x 128 rows — and the W tiles of the THREE
+  // vertical taps (r = 0, 1, 2) of one (s, channel block): the taps read the same pixels shifted
+  // by whole image rows, i.e. by boxW x 128 B = a multiple of the 1024 B swizzle atom, so they are
+  // three descriptor offsets into one box instead of three boxes through the L2 -> SM fabric
+  static constexpr int A_STAGE = HALO ? 2 * A_BYTES : A_BYTES;
+  static constexpr int W_STAGE = HALO ? 3 * W_BYTES : W_BYTES;
   // accumulator columns per chunk (GEGLU: 16 value + 16 gate columns -> 16 outputs)
   static constexpr int CH = (KIND == KIND_GEGLU) ? 32 : 16;
   // fp16 staging row: 16 outputs = two 16-byte halves, stored XOR-swizzled by bit 2 of the row so
   // that both the row-per-lane writes and the two-lanes-per-row reads are bank-conflict free
   static constexpr int OUT_PITCH = 32;
-  static constexpr int OUT_WARP = 2 * 32 * OUT_PITCH;        // one warp: two tiles of 32 rows
+  // one warp: two staging tiles of 32 rows (HALO: one — its ring needs the space, and its long
+  // K loops hide a store that waits for the previous one to have read the tile)
+  static constexpr int OUT_BUFS = HALO ? 1 : 2;
+  static constexpr int OUT_WARP = OUT_BUFS * 32 * OUT_PITCH;
   static constexpr int TAB_PITCH = BN + 4;
   static constexpr int TAB_FLOATS = (KIND == KIND_CONV) ? 16 * TAB_PITCH : 0;
   static constexpr int PARAM_FLOATS = 3 * BN + TAB_FLOATS;
   static constexpr int OFF_A = 0;
-  static constexpr int OFF_W = OFF_A + STAGES * A_BYTES;
-  static constexpr int OFF_OUT = OFF_W + STAGES * W_BYTES;
+  static constexpr int OFF_W = OFF_A + STAGES * A_STAGE;
+  static constexpr int OFF_OUT = OFF_W + STAGES * W_STAGE;
   static constexpr int OFF_PARAM = OFF_OUT + TP_EPI_WARPS * OUT_WARP;
   static constexpr int OFF_BAR = OFF_PARAM + ((PARAM_FLOATS * 4 + 15) / 16) * 16;
   static constexpr int NUM_BARS = (W4 ? 3 : 2) * STAGES + 4;
@@ -185,11 +195,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     if (p.dbg != nullptr && (cond)) p.dbg[blockIdx.x * 16 + (slot)] = gtime_ns(); \
   } while (0)
 
-template <int BN, int STAGES, int KIND, bool W4, int CS>
+template <int BN, int STAGES, int KIND, bool W4, int CS, bool HALO = false>
 __global__ void __launch_bounds__(W4 ? TP_THREADS_W4 : TP_THREADS, 1)
 tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ CUtensorMap tmD, const TcParams p) {
-  using L = TpSmem<BN, STAGES, KIND, W4, CS>;
+  using L = TpSmem<BN, STAGES, KIND, W4, CS, HALO>;
+  static_assert(!HALO || (KIND == KIND_CONV && !W4), "HALO: int8 3x3 convolutions only");
   static_assert(KIND == KIND_GEMM || KIND == KIND_CONV || KIND == KIND_GEGLU, "unsupported kind");
   static_assert(BN % 32 == 0 && BN / L::CH >= TP_EPI_PARTS && BN <= TP_SLOT_COLS,
                 "tile width (every epilogue warp owns >= 1 chunk)");
@@ -237,7 +248,9 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     g_begin = cid * base + (cid < rem ? cid : rem);
     g_end = g_begin + base + (cid < rem ? 1 : 0);
   }
-  const int num_kb = p.num_kb;
+  // ring iterations per tile: k-blocks, or (HALO) the 3 x kb_per_tap (s, channel block) pairs,
+  // each covering the three vertical taps
+  const int num_kb = HALO ? 3 * p.kb_per_tap : p.num_kb;
   const bool leader = crank == 0;
   // the leader's barriers as shared::cluster addresses (identity for the leader itself)
   auto leader_addr = [&](const void* bar) {
@@ -297,9 +310,18 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     auto load_w = [&](const Tile& t, int kb, int stage) {
       // W4: packed rows (64 B) land in the upper half of the slot, unswizzled, and complete on
       // this CTA's own raw_full barrier (the converter warps signal the leader's full barrier)
-      uint8_t* w_dst = sW + stage * L::W_BYTES + (W4 ? L::W_BYTES / 2 : 0);
+      uint8_t* w_dst = sW + stage * L::W_STAGE + (W4 ? L::W_BYTES / 2 : 0);
       const int row0 = t.n_tile0 + crank * WROWS;
-      if (KIND == KIND_CONV) {
+      if (HALO) {
+        // iteration kb = (s, channel block): the W tiles of taps (0, s), (1, s), (2, s)
+        const int s = kb / p.kb_per_tap;
+        const int c0 = (kb - s * p.kb_per_tap) * WK;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          if (PAIR) tma_load_3d_pair(w_dst + r * L::W_BYTES, &tmW, leader_addr(&full_bar[stage]), c0, r * 3 + s, row0);
+          else tma_load_3d(w_dst + r * L::W_BYTES, &tmW, &full_bar[stage], c0, r * 3 + s, row0);
+        }
+      } else if (KIND == KIND_CONV) {
         const int tap = kb / p.kb_per_tap;
         const int c0 = (kb - tap * p.kb_per_tap) * WK;
         if (W4 || !PAIR) tma_load_3d(w_dst, &tmW, W4 ? &raw_full[stage] : &full_bar[stage], c0, tap, row0);
@@ -310,8 +332,14 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     };
     auto load_a = [&](const Tile& t, int kb, int stage) {
-      uint8_t* a_dst = sA + stage * L::A_BYTES;
-      if (KIND == KIND_CONV) {
+      uint8_t* a_dst = sA + stage * L::A_STAGE;
+      if (HALO) {
+        // (boxH + 2) x boxW box starting one image row above the tile, shifted by s - 1 pixels
+        const int s = kb / p.kb_per_tap;
+        const int c0 = (kb - s * p.kb_per_tap) * BLOCK_K;
+        if (PAIR) tma_load_4d_pair(a_dst, &tmA, leader_addr(&full_bar[stage]), c0, t.tq0 - 1 + s, t.tp0 - 1, t.tn0);
+        else tma_load_4d(a_dst, &tmA, &full_bar[stage], c0, t.tq0 - 1 + s, t.tp0 - 1, t.tn0);
+      } else if (KIND == KIND_CONV) {
         const int tap = kb / p.kb_per_tap;
         const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
         const int r = tap / p.S, s = tap - r * p.S;
@@ -325,7 +353,7 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     };
     // bytes the LEADER's full barrier of a stage expects: A (+ unpacked W) of every CTA of the pair
-    const uint32_t full_tx = static_cast<uint32_t>(CS) * (a_bytes + (W4 ? 0u : W_TX));
+    const uint32_t full_tx = static_cast<uint32_t>(CS) * (a_bytes + (W4 ? 0u : (HALO ? 3u : 1u) * W_TX));
     // The first ring-full of WEIGHT k-blocks does not depend on the preceding kernel: issue it
     // before the programmatic-dependency wait (activations follow after it).
     uint32_t it = 0;                                     // k-block iterations issued so far
@@ -388,9 +416,22 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         TP_DBG(lane == 0 && kb == 0 && tl == dbg_tl, 10);                             // first stage landed
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(stage * (L::A_BYTES >> 4));
-          const uint64_t w_desc = w_desc0 + static_cast<uint64_t>(stage * (L::W_BYTES >> 4));
+          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(stage * (L::A_STAGE >> 4));
+          const uint64_t w_desc = w_desc0 + static_cast<uint64_t>(stage * (L::W_STAGE >> 4));
           if (!(p.dbg_mode & 1)) {
+            if (HALO) {
+              // tap r reads the box from image row r on: + r * boxW rows of 128 B (1024 B aligned)
+              const uint64_t a_tap = static_cast<uint64_t>((p.boxW * BLOCK_K) >> 4);
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                  const uint64_t ad = a_desc + r * a_tap + static_cast<uint64_t>(k * (UMMA_K >> 4));
+                  const uint64_t wd = w_desc + static_cast<uint64_t>(r * (L::W_BYTES >> 4) + k * (UMMA_K >> 4));
+                  if (PAIR) umma_i8_pair(d_tmem, ad, wd, IDESC, (kb | r | k) ? 1u : 0u);
+                  else umma_i8(d_tmem, ad, wd, IDESC, (kb | r | k) ? 1u : 0u);
+                }
+            } else {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
               if (PAIR) umma_i8_pair(d_tmem, a_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)),
@@ -398,6 +439,7 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                      (kb | k) ? 1u : 0u);
               else umma_i8(d_tmem, a_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)),
                            w_desc + static_cast<uint64_t>(k * (UMMA_K >> 4)), IDESC, (kb | k) ? 1u : 0u);
+            }
           }
           if (PAIR) {
             umma_commit_pair(&empty_bar[stage], 0x3);                // frees the slot in BOTH CTAs
@@ -522,10 +564,11 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       };
       // stage 16 halves of this lane's row and send the 32 x 16 tile out
       auto store_chunk = [&](const __half* y, int out_col) {
-        const uint32_t buf = stage_u32 + (nstore & 1u) * 1024u;
+        const uint32_t buf = stage_u32 + (L::OUT_BUFS == 2 ? (nstore & 1u) * 1024u : 0u);
         if (d_tma) {
-          // the store that last read this staging tile (two chunks ago) must be done reading
-          if (lane == 0) bulk_wait_read<1>();
+          // the store that last read this staging tile (two chunks ago; HALO: the previous one)
+          // must be done reading
+          if (lane == 0) bulk_wait_read<L::OUT_BUFS - 1>();
           __syncwarp();
           sts_v4(buf + lane * 32 + (sw << 4), reinterpret_cast<const uint4*>(y)[0]);
           sts_v4(buf + lane * 32 + ((sw ^ 1) << 4), reinterpret_cast<const uint4*>(y)[1]);
@@ -699,7 +742,7 @@ tc_i8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int stage = it % STAGES;
           mbar_wait(&raw_full[stage], (it / STAGES) & 1u);
-          uint8_t* wst = sW + stage * L::W_BYTES;
+          uint8_t* wst = sW + stage * L::W_STAGE;
           uint4 pk[PT];
 #pragma unroll
           for (int j = 0; j < PT; ++j) {

@@ -87,9 +87,35 @@ CONVS = [  # (n,h,w,c,k,r,s,pad,stride)
 ]
 
 
+# 3x3 / pad 1 / stride 1 on CTA pairs: the HALO form (one A box with a one-row halo for the three
+# vertical taps). Ragged tiles along P (24x24, 40x40), tiles narrower than 128 rows (48x48), 8-wide rows,
+# channel counts that are not a multiple of the 128-byte k-block, ragged N tiles (k = 200).
+HALO_CONVS = [(2, 64, 64, 320, 320), (8, 16, 16, 1280, 1280), (4, 32, 32, 640, 320), (3, 24, 24, 96, 200),
+              (2, 48, 48, 160, 160), (2, 16, 8, 320, 640), (2, 40, 40, 64, 96), (6, 16, 16, 2560, 1280)]
+
+
+@pytest.mark.parametrize("n,h,w,c,k", HALO_CONVS)
+@pytest.mark.parametrize("halo", [1, 0], ids=["halo", "plain"])
+def test_persistent_conv3x3_halo_bit_exact(ops, dev, n, h, w, c, k, halo):
+    from mixdq_b200 import _lib
+    lib = _lib.load()
+    lib.mixdq_debug_set_persist(2, 2)
+    lib.mixdq_debug_set_conv_halo(halo)
+    try:
+        _conv_case(ops, dev, n, h, w, c, k, 3, 3, 1, 1, False,
+                   "tcgen05-persist-halo" if halo else "tcgen05-persist")
+    finally:
+        lib.mixdq_debug_set_conv_halo(1)
+        lib.mixdq_debug_set_persist(1, 2)
+
+
 @pytest.mark.parametrize("n,h,w,c,k,r,s,pad,stride", CONVS)
 @pytest.mark.parametrize("w4", [False, True])
 def test_persistent_conv_bit_exact(ops, dev, forced, n, h, w, c, k, r, s, pad, stride, w4):
+    _conv_case(ops, dev, n, h, w, c, k, r, s, pad, stride, w4, None)
+
+
+def _conv_case(ops, dev, n, h, w, c, k, r, s, pad, stride, w4, want_path):
     from mixdq_b200 import _lib
     from mixdq_b200.nn.utils import pack_int4
     g = torch.Generator().manual_seed(n * h * w + c + k)
@@ -116,7 +142,11 @@ def test_persistent_conv_bit_exact(ops, dev, forced, n, h, w, c, k, r, s, pad, s
                                     residual=res.to(dev).contiguous(memory_format=torch.channels_last),
                                     _acc_out=acc)
     torch.cuda.synchronize()
-    assert _lib.last_path() == ("tcgen05-w4-persist" if w4 else "tcgen05-persist")
+    if want_path is None:
+        assert _lib.last_path() in (("tcgen05-w4-persist",) if w4 else
+                                    ("tcgen05-persist", "tcgen05-persist-halo"))
+    else:
+        assert _lib.last_path() == want_path
     ref, ref_acc = O.qconv2d_kernel(x, codes, w_scale * a_scale, wsum_krs,
                                     None if wsum_k is None else wsum_k * a_zp, a_zp, b, stride, pad)
     ref = (ref.float() + ca.float()[:, :, None, None]).half()
