@@ -630,12 +630,16 @@ static int conv_common(const int8_t* x, int64_t x_cpitch, const int8_t* w, const
   const int m_tiles = tilesQ * tilesP * tilesN;
   const int kb_per_tap = (C + BLOCK_K - 1) / BLOCK_K;
   int pbn = persist_bn(m_tiles, K, R * S * kb_per_tap, KIND_CONV);
-  const int pcs = pbn ? persist_cluster_size(m_tiles) : 1;
   // 3x3 convolutions on the persistent CTA-pair kernel: 160-wide tiles with one haloed A box for
-  // the three vertical taps (fewer operand bytes per MMA than any plain tile width)
-  const bool halo = pbn &&
-                    persist_halo_ok(160, w4, pcs, R, S, pad, stride, boxW, boxH, boxN);
+  // the three vertical taps (fewer operand bytes per MMA than any plain tile width); it has its
+  // own, lower size threshold
+  read_force_env();
+  const bool shape_forced = g_force_bn > 0 || g_force_splits > 0;
+  const bool halo = !shape_forced && (pbn || persist_halo_wanted(m_tiles)) &&
+                    persist_halo_ok(160, w4, persist_cluster_size(m_tiles), R, S, pad, stride, boxW,
+                                    boxH, boxN);
   if (halo) pbn = 160;
+  const int pcs = pbn ? persist_cluster_size(m_tiles) : 1;
   int bn = pbn, splits = 1;
   if (!pbn) pick_tile(m_tiles, K, R * S * kb_per_tap, true, st, &bn, &splits);
 

@@ -294,9 +294,182 @@ __device__ __forceinline__ int4 gn_vec8(const int4& raw, int c8, int cpg,
   return pack8(o);
 }
 
-// MODE 0: everything in one kernel (two grid barriers).  MODE 1 / MODE 2: the same code cut at
-// the first barrier into a statistics kernel and an apply kernel (normalise -> fp16 y + min/max
-// published for quant2.cu's single-pass quantiser), chained by programmatic dependent launch.
+// ---- GroupNorm statistics --------------------------------------------------------------------
+// An image is cut into UNITS of gn_unit_rows(C) consecutive pixel rows (4 / 2 / 1 for C <= 512 /
+// 1280 / 2560: the same units whatever the batch, the grid or the kernel form). One WARP reduces one
+// unit with ONE round of loads — every lane owns the 16-byte channel chunks lane, lane + 32, ...
+// and adds the unit's rows in ascending order (fp32) — then the per-chunk partials meet in a
+// warp-private shared-memory row and one lane per (group, quantity) adds the chunks of its group in
+// ascending order; that fp32 unit partial is converted to FIXED POINT. From there on everything is
+// integer addition — exact and order-independent — so a warp sums the units it walks in
+// registers, the CTA adds its warps up in shared memory and issues one atomic per (image, group,
+// quantity): the statistics of an image are bit-identical for every batch size, grid and
+// unit-to-warp assignment (static-scale UNets are invariant under batch sharding,
+// mixdq_b200/dp.py). RB x CPL = 8-10 sixteen-byte loads are in flight per lane (the first form had
+// one or two and ran at ~1 TB/s on batch-64 tensors); at batch 1 a warp has one unit.
+__host__ __device__ inline int gn_unit_rows(int nchunks) {
+  return nchunks <= 64 ? 4 : (nchunks <= 160 ? 2 : 1);
+}
+
+// per-lane constants of the (group, quantity) reduction: no division inside the unit loop
+struct GnPair {
+  int c_lo, c_hi;     // chunks overlapping the group
+  bool live, sq, first_hi;   // first_hi: chunk c_lo starts in the previous group -> take its high part
+};
+__device__ __forceinline__ GnPair gn_pair(int pq, int cpg, int G) {
+  GnPair p;
+  const int g = pq >> 1;
+  p.live = pq < 2 * G;
+  p.sq = (pq & 1) != 0;
+  p.c_lo = (g * cpg) >> 3;
+  p.c_hi = ((g + 1) * cpg - 1) >> 3;
+  p.first_hi = 8 * p.c_lo < g * cpg;
+  return p;
+}
+
+template <int CPL, int RB>
+__device__ __forceinline__ void gn_unit_stats(const __half* __restrict__ ximg, int64_t ldx, int r0,
+                                              int r1, int nchunks, int cpg,
+                                              float4* __restrict__ wpart, int lane,
+                                              const GnPair (&pr)[2], long long (&fx)[2]) {
+  int4 raw[RB][CPL];
+#pragma unroll
+  for (int u = 0; u < RB; ++u)
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const int c = lane + 32 * i;
+      if (r0 + u < r1 && c < nchunks)
+        raw[u][i] = ldg16(ximg + static_cast<int64_t>(r0 + u) * ldx + 8 * c);
+    }
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) {
+      const int c8 = 8 * c;
+      const int split = (c8 / cpg + 1) * cpg - c8;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int u = 0; u < RB; ++u) {
+        if (r0 + u < r1) {
+          float v[8];
+          unpack8(raw[u][i], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < split) { a0 += v[j]; a1 = fmaf(v[j], v[j], a1); }
+            else           { a2 += v[j]; a3 = fmaf(v[j], v[j], a3); }
+          }
+        }
+      }
+      wpart[c] = make_float4(a0, a1, a2, a3);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (pr[h].live) {
+      const float4 f = wpart[pr[h].c_lo];
+      float t = pr[h].first_hi ? (pr[h].sq ? f.w : f.z) : (pr[h].sq ? f.y : f.x);
+      for (int c = pr[h].c_lo + 1; c <= pr[h].c_hi; ++c) {
+        const float4 w4 = wpart[c];
+        t += pr[h].sq ? w4.y : w4.x;
+      }
+      // power-of-two scaling is exact in fp32: same value as the fp64 product
+      fx[h] += __float2ll_rn(t * (pr[h].sq ? static_cast<float>(kFixSq) : static_cast<float>(kFixSum)));
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void gn_unit_stats_any(const __half* __restrict__ ximg, int64_t ldx,
+                                                  int r0, int r1, int nchunks, int cpg,
+                                                  float4* __restrict__ wpart, int lane,
+                                                  const GnPair (&pr)[2], long long (&fx)[2]) {
+  if (nchunks <= 64) gn_unit_stats<2, 4>(ximg, ldx, r0, r1, nchunks, cpg, wpart, lane, pr, fx);
+  else if (nchunks <= 160) gn_unit_stats<5, 2>(ximg, ldx, r0, r1, nchunks, cpg, wpart, lane, pr, fx);
+  else gn_unit_stats<kGnMaxChunks, 1>(ximg, ldx, r0, r1, nchunks, cpg, wpart, lane, pr, fx);
+}
+
+// A warp's fixed-point sums for image n: into ITS row of the CTA's shared-memory table when the
+// image is one of the kGnSlots the CTA's contiguous range starts with (plain 64-bit adds, no
+// atomics), else straight to the workspace. Thousands of warps adding to the 2 x G words of ONE
+// image serialise in L2, so the CTA adds its warps up first (gn_publish_slots).
+constexpr int kGnSlots = 2;
+__device__ __forceinline__ void gn_flush_stats(DynWs* __restrict__ ws, unsigned long long* s_fx,
+                                               int n_base, int n, int G, int warp, int lane,
+                                               long long (&fx)[2]) {
+  const int slot = n - n_base;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int pq = lane + 32 * h;
+    if (pq < 2 * G && fx[h] != 0) {
+      if (slot >= 0 && slot < kGnSlots)
+        s_fx[(warp * kGnSlots + slot) * 64 + pq] += static_cast<unsigned long long>(fx[h]);
+      else
+        atomicAdd(&ws->gsum[(n * G) * 2 + pq], static_cast<unsigned long long>(fx[h]));
+    }
+    fx[h] = 0;
+  }
+}
+// after a __syncthreads(): the CTA's table -> one atomic per (image, group, quantity)
+__device__ __forceinline__ void gn_publish_slots(DynWs* __restrict__ ws,
+                                                 const unsigned long long* s_fx, int n_base, int NB,
+                                                 int G, int warps) {
+  for (int i = threadIdx.x; i < kGnSlots * 64; i += blockDim.x) {
+    const int slot = i >> 6, pq = i & 63;
+    unsigned long long v = 0ull;
+    for (int w = 0; w < warps; ++w) v += s_fx[(w * kGnSlots + slot) * 64 + pq];
+    if (v != 0ull && pq < 2 * G && n_base + slot < NB)
+      atomicAdd(&ws->gsum[((n_base + slot) * G) * 2 + pq], v);
+  }
+}
+
+// statistics kernel of the barrier-free form: every warp of the launch walks a CONTIGUOUS range of
+// the NB x units_per_image units; blockDim.x / 32 warps per CTA — few units are spread over many
+// CTAs of few warps, so that at batch 1 every SM pulls a few KB instead of 8 SMs pulling 80 KB
+// (dynamic shared memory: warps x nchunks float4)
+template <int CPL, int RB>
+__global__ void __launch_bounds__(kFqThreads, 1)
+gn_stats_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C, int G,
+                DynWs* __restrict__ ws, int units_per_warp) {
+  extern __shared__ float4 gn_part[];
+  __shared__ unsigned long long s_fx[kFqWarps * kGnSlots * 64];
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wpc = blockDim.x >> 5;
+  const int nchunks = C >> 3, cpg = C / G;
+  const int ur = gn_unit_rows(nchunks);
+  const int upi = (HW + ur - 1) / ur;
+  const long long total = static_cast<long long>(NB) * upi;
+  const long long cta_u0 = static_cast<long long>(blockIdx.x) * wpc * units_per_warp;
+  const int n_base = static_cast<int>(cta_u0 / upi);
+  const GnPair pr[2] = {gn_pair(lane, cpg, G), gn_pair(lane + 32, cpg, G)};
+  for (int i = threadIdx.x; i < wpc * kGnSlots * 64; i += blockDim.x) s_fx[i] = 0ull;
+  __syncthreads();
+  pdl_wait();
+  long long u = cta_u0 + static_cast<long long>(warp) * units_per_warp;
+  const long long u_end = u + units_per_warp < total ? u + units_per_warp : total;
+  float4* wpart = gn_part + warp * nchunks;
+  long long fx[2] = {0, 0};
+  int cur_n = -1;
+  for (; u < u_end; ++u) {
+    const int n = static_cast<int>(u / upi);
+    const int r0 = static_cast<int>(u - static_cast<long long>(n) * upi) * ur;
+    if (n != cur_n) {
+      if (cur_n >= 0) gn_flush_stats(ws, s_fx, n_base, cur_n, G, warp, lane, fx);
+      cur_n = n;
+    }
+    gn_unit_stats<CPL, RB>(x + static_cast<int64_t>(n) * HW * ldx, ldx, r0, min(HW, r0 + ur), nchunks,
+                           cpg, wpart, lane, pr, fx);
+  }
+  if (cur_n >= 0) gn_flush_stats(ws, s_fx, n_base, cur_n, G, warp, lane, fx);
+  __syncthreads();
+  gn_publish_slots(ws, s_fx, n_base, NB, G, wpc);
+}
+
+// MODE 0: everything in one kernel (two grid barriers).  MODE 2: the apply kernel of the
+// barrier-free form (gn_stats_kernel -> this: normalise -> fp16 y + min/max published for
+// quant2.cu's single-pass quantiser, or int8 with static scales), chained by programmatic
+// dependent launch.
 template <bool SILU, int MODE>
 __global__ void __launch_bounds__(kFqThreads, 1)
 gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C, int G,
@@ -310,79 +483,35 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
   extern __shared__ int4 stash[];   // [stash_rows][C/8]
   __shared__ float s_mean[32], s_rstd[32];
   __shared__ int s_last;
+  __shared__ unsigned long long s_fx0[(MODE == 0 ? kFqWarps * kGnSlots * 64 : 1)];   // MODE 0 statistics
   pdl_launch_dependents();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = C >> 3;
   const int cpg = C / G;
-  // MODE 1 (statistics kernel of the barrier-free form): the launch covers NB x ctas_per_image
-  // VIRTUAL blocks — every image is cut into the same row ranges whatever the batch is, so its
-  // statistics (fixed-order fp32 partial per block, then order-independent fixed-point
-  // accumulation) do not depend on the other images of the batch — walked by a resident grid.
-  const int vtotal = (MODE == 1) ? NB * ctas_per_image : static_cast<int>(gridDim.x);
-  for (int vb = blockIdx.x; vb < vtotal; vb += gridDim.x) {
+  {
+  const int vb = blockIdx.x;
   const int n = vb / ctas_per_image;
   const int row0 = (vb - n * ctas_per_image) * rows_per_cta;
   const int row1 = min(HW, row0 + rows_per_cta);
   const __half* ximg = x + static_cast<int64_t>(n) * HW * ldx;
 
   if (MODE != 2) {
-  // ---- phase 0: per-(n, group) sum / sum of squares ----
-  float acc[kGnMaxChunks][4];   // per owned chunk: (sum, sq) of its low group, (sum, sq) of its high group
-#pragma unroll
-  for (int i = 0; i < kGnMaxChunks; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-  for (int r = row0 + warp; r < row1; r += kFqWarps) {
-    const __half* xrow = ximg + static_cast<int64_t>(r) * ldx;
-#pragma unroll
-    for (int i = 0; i < kGnMaxChunks; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunks) {
-        float v[8];
-        unpack8(ldg16(xrow + 8 * c), v);
-        const int c8 = 8 * c;
-        const int split = (c8 / cpg + 1) * cpg - c8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j < split) { acc[i][0] += v[j]; acc[i][1] = fmaf(v[j], v[j], acc[i][1]); }
-          else           { acc[i][2] += v[j]; acc[i][3] = fmaf(v[j], v[j], acc[i][3]); }
-        }
-      }
-    }
+  // ---- phase 0: per-(n, group) sum / sum of squares (MODE 0 only; the barrier-free form runs
+  //      gn_stats_kernel): this CTA's rows = whole units (rows_per_cta is a multiple of 4) ----
+  {
+    const int ur = gn_unit_rows(nchunks);
+    float4* wpart = reinterpret_cast<float4*>(stash) + warp * nchunks;   // stash not needed yet
+    const GnPair pr[2] = {gn_pair(lane, cpg, G), gn_pair(lane + 32, cpg, G)};
+    for (int i = threadIdx.x; i < kFqWarps * kGnSlots * 64; i += kFqThreads) s_fx0[i] = 0ull;
+    __syncthreads();
+    long long fx[2] = {0, 0};
+    for (int r0 = row0 + warp * ur; r0 < row1; r0 += kFqWarps * ur)
+      gn_unit_stats_any(ximg, ldx, r0, min(row1, r0 + ur), nchunks, cpg, wpart, lane, pr, fx);
+    gn_flush_stats(ws, s_fx0, n, n, G, warp, lane, fx);
+    __syncthreads();
+    gn_publish_slots(ws, s_fx0, n, NB, G, kFqWarps);
   }
-  // fixed-order (deterministic) reduction inside the CTA, using the not-yet-needed stash as
-  // scratch: lanes publish their chunk partials [warp][chunk] -> one thread per chunk sums the
-  // warps -> one thread per (group, quantity) sums the chunks that overlap the group.
-  float4* part = reinterpret_cast<float4*>(stash);          // [kFqWarps][nchunks]
-#pragma unroll
-  for (int i = 0; i < kGnMaxChunks; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nchunks) part[warp * nchunks + c] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < nchunks; c += kFqThreads) {
-    float4 t = part[c];
-#pragma unroll
-    for (int w = 1; w < kFqWarps; ++w) {
-      const float4 u = part[w * nchunks + c];
-      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
-    }
-    part[c] = t;     // only this thread touches column c
-  }
-  __syncthreads();
-  if (threadIdx.x < 2 * G) {
-    const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
-    const int c_lo = (g * cpg) >> 3, c_hi = ((g + 1) * cpg - 1) >> 3;
-    float t = 0.f;
-    for (int c = c_lo; c <= c_hi; ++c) {
-      const float4 u = part[c];
-      const int g0 = (8 * c) / cpg;
-      if (g0 == g) t += k ? u.y : u.x;
-      else if (g0 + 1 == g) t += k ? u.w : u.z;
-    }
-    const long long fixed = __double2ll_rn(static_cast<double>(t) * (k ? kFixSq : kFixSum));
-    atomicAdd(&ws->gsum[(n * G) * 2 + threadIdx.x], static_cast<unsigned long long>(fixed));
-  }
-  if (MODE == 1) { __syncthreads(); continue; }   // statistics kernel: the kernel boundary is the barrier
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -491,7 +620,7 @@ gn_quant_kernel(const __half* __restrict__ x, int64_t ldx, int NB, int HW, int C
       qrow[c] = qdiff_vec8(y, delta, z);
     }
   }
-  }  // virtual blocks (one iteration except for MODE 1)
+  }
 }
 
 template <typename K>
@@ -703,7 +832,8 @@ static int gn_entry(const mixdq_half_t* x, int64_t ldx, int NB, int HW, int C, i
   static bool attr = false;
   if (!attr) {
     if (set_smem(gn_quant_kernel<true, 0>, kFqMaxSmem) || set_smem(gn_quant_kernel<false, 0>, kFqMaxSmem) ||
-        set_smem(gn_quant_kernel<true, 1>, kFqMaxSmem) || set_smem(gn_quant_kernel<false, 1>, kFqMaxSmem) ||
+        set_smem(gn_stats_kernel<2, 4>, kFqMaxSmem) || set_smem(gn_stats_kernel<5, 2>, kFqMaxSmem) ||
+        set_smem(gn_stats_kernel<kGnMaxChunks, 1>, kFqMaxSmem) ||
         set_smem(gn_quant_kernel<true, 2>, kFqMaxSmem) || set_smem(gn_quant_kernel<false, 2>, kFqMaxSmem))
       return MIXDQ_ERR_CUDA;
     attr = true;
@@ -716,34 +846,37 @@ static int gn_entry(const mixdq_half_t* x, int64_t ldx, int NB, int HW, int C, i
   if (cpi > max_useful) cpi = max_useful;
   if (cpi < 1) cpi = 1;
   int rpc = (HW + cpi - 1) / cpi;
+  rpc = (rpc + 3) / 4 * 4;                     // whole statistics units (4 / 2 / 1 rows) per CTA
   cpi = (HW + rpc - 1) / rpc;
   int64_t srows = kFqMaxSmem / (static_cast<int64_t>(C) * 2);
   if (srows > rpc) srows = rpc;
   int smem = static_cast<int>(srows * C * 2);
-  const int scratch = kFqWarps * (C / 8) * 16;   // phase-0 partials [warps][chunks] float4
+  const int scratch = kFqWarps * (C / 8) * 16;   // statistics partials [warps][chunks] float4
   if (smem < scratch) smem = scratch;
   if (three_kernels) {
-    // statistics kernel -> apply kernel (fp16 y + min/max) -> single-pass quantiser. No CTA waits
-    // for another one, so the grids need not be co-resident: the same row split is kept because
-    // the statistics kernel's deterministic in-CTA reduction is written for it.
-    auto k1 = silu ? gn_quant_kernel<true, 1> : gn_quant_kernel<false, 1>;
+    // statistics kernel -> apply kernel (fp16 y + min/max, or int8) -> single-pass quantiser. No
+    // CTA waits for another one, so the grids need not be co-resident.
     auto k2 = silu ? gn_quant_kernel<true, 2> : gn_quant_kernel<false, 2>;
     const __half* xh = reinterpret_cast<const __half*>(x);
     const __half* gh = reinterpret_cast<const __half*>(gamma);
     const __half* bh = reinterpret_cast<const __half*>(beta);
     __half* yh = reinterpret_cast<__half*>(y_out);
     DynWs* w = static_cast<DynWs*>(ws);
-    // statistics: every image is cut into the SAME row ranges whatever the batch is (the batch-1
-    // split: one block per SM), walked as virtual blocks by a resident grid — an image's
-    // statistics, hence the whole static-scale UNet, are invariant under batch sharding
-    // (mixdq_b200/dp.py; a per-batch split changed the fp32 partial sums in the last bits)
-    int cpi1 = kNumSm < max_useful ? kNumSm : max_useful;
-    const int rpc1 = (HW + cpi1 - 1) / cpi1;
-    cpi1 = (HW + rpc1 - 1) / rpc1;
-    const int g1 = NB * cpi1 < NB * cpi ? NB * cpi1 : NB * cpi;
-    if (launch_pdl(k1, g1, kFqThreads, scratch, st, xh, ldx, NB, HW, C, G, gh, bh, eps, q, yh,
-                   w, scale_out, zp_out, cpi1, rpc1, 0, static_cast<int8_t*>(nullptr), static_cast<const float*>(nullptr),
-                   static_cast<const float*>(nullptr)) != cudaSuccess)
+    // statistics: one warp per unit, contiguous unit ranges per warp (<= a full GPU of warps),
+    // the warps spread over as many CTAs as there are SMs
+    const int ur = gn_unit_rows(C / 8);
+    const long long units = static_cast<long long>(NB) * ((HW + ur - 1) / ur);
+    long long warps = static_cast<long long>(kNumSm) * kFqWarps;
+    if (warps > units) warps = units;
+    const int upw = static_cast<int>((units + warps - 1) / warps);
+    warps = (units + upw - 1) / upw;
+    int g1 = warps < kNumSm ? static_cast<int>(warps) : kNumSm;
+    const int wpc = static_cast<int>((warps + g1 - 1) / g1);          // <= kFqWarps
+    g1 = static_cast<int>((warps + wpc - 1) / wpc);
+    auto k1 = (C / 8 <= 64) ? gn_stats_kernel<2, 4>
+              : (C / 8 <= 160) ? gn_stats_kernel<5, 2> : gn_stats_kernel<kGnMaxChunks, 1>;
+    if (launch_pdl(k1, g1, 32 * wpc, wpc * (C / 8) * 16, st, xh, ldx, NB, HW, C, G, w, upw) !=
+        cudaSuccess)
       return MIXDQ_ERR_CUDA;
     if (launch_pdl(k2, NB * cpi, kFqThreads, 0, st, xh, ldx, NB, HW, C, G, gh, bh, eps, q, yh, w,
                    scale_out, zp_out, cpi, rpc, 0, qs, s_inv, s_zp) != cudaSuccess)

@@ -158,6 +158,14 @@ bool persist_halo_ok(int bn, bool w4, int cs, int R, int S, int pad, int stride,
          boxN == 1 && (boxW % 8) == 0 && (boxH + 2) * boxW <= 2 * BLOCK_M;
 }
 
+// HALO convolutions win from 4 m-tiles on (tools/tune_persist.py conv3x3, batch 1..8: 9.9 vs 11.9 us
+// at M=4096 N=320, 15.0 vs 41.8 us at M=4096 N=640, 24.3 vs 72.0 us at M=2048 N=1280 K=11520; the
+// M=256 layers stay on the one-tile split-K kernel, 13.9 vs 22.6 us)
+bool persist_halo_wanted(int m_tiles) {
+  read_env();
+  return g_persist_mode == 2 || (g_persist_mode == 1 && m_tiles >= 4);
+}
+
 int persist_launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmD,
                              TcParams p, cudaStream_t st) {
   return launch<160, 3, KIND_CONV, false, 2, true>(tmA, tmW, tmD, p, st);

@@ -26,6 +26,7 @@ int persist_launch(int kind, int bn, bool w4, int cs, const CUtensorMap& tmA,
 void persist_set_halo(int on);      // test / tuning hook
 bool persist_halo_ok(int bn, bool w4, int cs, int R, int S, int pad, int stride, int boxW, int boxH,
                      int boxN);
+bool persist_halo_wanted(int m_tiles);   // problem large enough for the HALO form (its own threshold)
 int persist_launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmD,
                              TcParams p, cudaStream_t st);
 

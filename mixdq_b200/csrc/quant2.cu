@@ -279,7 +279,10 @@ quant_rows_premm_kernel(const __half* __restrict__ x, int64_t ldx, unsigned int 
 // CTAs), 8 warps and a row loop (<= 512 CTAs = partials) for larger M.
 // PyTorch: statistics in fp32, biased variance (same restatement as fused_quant.cu::ln_row).
 // ---------------------------------------------------------------------------------------------
-template <int MAXCH, int NT>
+// ROWS independent rows per warp and loop iteration: ROWS x MAXCH sixteen-byte loads in flight per
+// lane (narrow rows — C = 320: 40 chunks, 1.25 per lane — left the big-batch launches at
+// ~2.7 TB/s with one row at a time). Rows never interact, so the results do not depend on ROWS.
+template <int MAXCH, int NT, int ROWS = 1>
 __global__ void __launch_bounds__(NT)
 ln_minmax_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
                  const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps,
@@ -315,20 +318,29 @@ ln_minmax_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
   pdl_wait();
   dbg.waited(ws);
   __half2 mn = __float2half2_rn(0.0f), mx = mn;
+  const int rstep = gridDim.x * (NT / 32);
 #pragma unroll 1
-  for (int r = blockIdx.x * (NT / 32) + warp; r < M; r += gridDim.x * (NT / 32)) {
-    const int4* xrow = reinterpret_cast<const int4*>(x + static_cast<int64_t>(r) * ldx);
-    int4 raw[MAXCH];
+  for (int rb = blockIdx.x * (NT / 32) + warp; rb < M; rb += ROWS * rstep) {
+    int4 raw[ROWS][MAXCH];
 #pragma unroll
-    for (int i = 0; i < MAXCH; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunks) raw[i] = __ldcg(xrow + c);
+    for (int u = 0; u < ROWS; ++u) {
+      const int r = rb + u * rstep;
+      const int4* xrow = reinterpret_cast<const int4*>(x + static_cast<int64_t>(r) * ldx);
+#pragma unroll
+      for (int i = 0; i < MAXCH; ++i) {
+        const int c = lane + 32 * i;
+        if (r < M && c < nchunks) raw[u][i] = __ldcg(xrow + c);
+      }
     }
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+    const int r = rb + u * rstep;
+    if (r >= M) break;                       // warp-uniform
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXCH; ++i) {
       if (lane + 32 * i < nchunks) {
-        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[i]);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[u][i]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = __half22float2(h2[j]);
@@ -344,7 +356,7 @@ ln_minmax_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
 #pragma unroll
     for (int i = 0; i < MAXCH; ++i) {
       if (lane + 32 * i < nchunks) {
-        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[i]);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[u][i]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = __half22float2(h2[j]);
@@ -362,7 +374,7 @@ ln_minmax_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
     for (int i = 0; i < MAXCH; ++i) {
       const int c = lane + 32 * i;
       if (c < nchunks) {
-        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[i]);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[u][i]);
         const __half2* g2 = reinterpret_cast<const __half2*>(&gr[i]);
         const __half2* b2 = reinterpret_cast<const __half2*>(&br[i]);
         int4 out;
@@ -382,6 +394,7 @@ ln_minmax_kernel(const __half* __restrict__ x, int64_t ldx, int M, int C,
           yrow[c] = out;
         }
       }
+    }
     }
   }
   dbg.stamp(2);
@@ -503,7 +516,14 @@ int mixdq_q2_ln(const __half* x, int64_t ldx, int M, int C, const __half* gamma,
   } else {
     g1 = (M + 7) / 8;
     if (g1 > 512) g1 = 512;
-    e = (C <= 5 * 256)
+    // several rows in flight per warp once every warp has more than one row to walk
+    const bool multi = M >= 2 * 512 * 8;
+    if (multi && C <= 2 * 256)
+      e = launch_pdl(ln_minmax_kernel<2, 256, 4>, g1, 256, 0, st, x, ldx, M, C, gamma, beta, eps, y, w, qs, s_inv, s_zp);
+    else if (multi && C <= 3 * 256)
+      e = launch_pdl(ln_minmax_kernel<3, 256, 2>, g1, 256, 0, st, x, ldx, M, C, gamma, beta, eps, y, w, qs, s_inv, s_zp);
+    else
+      e = (C <= 5 * 256)
             ? launch_pdl(ln_minmax_kernel<5, 256>, g1, 256, 0, st, x, ldx, M, C, gamma, beta, eps, y, w, qs, s_inv, s_zp)
             : launch_pdl(ln_minmax_kernel<8, 256>, g1, 256, 0, st, x, ldx, M, C, gamma, beta, eps, y, w, qs, s_inv, s_zp);
   }

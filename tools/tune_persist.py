@@ -1,6 +1,7 @@
 """Per shape: one-tile-per-CTA kernel vs the persistent kernel at every tile width (CTA pairs),
 same harness as the config-5 sweep (tools/layer_sweep.time_shape). Feeds the tile heuristic of
-csrc/persist.cu::persist_pick_bn.   python tools/tune_persist.py [batches, default 1,8]"""
+csrc/persist.cu::persist_pick_bn.   python tools/tune_persist.py [batches, default 1,8] [kind prefix]
+(3x3 / stride 1 convolutions at width 160 run the HALO form unless MIXDQ_CONV_HALO=0)"""
 import sys
 from pathlib import Path
 import torch
@@ -11,9 +12,10 @@ from tools import layer_sweep as LS
 dev = torch.device("cuda:0")
 lib = _lib.load()
 batches = [int(b) for b in (sys.argv[1] if len(sys.argv) > 1 else "1,8").split(",")]
+only = sys.argv[2] if len(sys.argv) > 2 else ""        # kind prefix filter, e.g. conv3x3
 for batch in batches:
     for kind, M, N, K, count in LS.APPENDIX_A:
-        if M * batch < 256 or N < 64 or K % 16:
+        if M * batch < 256 or N < 64 or K % 16 or not kind.startswith(only):
             continue
         res = {}
         for tag, mode, bn in (("tile", 0, 0), ("p128", 2, 128), ("p160", 2, 160), ("p256", 2, 256)):
