@@ -176,6 +176,106 @@ simt_conv_kernel(SimtConvArgs c) {
   c.y[static_cast<int64_t>(pix) * c.K + k] = __float2half_rn(f);
 }
 
+// Four input channels (conv_in of both UNets: C = 4, 3x3, pad 1, stride 1): a pixel's channels are
+// ONE 32-bit word, a tap of one output channel is one dp4a. A thread computes 8 consecutive output
+// channels of kC4Px consecutive pixels of a row: the 3 x (kC4Px + 2) input words it needs are
+// broadcast loads, the 9 x 8 weight words and border sums come from a [tap][k] copy in shared
+// memory (two conflict-free LDS.128 per tap, reused for all its pixels), results leave as 16-byte
+// stores. Same integers, same fp32 border-sum order (valid taps, r then s ascending) and the same
+// epilogue as simt_conv_kernel, which spent 2 ms per batch-64 launch on this layer (one thread per
+// output with two scalar loads per tap) against ~30 us of output traffic.
+constexpr int kC4Px = 4;
+__global__ void __launch_bounds__(256)
+simt_conv_c4_kernel(SimtConvArgs c, int kgroups, int slots) {
+  extern __shared__ int c4_smem[];
+  int* s_w = c4_smem;                                              // [9][K] packed 4-channel words
+  float* s_ws = reinterpret_cast<float*>(c4_smem + 9 * c.K);       // [9][K] border sums
+  for (int i = threadIdx.x; i < 9 * c.K; i += blockDim.x) {
+    const int tap = i / c.K, k = i - tap * c.K;
+    s_w[i] = __ldg(reinterpret_cast<const int*>(c.w) + k * 9 + tap);
+    s_ws[i] = __ldg(c.wsum_krs + k * 9 + tap);
+  }
+  __syncthreads();
+  const int kg = threadIdx.x % kgroups, slot = threadIdx.x / kgroups;
+  if (slot >= slots) return;
+  const int qgroups = (c.Q + kC4Px - 1) / kC4Px;
+  const long long items = static_cast<long long>(c.N) * c.P * qgroups;
+  // the grid is capped at a few CTAs per SM: the 9 x K weight words are staged once per CTA
+  for (long long item = static_cast<long long>(blockIdx.x) * slots + slot; item < items;
+       item += static_cast<long long>(gridDim.x) * slots) {   // (n, p, q-group)
+  const int qg = static_cast<int>(item % qgroups);
+  const int p = static_cast<int>((item / qgroups) % c.P);
+  const int n = static_cast<int>(item / (static_cast<long long>(qgroups) * c.P));
+  const int q0 = qg * kC4Px, k0 = kg * 8;
+  const int* x32 = reinterpret_cast<const int*>(c.x) + static_cast<int64_t>(n) * c.H * c.W;
+  int xin[3][kC4Px + 2];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int h = p - 1 + r;
+#pragma unroll
+    for (int j = 0; j < kC4Px + 2; ++j) {
+      const int w = q0 - 1 + j;
+      xin[r][j] = (h >= 0 && h < c.H && w >= 0 && w < c.W) ? __ldg(x32 + h * c.W + w) : 0;
+    }
+  }
+  int acc[kC4Px][8];
+  float wacc[kC4Px][8];
+#pragma unroll
+  for (int i = 0; i < kC4Px; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[i][j] = 0; wacc[i][j] = 0.f; }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const bool hv = (p - 1 + r) >= 0 && (p - 1 + r) < c.H;
+#pragma unroll
+    for (int s2 = 0; s2 < 3; ++s2) {
+      const int tap = r * 3 + s2;
+      const int4 w0 = *reinterpret_cast<const int4*>(s_w + tap * c.K + k0);
+      const int4 w1 = *reinterpret_cast<const int4*>(s_w + tap * c.K + k0 + 4);
+      const float4 f0 = *reinterpret_cast<const float4*>(s_ws + tap * c.K + k0);
+      const float4 f1 = *reinterpret_cast<const float4*>(s_ws + tap * c.K + k0 + 4);
+      const int wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+      for (int i = 0; i < kC4Px; ++i) {
+        const int w = q0 + i - 1 + s2;
+        const bool valid = hv && w >= 0 && w < c.W;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[i][j] = __dp4a(xin[r][i + s2], wv[j], acc[i][j]);
+          if (valid) wacc[i][j] = __fadd_rn(wacc[i][j], fv[j]);
+        }
+      }
+    }
+  }
+  const float zp = __ldg(c.zp);
+  float sc[8], bs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(c.scale + k0 + j);
+    bs[j] = c.bias ? __half2float(c.bias[k0 + j]) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < kC4Px; ++i) {
+    const int q = q0 + i;
+    if (q >= c.Q) break;
+    const int64_t pix = (static_cast<int64_t>(n) * c.P + p) * c.Q + q;
+    __align__(16) __half o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float f = dequant_f32(acc[i][j], __fmul_rn(wacc[i][j], zp), sc[j]);
+      if (c.bias) f = __fadd_rn(f, bs[j]);
+      o[j] = __float2half_rn(f);
+    }
+    if (c.acc_out) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) c.acc_out[pix * c.K + k0 + j] = acc[i][j];
+    }
+    *reinterpret_cast<uint4*>(c.y + pix * c.K + k0) = *reinterpret_cast<const uint4*>(o);
+  }
+  }
+}
+
 int simt_gemm_launch(const SimtGemmArgs& g, cudaStream_t st) {
   dim3 grid((g.M + 7) / 8, (g.N + 31) / 32);
   if (grid.y > 65535) return -1;
@@ -189,6 +289,18 @@ int simt_conv_launch(const SimtConvArgs& c, cudaStream_t st) {
   if (grid.y > 65535 || npix > 2147483647LL) return -1;
   const bool v16 = (c.C % 16 == 0) && (c.x_cpitch % 16 == 0) &&
                    ((reinterpret_cast<uintptr_t>(c.x) | reinterpret_cast<uintptr_t>(c.w)) & 15) == 0;
+  const bool c4 = c.C == 4 && c.x_cpitch == 4 && c.R == 3 && c.S == 3 && c.stride == 1 && c.pad == 1 &&
+                  c.wsum_krs != nullptr && c.K % 8 == 0 && c.K / 8 <= 256 && c.K <= 1024 &&
+                  ((reinterpret_cast<uintptr_t>(c.x) | reinterpret_cast<uintptr_t>(c.w)) & 3) == 0 &&
+                  (reinterpret_cast<uintptr_t>(c.y) & 15) == 0;
+  if (c4) {
+    const int kgroups = c.K / 8, slots = 256 / kgroups;
+    const long long items = static_cast<long long>(c.N) * c.P * ((c.Q + kC4Px - 1) / kC4Px);
+    long long blocks = (items + slots - 1) / slots;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    simt_conv_c4_kernel<<<static_cast<unsigned>(blocks), 256, 9 * c.K * 8, st>>>(c, kgroups, slots);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
   if (c.K <= 8 && v16)
     simt_conv_smallk_kernel<<<dim3(grid.x), 256, 0, st>>>(c);
   else

@@ -27,7 +27,7 @@ for line in sass.splitlines():
         m = pat.search(line)
         if m:
             counts[cur][m.group(1)] += 1
-        if re.search(r"/\*[0-9a-f]{4}\*/", line):
+        if re.search(r"/\*[0-9a-f]{4,}\*/\s+[A-Z@]", line):
             counts[cur]["_instr"] += 1
 print(f"# {lib}  sha256 {hashlib.sha256(lib.read_bytes()).hexdigest()[:16]}  (cuobjdump -sass, sm_100a)")
 print("# instructions | mnemonic counts")
