@@ -223,11 +223,17 @@ extern "C" void mixdq_debug_force_bn(int bn) { g_force_bn = bn; }
 extern "C" void mixdq_debug_force_splits(int s) { g_force_splits = s; }
 // MIXDQ_A_PREFETCH=1 enables an L2 prefetch of the first A tile before the dependency wait.
 // Measured neutral on B200 (7.878 vs 7.872 ms per batch-1 step), hence off by default.
+// weight k-blocks beyond the ring -> L2 before the dependency wait: same-box A/B, twice each:
+// batch 1 7.3437 / 7.3435 -> 7.3267 / 7.3283 ms/step, batch 8 16.827 / 16.828 -> 16.840 / 16.839
+constexpr bool kWPrefetchDefault = true;
 static int g_a_prefetch = -1;
 static int a_prefetch_flag() {
   if (g_a_prefetch < 0) {
     const char* e = getenv("MIXDQ_A_PREFETCH");
     g_a_prefetch = (e && e[0] == '1') ? 1 : 0;
+    // bit 1: weight k-blocks beyond the ring are L2-prefetched before the dependency wait
+    const char* w = getenv("MIXDQ_W_PREFETCH");
+    if (w ? (w[0] != '0') : kWPrefetchDefault) g_a_prefetch |= 2;
   }
   return g_a_prefetch;
 }

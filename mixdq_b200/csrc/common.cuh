@@ -155,6 +155,12 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, in
                "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2,
                                                 int c3) {
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(

@@ -110,7 +110,8 @@ struct TcParams {
   int32_t* ws;            // split-K exchange workspace: [CTA][BN/4][128][4] int32 (splits > 1)
   unsigned long long* dbg; // optional phase timestamps (globaltimer ns), 8 slots per CTA
   int dbg_mode;            // profiling only: bit0 = skip MMA issue, bit1 = skip TMA loads
-  int a_prefetch;          // 1: L2-prefetch the first A tile before the dependency wait
+  int a_prefetch;          // bit 0: L2-prefetch the first A tile before the dependency wait;
+                           // bit 1: L2-prefetch the weight k-blocks the ring cannot hold
 };
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -355,8 +356,28 @@ tc_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           else mbar_expect_tx(&full_bar[i], ns * (a_bytes + L::W_SUB));
           for (int u = 0; u < ns; ++u) load_w(kb_begin + i * L::KSUB + u, i, u);
         }
+        // WEIGHT k-blocks beyond the ring: pull them from HBM into L2 now, while the preceding
+        // (short) kernel still runs — inside the UNet graph every weight byte is cold, and the
+        // k-blocks the ring cannot hold would otherwise start their HBM trip only when a slot
+        // frees up after the dependency wait (ff.net.2: 32 of its 40 k-blocks)
+        if (p.a_prefetch & 2) {
+          for (int si = npre; si < nst; ++si) {
+            const int ns = nsub_of(si);
+            for (int u = 0; u < ns; ++u) {
+              const int kb = kb_begin + si * L::KSUB + u;
+              if (KIND == KIND_CONV) {
+                const int tap = kb / p.kb_per_tap;
+                tma_prefetch_3d(&tmW, (kb - tap * p.kb_per_tap) * WK, tap, n_tile0);
+              } else if (KIND == KIND_SPLIT && kb >= p.num_kb) {
+                tma_prefetch_2d(&tmW1, (kb - p.num_kb) * WK, n_tile0);
+              } else {
+                tma_prefetch_2d(&tmW, kb * WK, n_tile0);
+              }
+            }
+          }
+        }
         // warm the path of the first A tile (L2 prefetch: its contents are not consumed)
-        if (p.a_prefetch) {
+        if (p.a_prefetch & 1) {
           const int kb = kb_begin;
           if (KIND == KIND_CONV) {
             const int tap = kb / p.kb_per_tap;
