@@ -79,67 +79,90 @@ simt_gemm_kernel(SimtGemmArgs g) {
 
 // Few output channels (SDXL conv_out: K = 4, C = 320): one WARP per output pixel, the lanes split
 // the (tap, 16-channel chunk) items of the reduction and shuffle-add their INT32 partials (exact,
-// order-independent); lane k < K finishes channel k with the same epilogue as below. The
-// one-thread-per-(pixel, channel) kernel left 28 of 32 lanes idle there (35 us per launch).
+// order-independent); lane k < K finishes channel k with the same epilogue as below. The weights
+// (K x R x S x C bytes, <= 46 KB) are staged in shared memory once per CTA and the CTAs walk the
+// pixels with a grid stride: the first form fetched K sixteen-byte weight vectors per item from
+// global memory (448 us per batch-64 launch for 2 MB of output). KMAX = 4 halves the shuffles.
+template <int KMAX>
 __global__ void __launch_bounds__(256)
 simt_conv_smallk_kernel(SimtConvArgs c) {
-  const int lane = threadIdx.x & 31;
-  const unsigned int pix = blockIdx.x * 8u + (threadIdx.x >> 5);
-  const unsigned int npix = static_cast<unsigned int>(c.N) * c.P * c.Q;
-  if (pix >= npix) return;
-  const int q = pix % c.Q;
-  const int p = (pix / c.Q) % c.P;
-  const int n = pix / (static_cast<unsigned int>(c.Q) * c.P);
-  const int h0 = p * c.stride - c.pad, w0 = q * c.stride - c.pad;
+  extern __shared__ int4 sk_w[];                       // [K][R*S][C/16]
   const int chunks = c.C >> 4;
-  const int items = c.R * c.S * chunks;
-  int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int it = lane; it < items; it += 32) {
-    const int tap = it / chunks, ch = it - tap * chunks;
-    const int r = tap / c.S, s = tap - r * c.S;
-    const int h = h0 + r, w = w0 + s;
-    if (h < 0 || h >= c.H || w < 0 || w >= c.W) continue;
-    const int4 x = __ldg(reinterpret_cast<const int4*>(
-                             c.x + ((static_cast<int64_t>(n) * c.H + h) * c.W + w) * c.x_cpitch) + ch);
+  const int taps = c.R * c.S;
+  const int items = taps * chunks;
+  for (int i = threadIdx.x; i < c.K * items; i += blockDim.x)
+    sk_w[i] = __ldg(reinterpret_cast<const int4*>(c.w) + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned int npix = static_cast<unsigned int>(c.N) * c.P * c.Q;
+  for (unsigned int pix = blockIdx.x * 8u + (threadIdx.x >> 5); pix < npix; pix += gridDim.x * 8u) {
+    const int q = pix % c.Q;
+    const int p = (pix / c.Q) % c.P;
+    const int n = pix / (static_cast<unsigned int>(c.Q) * c.P);
+    const int h0 = p * c.stride - c.pad, w0 = q * c.stride - c.pad;
+    int acc[KMAX];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (k < c.K) {
-        const int4 y = __ldg(reinterpret_cast<const int4*>(
-                                 c.w + ((static_cast<int64_t>(k) * c.R + r) * c.S + s) * c.C) + ch);
-        acc[k] = __dp4a(x.x, y.x, acc[k]);
-        acc[k] = __dp4a(x.y, y.y, acc[k]);
-        acc[k] = __dp4a(x.z, y.z, acc[k]);
-        acc[k] = __dp4a(x.w, y.w, acc[k]);
+    for (int k = 0; k < KMAX; ++k) acc[k] = 0;
+    // three items per lane and round: their activation loads are in flight together
+    constexpr int UI = 3;
+    for (int it0 = lane; it0 < items; it0 += 32 * UI) {
+      int4 x[UI];
+      bool ok[UI];
+#pragma unroll
+      for (int u = 0; u < UI; ++u) {
+        const int it = it0 + 32 * u;
+        const int tap = it / chunks, ch = it - tap * chunks;
+        const int r = tap / c.S, s = tap - r * c.S;
+        const int h = h0 + r, w = w0 + s;
+        ok[u] = it < items && h >= 0 && h < c.H && w >= 0 && w < c.W;
+        if (ok[u])
+          x[u] = __ldg(reinterpret_cast<const int4*>(
+                           c.x + ((static_cast<int64_t>(n) * c.H + h) * c.W + w) * c.x_cpitch) + ch);
+      }
+#pragma unroll
+      for (int u = 0; u < UI; ++u) {
+        if (!ok[u]) continue;
+        const int it = it0 + 32 * u;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          if (k < c.K) {
+            const int4 y = sk_w[k * items + it];
+            acc[k] = __dp4a(x[u].x, y.x, acc[k]);
+            acc[k] = __dp4a(x[u].y, y.y, acc[k]);
+            acc[k] = __dp4a(x[u].z, y.z, acc[k]);
+            acc[k] = __dp4a(x[u].w, y.w, acc[k]);
+          }
+        }
       }
     }
-  }
-  int mine = 0;
+    int mine = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    int v = acc[k];
+    for (int k = 0; k < KMAX; ++k) {
+      int v = acc[k];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == k) mine = v;
-  }
-  if (lane >= c.K) return;
-  const int k = lane;
-  float wacc = 0.f;
-  if (c.wsum_krs) {
-    for (int r = 0; r < c.R; ++r) {
-      const int h = h0 + r;
-      if (h < 0 || h >= c.H) continue;
-      for (int s = 0; s < c.S; ++s) {
-        const int w = w0 + s;
-        if (w < 0 || w >= c.W) continue;
-        wacc = __fadd_rn(wacc, __ldg(c.wsum_krs + (static_cast<int64_t>(k) * c.R + r) * c.S + s));
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == k) mine = v;
+    }
+    if (lane >= c.K) continue;
+    const int k = lane;
+    float wacc = 0.f;
+    if (c.wsum_krs) {
+      for (int r = 0; r < c.R; ++r) {
+        const int h = h0 + r;
+        if (h < 0 || h >= c.H) continue;
+        for (int s = 0; s < c.S; ++s) {
+          const int w = w0 + s;
+          if (w < 0 || w >= c.W) continue;
+          wacc = __fadd_rn(wacc, __ldg(c.wsum_krs + (static_cast<int64_t>(k) * c.R + r) * c.S + s));
+        }
       }
     }
+    if (c.acc_out) c.acc_out[static_cast<int64_t>(pix) * c.K + k] = mine;
+    const float b0 = c.wsum_krs ? __fmul_rn(wacc, __ldg(c.zp)) : __ldg(c.bias0_k + k);
+    float f = dequant_f32(mine, b0, __ldg(c.scale + k));
+    if (c.bias) f = __fadd_rn(f, __half2float(c.bias[k]));
+    c.y[static_cast<int64_t>(pix) * c.K + k] = __float2half_rn(f);
   }
-  if (c.acc_out) c.acc_out[static_cast<int64_t>(pix) * c.K + k] = mine;
-  const float b0 = c.wsum_krs ? __fmul_rn(wacc, __ldg(c.zp)) : __ldg(c.bias0_k + k);
-  float f = dequant_f32(mine, b0, __ldg(c.scale + k));
-  if (c.bias) f = __fadd_rn(f, __half2float(c.bias[k]));
-  c.y[static_cast<int64_t>(pix) * c.K + k] = __float2half_rn(f);
 }
 
 __global__ void __launch_bounds__(256)
@@ -301,9 +324,12 @@ int simt_conv_launch(const SimtConvArgs& c, cudaStream_t st) {
     simt_conv_c4_kernel<<<static_cast<unsigned>(blocks), 256, 9 * c.K * 8, st>>>(c, kgroups, slots);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   }
-  if (c.K <= 8 && v16)
-    simt_conv_smallk_kernel<<<dim3(grid.x), 256, 0, st>>>(c);
-  else
+  const size_t wbytes = static_cast<size_t>(c.K) * c.R * c.S * c.C;
+  if (c.K <= 8 && v16 && wbytes <= 46 * 1024) {
+    unsigned int blocks = grid.x < 148u * 8u ? grid.x : 148u * 8u;
+    if (c.K <= 4) simt_conv_smallk_kernel<4><<<blocks, 256, wbytes, st>>>(c);
+    else simt_conv_smallk_kernel<8><<<blocks, 256, wbytes, st>>>(c);
+  } else
     simt_conv_kernel<<<grid, 256, 0, st>>>(c);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
