@@ -454,6 +454,7 @@ def test_qconv2d_tcgen05_bit_exact(ops, dev, n, h, w, c, k, r, s, pad, stride):
 @pytest.mark.parametrize("n,h,w,c,k,r,s,pad,stride", [
     (1, 64, 64, 4, 320, 3, 3, 1, 1), (1, 64, 64, 320, 4, 3, 3, 1, 1),       # conv_in / conv_out
     (3, 9, 13, 4, 64, 3, 3, 1, 1), (2, 5, 3, 4, 2048, 3, 3, 1, 1), (2, 6, 6, 4, 24, 3, 3, 1, 1),   # 4-channel kernel: ragged q groups, K groups
+    (2, 9, 9, 64, 8, 3, 3, 1, 1), (3, 10, 7, 48, 8, 3, 3, 1, 2), (2, 8, 8, 1280, 8, 3, 3, 1, 1),   # few output channels: K = 8 form, weights beyond the shared-memory budget
     (1, 9, 9, 32, 32, 5, 5, 2, 1)])
 def test_qconv2d_other_geometries_bit_exact(ops, dev, n, h, w, c, k, r, s, pad, stride):
     _conv_case(ops, dev, n, h, w, c, k, r, s, pad, stride)
