@@ -48,7 +48,13 @@ int persist_pick_bn(int m_tiles, int N, int num_kb, int kind) {
   const int sms = num_sms();
   // (M = 256 problems: the batch-1 GEGLU projection measured 9.9 us persistent vs 9.3 us one-tile
   // inside the UNet graph although it wins in isolation)
-  if (g_persist_mode == 1 && (m_tiles < 4 || static_cast<long>(m_tiles) * ((N + 127) / 128) < 120))
+  // (one m-tile and >= ~4 waves of weight tiles — SDXL's hoisted cross-attention K / V projection,
+  // M = 77, N = 166 400, K = 2048, 341 MB of weights — is a pure weight stream: persistent single
+  // CTAs walk contiguous tile ranges without the wave tail, 87 -> 63 us = 3.9 -> 5.4 TB/s,
+  // tools/kv_gemm_bench.py)
+  const long tiles128 = static_cast<long>(m_tiles) * ((N + 127) / 128);
+  const bool weight_stream = m_tiles == 1 && tiles128 >= 600;
+  if (g_persist_mode == 1 && !weight_stream && (m_tiles < 4 || tiles128 < 120))
     return 0;
   const int cands[3] = {256, 160, 128};
   const double t_kb[3] = {0.38, 0.31, 0.29};
