@@ -36,7 +36,9 @@ def test_no_torch_or_python_dependency():
     import subprocess
     from mixdq_b200 import _lib
     out = subprocess.run(["ldd", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
-    assert "torch" not in out and "python" not in out and "c10" not in out
+    # library names only: the load addresses ldd prints are random hex and may contain "c10"
+    names = [line.split()[0] for line in out.splitlines() if line.strip()]
+    assert not any(("torch" in n) or ("python" in n) or ("c10" in n) for n in names), names
 
 
 def test_version_and_strerror(lib):
